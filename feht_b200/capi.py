@@ -1,0 +1,333 @@
+"""ctypes binding of libfeht_cuda.so (include/feht_cuda.h) -- the Python test/bench harness.
+
+This is a thin 1:1 wrapper: every method is one C-ABI call with numpy host buffers.  There is no
+Python or CPU fallback: if the shared library is missing or no B200 is visible the import of the
+library / `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "libfeht_cuda.so"
+
+OK = 0
+CORRECTION_NONE, CORRECTION_BONFERRONI = 0, 1
+SORT_ABS_RATIO_DESC, SORT_PVALUE_ASC = 0, 1
+ENGINE_AUTO, ENGINE_POPC, ENGINE_GEMM = 0, 1, 2
+E_INVALID, E_CUDA, E_BOUNDS, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5
+
+# every symbol include/feht_cuda.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "feht_create", "feht_destroy", "feht_last_error", "feht_set_stream", "feht_version",
+    "feht_set_samples", "feht_reserve_rows", "feht_clear_rows", "feht_add_rows_chars",
+    "feht_add_rows_packed", "feht_add_snp_packed", "feht_add_snp_chars", "feht_generate_synthetic",
+    "feht_read_plane", "feht_row_stride_words", "feht_num_rows", "feht_add_comparison",
+    "feht_add_category", "feht_clear_comparisons", "feht_num_comparisons", "feht_comparison_info",
+    "feht_set_count_engine", "feht_run", "feht_result_count", "feht_result_total",
+    "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
+    "feht_choose_table", "feht_eval_tables",
+]
+
+
+class FehtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"feht error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class SynthSpec(C.Structure):
+    """feht_synth_spec (include/feht_cuda.h) == fo_synth_spec (oracle/feht_oracle.h)."""
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("n_samples", C.c_int64),
+        ("missing_thr", C.c_uint32),
+        ("planted_per_million", C.c_uint32),
+        ("split_col", C.c_int64),
+        ("thr_hi", C.c_uint32),
+        ("thr_lo", C.c_uint32),
+        ("freq_thr", C.c_uint32 * 256),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libfeht_cuda.so; loud failure when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m feht_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(str(_LIB_PATH))
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    L.feht_create.argtypes = [P(vp), C.c_int]
+    L.feht_create.restype = C.c_int
+    L.feht_destroy.argtypes = [vp]
+    L.feht_destroy.restype = None
+    L.feht_last_error.argtypes = [vp]
+    L.feht_last_error.restype = C.c_char_p
+    L.feht_set_stream.argtypes = [vp, vp]
+    L.feht_version.argtypes = []
+    L.feht_version.restype = C.c_char_p
+    L.feht_set_samples.argtypes = [vp, i64]
+    L.feht_reserve_rows.argtypes = [vp, i64]
+    L.feht_clear_rows.argtypes = [vp]
+    L.feht_add_rows_chars.argtypes = [vp, vp, vp, i64, vp]
+    L.feht_add_snp_chars.argtypes = [vp, vp, vp, i64, vp]
+    L.feht_add_rows_packed.argtypes = [vp, vp, vp, i64, i64, vp]
+    L.feht_add_snp_packed.argtypes = [vp, vp, vp, vp, i64, i64, vp]
+    L.feht_generate_synthetic.argtypes = [vp, P(SynthSpec), C.c_int, i64, i64]
+    L.feht_read_plane.argtypes = [vp, C.c_int, i64, i64, vp]
+    L.feht_row_stride_words.argtypes = [vp]
+    L.feht_row_stride_words.restype = i64
+    L.feht_num_rows.argtypes = [vp]
+    L.feht_num_rows.restype = i64
+    L.feht_add_comparison.argtypes = [vp, vp, i64, vp, i64]
+    L.feht_add_comparison.restype = i64
+    L.feht_add_category.argtypes = [vp, vp, i32]
+    L.feht_add_category.restype = i64
+    L.feht_clear_comparisons.argtypes = [vp]
+    L.feht_num_comparisons.argtypes = [vp]
+    L.feht_num_comparisons.restype = i64
+    L.feht_comparison_info.argtypes = [vp, i64, P(i32), P(i32), P(i32), P(i32)]
+    L.feht_set_count_engine.argtypes = [vp, C.c_int]
+    L.feht_run.argtypes = [vp, C.c_int, f64, C.c_int, i64]
+    L.feht_result_count.argtypes = [vp, i64]
+    L.feht_result_count.restype = i64
+    L.feht_result_total.argtypes = [vp]
+    L.feht_result_total.restype = i64
+    L.feht_result_fetch.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.feht_set_row_base.argtypes = [vp, i64]
+    L.feht_last_timings.argtypes = [vp, P(f64), C.c_int]
+    L.feht_merge_sorted.argtypes = [C.c_int, P(i64), P(vp), P(vp), C.c_int, vp, vp]
+    L.feht_choose_table.argtypes = [vp, i64]
+    L.feht_choose_table.restype = i64
+    L.feht_eval_tables.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def version() -> str:
+    return lib().feht_version().decode()
+
+
+def choose_table() -> np.ndarray:
+    n = lib().feht_choose_table(None, 0)
+    out = np.empty(n, dtype=np.float64)
+    lib().feht_choose_table(_ptr(out), n)
+    return out
+
+
+def merge_sorted(keys, ranks, sort_key=SORT_ABS_RATIO_DESC):
+    """Host k-way merge of sorted shards -> (shard, index) arrays in merged order."""
+    n_shards = len(keys)
+    keys = [np.ascontiguousarray(k, dtype=np.float64) for k in keys]
+    ranks = [np.ascontiguousarray(r, dtype=np.int32) for r in ranks]
+    n = (C.c_int64 * max(n_shards, 1))(*[len(k) for k in keys])
+    kp = (C.c_void_p * max(n_shards, 1))(*[k.ctypes.data for k in keys])
+    rp = (C.c_void_p * max(n_shards, 1))(*[r.ctypes.data for r in ranks])
+    total = int(sum(len(k) for k in keys))
+    out_s = np.empty(total, dtype=np.int32)
+    out_i = np.empty(total, dtype=np.int64)
+    rc = lib().feht_merge_sorted(n_shards, n, kp, rp, sort_key, _ptr(out_s), _ptr(out_i))
+    if rc != OK:
+        raise FehtError(rc, "feht_merge_sorted")
+    return out_s, out_i
+
+
+class Context:
+    """One feht_ctx = one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.feht_create(C.byref(h), device)
+        if rc != OK:
+            raise FehtError(rc, self._L.feht_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.feht_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc < 0:
+            raise FehtError(int(rc), self._L.feht_last_error(self._h).decode())
+        return rc
+
+    # ---- data
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._L.feht_set_stream(self._h, cuda_stream_ptr))
+
+    def set_samples(self, n: int):
+        self._check(self._L.feht_set_samples(self._h, n))
+
+    def reserve_rows(self, n: int):
+        self._check(self._L.feht_reserve_rows(self._h, n))
+
+    def clear_rows(self):
+        self._check(self._L.feht_clear_rows(self._h))
+
+    @staticmethod
+    def _rows_to_flat(rows):
+        """list of bytes rows (or a 2-D uint8 array) -> (flat uint8, int64 offsets)."""
+        if isinstance(rows, np.ndarray) and rows.ndim == 2:
+            flat = np.ascontiguousarray(rows, dtype=np.uint8).reshape(-1)
+            off = np.arange(rows.shape[0] + 1, dtype=np.int64) * rows.shape[1]
+            return flat, off
+        lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
+        off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        flat = np.frombuffer(b"".join(bytes(r) for r in rows), dtype=np.uint8)
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=np.uint8)
+        return np.ascontiguousarray(flat), off
+
+    def add_rows_chars(self, rows, name_rank=None):
+        flat, off = self._rows_to_flat(rows)
+        nr = _i32(name_rank)
+        self._check(self._L.feht_add_rows_chars(self._h, _ptr(flat), _ptr(off), len(off) - 1, _ptr(nr)))
+
+    def add_rows_chars_raw(self, flat_ptr: int, off_ptr: int, n_rows: int, name_rank_ptr: int | None = None):
+        """Pointers straight through (bench: pinned torch buffers)."""
+        self._check(self._L.feht_add_rows_chars(self._h, flat_ptr, off_ptr, n_rows, name_rank_ptr))
+
+    def add_snp_chars(self, rows, name_rank=None):
+        flat, off = self._rows_to_flat(rows)
+        nr = _i32(name_rank)
+        self._check(self._L.feht_add_snp_chars(self._h, _ptr(flat), _ptr(off), len(off) - 1, _ptr(nr)))
+
+    def add_rows_packed(self, value, valid, name_rank=None):
+        value = np.ascontiguousarray(value, dtype=np.uint64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint64)
+        assert value.shape == valid.shape and value.ndim == 2
+        nr = _i32(name_rank)
+        self._check(self._L.feht_add_rows_packed(self._h, _ptr(value), _ptr(valid), value.shape[0],
+                                                 value.shape[1], _ptr(nr)))
+
+    def add_rows_packed_raw(self, value_ptr: int, valid_ptr: int, n_rows: int, stride_words: int):
+        self._check(self._L.feht_add_rows_packed(self._h, value_ptr, valid_ptr, n_rows, stride_words, None))
+
+    def add_snp_packed(self, hi, lo, valid, name_rank=None):
+        hi = np.ascontiguousarray(hi, dtype=np.uint64)
+        lo = np.ascontiguousarray(lo, dtype=np.uint64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint64)
+        nr = _i32(name_rank)
+        self._check(self._L.feht_add_snp_packed(self._h, _ptr(hi), _ptr(lo), _ptr(valid), hi.shape[0],
+                                                hi.shape[1], _ptr(nr)))
+
+    def generate_synthetic(self, spec: SynthSpec, snp_mode: bool, first_row: int, n_rows: int):
+        self._check(self._L.feht_generate_synthetic(self._h, C.byref(spec), int(snp_mode), first_row, n_rows))
+
+    def read_plane(self, plane: int, row0: int, n: int) -> np.ndarray:
+        w = self.row_stride_words
+        out = np.empty((n, w), dtype=np.uint64)
+        self._check(self._L.feht_read_plane(self._h, plane, row0, n, _ptr(out)))
+        return out
+
+    @property
+    def row_stride_words(self) -> int:
+        return int(self._L.feht_row_stride_words(self._h))
+
+    @property
+    def num_rows(self) -> int:
+        return int(self._L.feht_num_rows(self._h))
+
+    # ---- comparisons
+    def add_comparison(self, g1_cols, g2_cols) -> int:
+        g1, g2 = _i32(g1_cols), _i32(g2_cols)
+        return int(self._check(self._L.feht_add_comparison(self._h, _ptr(g1), len(g1), _ptr(g2), len(g2))))
+
+    def add_category(self, value_of_sample, n_values: int) -> int:
+        v = _i32(value_of_sample)
+        return int(self._check(self._L.feht_add_category(self._h, _ptr(v), n_values)))
+
+    def clear_comparisons(self):
+        self._check(self._L.feht_clear_comparisons(self._h))
+
+    @property
+    def num_comparisons(self) -> int:
+        return int(self._L.feht_num_comparisons(self._h))
+
+    def comparison_info(self, c: int):
+        k, cat, v1, v2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._L.feht_comparison_info(self._h, c, C.byref(k), C.byref(cat), C.byref(v1), C.byref(v2)))
+        return k.value, cat.value, v1.value, v2.value
+
+    def set_count_engine(self, engine: int):
+        self._check(self._L.feht_set_count_engine(self._h, engine))
+
+    def set_row_base(self, base: int):
+        self._check(self._L.feht_set_row_base(self._h, base))
+
+    # ---- run
+    def run(self, correction=CORRECTION_BONFERRONI, ratio_filter=0.0, sort_key=SORT_ABS_RATIO_DESC,
+            bonferroni_n=0):
+        self._check(self._L.feht_run(self._h, correction, float(ratio_filter), sort_key, bonferroni_n))
+
+    def result_count(self, c: int) -> int:
+        return int(self._check(self._L.feht_result_count(self._h, c)))
+
+    def result_total(self) -> int:
+        return int(self._check(self._L.feht_result_total(self._h)))
+
+    def fetch(self, c: int) -> dict:
+        n = self.result_count(c)
+        out = {
+            "row": np.empty(n, np.int64), "goa": np.empty(n, np.int32), "gob": np.empty(n, np.int32),
+            "gta": np.empty(n, np.int32), "gtb": np.empty(n, np.int32), "p": np.empty(n, np.float64),
+            "ratio": np.empty(n, np.float64), "name_rank": np.empty(n, np.int32),
+        }
+        self._check(self._L.feht_result_fetch(self._h, c, _ptr(out["row"]), _ptr(out["goa"]), _ptr(out["gob"]),
+                                              _ptr(out["gta"]), _ptr(out["gtb"]), _ptr(out["p"]),
+                                              _ptr(out["ratio"]), _ptr(out["name_rank"])))
+        return out
+
+    def fetch_raw(self, c: int, ptrs: dict):
+        """ptrs: name -> host address (pinned buffers owned by the caller)."""
+        g = ptrs.get
+        self._check(self._L.feht_result_fetch(self._h, c, g("row"), g("goa"), g("gob"), g("gta"), g("gtb"),
+                                              g("p"), g("ratio"), g("name_rank")))
+
+    def timings(self) -> dict:
+        buf = (C.c_double * 7)()
+        self._check(self._L.feht_last_timings(self._h, buf, 7))
+        keys = ["count_ms", "test_ms", "order_ms", "total_ms", "launches", "count_launches", "count_bytes"]
+        return dict(zip(keys, list(buf)))
+
+    def eval_tables(self, goa, gob, gta, gtb):
+        a, b, c_, d = _i32(goa), _i32(gob), _i32(gta), _i32(gtb)
+        n = len(a)
+        p = np.empty(n, np.float64)
+        r = np.empty(n, np.float64)
+        self._check(self._L.feht_eval_tables(self._h, _ptr(a), _ptr(b), _ptr(c_), _ptr(d), n, _ptr(p), _ptr(r)))
+        return p, r

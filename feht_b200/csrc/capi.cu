@@ -1,0 +1,885 @@
+// capi.cu -- the C ABI of libfeht_cuda.so (include/feht_cuda.h): context, uploads, run, fetch.
+//
+// The run replaces app/Main.hs:26-29 of the reference: generateResultMap (Comparison.hs:86-111),
+// applyMultipleTestingCorrection (:238-264) and the filter + ordering half of
+// formatComparisonResultsAsTable (:139-162).  Everything heavy happens in the kernels
+// (pack.cu K0, count_popc.cu K1, count_gemm.cu K2, fet.cu K3, sort.cu K4); this file owns device
+// memory, turns column lists / categories into bit masks and slot descriptors, sequences the
+// launches on one stream and times the stages with CUDA events.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <queue>
+
+#include "common.cuh"
+
+using namespace feht;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Comp {
+    int kind = 0;      // 0 explicit, 1 pair, 2 one-vs-rest
+    int cat = -1;
+    int v1 = -1, v2 = -1;
+    std::vector<int32_t> g1, g2;  // explicit only
+    int64_t max_col = -1;
+};
+
+struct Cat {
+    std::vector<int32_t> value_of_sample;
+    int n_values = 0;
+    int64_t max_col = -1;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+};
+
+}  // namespace
+
+struct feht_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, st = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    std::string err;
+
+    int64_t S = 0, W = 0;
+    int snp = -1;  // -1 no rows yet, 0 binary, 1 snp
+    int64_t n_units = 0, cap_units = 0;  // rows (binary) or sites (snp)
+    uint64_t *plane[3] = {nullptr, nullptr, nullptr};  // value|hi, valid, lo
+    DevBuf<int32_t> rank;
+    int have_rank = -1;  // -1 unknown, 0 none, 1 given
+    int64_t min_row_len = std::numeric_limits<int64_t>::max();
+    int64_t row_base = 0;
+
+    std::vector<Comp> comps;
+    std::vector<Cat> cats;
+    int engine = FEHT_ENGINE_AUTO;
+
+    double *d_choose = nullptr;
+    DevBuf<unsigned char> stage[2];
+
+    // scratch for a run
+    DevBuf<uint4> masks;
+    DevBuf<int4> counts;
+    DevBuf<CompDesc> descs;
+    DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
+    DevBuf<long long> seg_base;
+    DevBuf<int32_t> r_comp, r_row, r_rank, o_row, o_rank;
+    DevBuf<int4> r_cnt, o_cnt;
+    DevBuf<double> r_p, r_ratio, o_p, o_ratio;
+    SortWorkspace sw;
+    DevBuf<uint32_t> sw_perm_a, sw_perm_b, sw_hist, sw_k0, sw_k1, sw_k2, sw_k3, sw_oa;
+
+    bool has_results = false;
+    int64_t n_surv = 0;
+    std::vector<int64_t> seg_off;
+    Timings tm;
+};
+
+namespace {
+
+int fail(feht_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(c, expr)                                                                                \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail((c), FEHT_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                 \
+    } while (0)
+
+template <class T>
+cudaError_t ensure(DevBuf<T> &b, size_t n) {
+    if (n <= b.cap && b.p) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&b.p, n * sizeof(T));
+    if (e == cudaSuccess) b.cap = n;
+    return e;
+}
+
+template <class T>
+void release(DevBuf<T> &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int use_device(feht_ctx *c) {
+    CU(c, cudaSetDevice(c->device));
+    return FEHT_OK;
+}
+
+// grow the planes (and rank) to hold `need` units, keeping the contents
+int grow_rows(feht_ctx *c, int64_t need, int n_planes) {
+    if (need <= c->cap_units) {
+        bool all = true;
+        for (int i = 0; i < n_planes; ++i) all = all && c->plane[i];
+        if (all) return FEHT_OK;
+    }
+    int64_t cap = std::max<int64_t>(need, c->cap_units + c->cap_units / 2);
+    if (cap < 1) cap = 1;
+    const size_t words = size_t(cap) * size_t(c->W);
+    for (int i = 0; i < n_planes; ++i) {
+        uint64_t *np = nullptr;
+        CU(c, cudaMalloc(&np, words * 8));
+        if (c->plane[i] && c->n_units > 0)
+            CU(c, cudaMemcpyAsync(np, c->plane[i], size_t(c->n_units) * c->W * 8,
+                                  cudaMemcpyDeviceToDevice, c->st));
+        if (c->plane[i]) {
+            CU(c, cudaStreamSynchronize(c->st));
+            cudaFree(c->plane[i]);
+        }
+        c->plane[i] = np;
+    }
+    c->cap_units = cap;
+    return FEHT_OK;
+}
+
+int append_rank(feht_ctx *c, const int32_t *name_rank, int64_t n_marker_rows, int64_t first_marker) {
+    const int given = name_rank ? 1 : 0;
+    if (c->have_rank == -1) c->have_rank = given;
+    if (c->have_rank != given)
+        return fail(c, FEHT_E_INVALID, "name_rank must be given for all rows or for none");
+    if (!given) return FEHT_OK;
+    const size_t need = size_t(first_marker + n_marker_rows);
+    if (need > c->rank.cap) {
+        DevBuf<int32_t> nb;
+        CU(c, ensure(nb, std::max(need, c->rank.cap + c->rank.cap / 2)));
+        if (c->rank.p && first_marker > 0)
+            CU(c, cudaMemcpyAsync(nb.p, c->rank.p, size_t(first_marker) * 4, cudaMemcpyDeviceToDevice, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+        release(c->rank);
+        c->rank = nb;
+    }
+    CU(c, cudaMemcpyAsync(c->rank.p + first_marker, name_rank, size_t(n_marker_rows) * 4,
+                          cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    return FEHT_OK;
+}
+
+int64_t marker_rows(const feht_ctx *c) { return c->snp == 1 ? 4 * c->n_units : c->n_units; }
+
+int check_mode(feht_ctx *c, int snp) {
+    if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
+    if (c->snp == -1) c->snp = snp;
+    if (c->snp != snp)
+        return fail(c, FEHT_E_INVALID, "a context holds either binary rows or SNP sites, not both");
+    return FEHT_OK;
+}
+
+constexpr size_t kStageBytes = size_t(96) << 20;
+
+// Upload `total` bytes from host in pieces chosen by `next_piece` and hand each staged piece to
+// `consume(dev_ptr, piece_index)` on the context stream; two staging buffers so that the copy of
+// piece i+1 overlaps the kernel on piece i.
+template <class Next, class Consume>
+int staged_upload(feht_ctx *c, Next next_piece, Consume consume) {
+    for (int b = 0; b < 2; ++b) CU(c, ensure(c->stage[b], kStageBytes));
+    int i = 0;
+    for (;; ++i) {
+        const int b = i & 1;
+        const void *src = nullptr;
+        size_t bytes = 0;
+        if (!next_piece(i, &src, &bytes)) break;
+        if (bytes > kStageBytes) return fail(c, FEHT_E_INVALID, "internal: staging piece too large");
+        if (i >= 2) CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_used[b], 0));
+        if (bytes)
+            CU(c, cudaMemcpyAsync(c->stage[b].p, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->st, c->ev_copied[b], 0));
+        int rc = consume(c->stage[b].p, i);
+        if (rc) return rc;
+        CU(c, cudaEventRecord(c->ev_used[b], c->st));
+    }
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, cudaStreamSynchronize(c->st));
+    return FEHT_OK;
+}
+
+int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offsets, int64_t n,
+                     const int32_t *name_rank, int snp) {
+    if (!c) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    if (int rc = check_mode(c, snp)) return rc;
+    if (n < 0 || (n > 0 && (!chars || !row_offsets))) return fail(c, FEHT_E_INVALID, "null rows");
+    if (n == 0) return FEHT_OK;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t len = row_offsets[r + 1] - row_offsets[r];
+        if (len < 0) return fail(c, FEHT_E_INVALID, "row_offsets must be non-decreasing");
+        c->min_row_len = std::min(c->min_row_len, len);
+    }
+    const int n_planes = snp ? 3 : 2;
+    if (int rc = grow_rows(c, c->n_units + n, n_planes)) return rc;
+    const int mult = snp ? 4 : 1;
+    if (int rc = append_rank(c, name_rank, n * mult, c->n_units * mult)) return rc;
+
+    // pieces = runs of whole rows whose chars + offsets fit a staging buffer
+    std::vector<int64_t> piece_first;
+    {
+        int64_t r = 0;
+        while (r < n) {
+            piece_first.push_back(r);
+            size_t bytes = 0;
+            int64_t q = r;
+            while (q < n) {
+                const size_t add = size_t(row_offsets[q + 1] - row_offsets[q]) + 8;
+                if (add + 64 > kStageBytes)
+                    return fail(c, FEHT_E_INVALID, "a single row exceeds the staging buffer");
+                if (bytes + add + 64 > kStageBytes) break;
+                bytes += add;
+                ++q;
+            }
+            r = q;
+        }
+        piece_first.push_back(n);
+    }
+    // Layout of a staged piece: [offsets (rows+1) x int64, rebased to 0][chars...]
+    std::vector<std::vector<int64_t>> rebased(2);
+    const int64_t first_unit = c->n_units;
+    auto next_piece = [&](int i, const void **src, size_t *bytes) -> bool {
+        if (size_t(i) + 1 >= piece_first.size()) return false;
+        *src = nullptr;
+        *bytes = 0;  // copies are issued by consume (two regions)
+        return true;
+    };
+    auto consume = [&](unsigned char *dev, int i) -> int {
+        const int64_t r0 = piece_first[i], r1 = piece_first[i + 1];
+        const int64_t rows = r1 - r0;
+        std::vector<int64_t> &off = rebased[i & 1];
+        off.resize(size_t(rows) + 1);
+        for (int64_t r = 0; r <= rows; ++r) off[size_t(r)] = row_offsets[r0 + r] - row_offsets[r0];
+        const size_t off_bytes = (size_t(rows) + 1) * 8;
+        const size_t off_pad = (off_bytes + 63) & ~size_t(63);
+        const size_t char_bytes = size_t(row_offsets[r1] - row_offsets[r0]);
+        CU(c, cudaMemcpyAsync(dev, off.data(), off_bytes, cudaMemcpyHostToDevice, c->st));
+        if (char_bytes)
+            CU(c, cudaMemcpyAsync(dev + off_pad, chars + row_offsets[r0], char_bytes,
+                                  cudaMemcpyHostToDevice, c->st));
+        const int64_t u0 = first_unit + r0;
+        if (snp)
+            CU(c, launch_pack_snp_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows,
+                                        c->S, c->W, c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W,
+                                        c->plane[2] + u0 * c->W, c->st));
+        else
+            CU(c, launch_pack_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S,
+                                    c->W, c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->st));
+        // `off` is reused two pieces later: the copy above must have consumed it by then
+        CU(c, cudaStreamSynchronize(c->st));
+        return FEHT_OK;
+    };
+    if (int rc = staged_upload(c, next_piece, consume)) return rc;
+    c->n_units += n;
+    c->has_results = false;
+    return FEHT_OK;
+}
+
+int add_packed_common(feht_ctx *c, const uint64_t *const *src_planes, const int *dst_index,
+                      int n_planes, int64_t n, int64_t stride, const int32_t *name_rank, int snp) {
+    if (!c) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    if (int rc = check_mode(c, snp)) return rc;
+    const int64_t need_words = (c->S + 63) / 64;
+    if (n < 0 || stride < need_words) return fail(c, FEHT_E_INVALID, "row_stride_words < ceil(S/64)");
+    if (n == 0) return FEHT_OK;
+    for (int i = 0; i < n_planes; ++i)
+        if (!src_planes[i]) return fail(c, FEHT_E_INVALID, "null plane");
+    if (int rc = grow_rows(c, c->n_units + n, n_planes)) return rc;
+    const int mult = snp ? 4 : 1;
+    if (int rc = append_rank(c, name_rank, n * mult, c->n_units * mult)) return rc;
+    c->min_row_len = std::min(c->min_row_len, c->S);
+
+    const int64_t rows_per_piece = std::max<int64_t>(1, int64_t(kStageBytes / (size_t(stride) * 8)));
+    if (size_t(stride) * 8 > kStageBytes) return fail(c, FEHT_E_INVALID, "row too long for staging");
+    const int64_t pieces_per_plane = (n + rows_per_piece - 1) / rows_per_piece;
+    const int64_t first_unit = c->n_units;
+    // plane order: valid first so that value can be ANDed with it (binary mode)
+    auto next_piece = [&](int i, const void **src, size_t *bytes) -> bool {
+        const int64_t pl = i / pieces_per_plane, pc = i % pieces_per_plane;
+        if (pl >= n_planes) return false;
+        const int64_t r0 = pc * rows_per_piece, r1 = std::min(n, r0 + rows_per_piece);
+        *src = src_planes[pl] + r0 * stride;
+        *bytes = size_t(r1 - r0) * size_t(stride) * 8;
+        return true;
+    };
+    auto consume = [&](unsigned char *dev, int i) -> int {
+        const int64_t pl = i / pieces_per_plane, pc = i % pieces_per_plane;
+        const int64_t r0 = pc * rows_per_piece, r1 = std::min(n, r0 + rows_per_piece);
+        uint64_t *dst = c->plane[dst_index[pl]] + (first_unit + r0) * c->W;
+        const uint64_t *and_with = nullptr;
+        if (!snp && dst_index[pl] == 0) and_with = c->plane[1] + (first_unit + r0) * c->W;
+        CU(c, launch_repack_rows(reinterpret_cast<const uint64_t *>(dev), stride, dst, c->W, c->S,
+                                 r1 - r0, and_with, c->st));
+        return FEHT_OK;
+    };
+    if (int rc = staged_upload(c, next_piece, consume)) return rc;
+    c->n_units += n;
+    c->has_results = false;
+    return FEHT_OK;
+}
+
+}  // namespace
+
+// =================================================================================== context ==
+extern "C" const char *feht_version(void) { return "feht_b200 0.1 (sm_100a; K0 pack, K1 popc, K3 fet, K4 sort)"; }
+
+extern "C" int feht_create(feht_ctx **out, int device) {
+    if (!out) return fail(nullptr, FEHT_E_INVALID, "out is null");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, FEHT_E_NODEVICE, "no CUDA device (%s); libfeht_cuda has no CPU fallback",
+                    e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(nullptr, FEHT_E_INVALID, "device %d of %d", device, n_dev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, FEHT_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, FEHT_E_NODEVICE,
+                    "device %d is sm_%d%d; libfeht_cuda is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    feht_ctx *c = new (std::nothrow) feht_ctx();
+    if (!c) return fail(nullptr, FEHT_E_NOMEM, "out of host memory");
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    auto bail = [&](const char *what, cudaError_t err) {
+        fail(nullptr, FEHT_E_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        feht_destroy(c);
+        return FEHT_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    c->st = c->own_stream;
+    for (int i = 0; i < 4; ++i)
+        if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail("event", e);
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+        if ((e = cudaEventCreateWithFlags(&c->ev_used[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    }
+    const std::vector<double> &tab = host_choose_table();
+    if ((e = cudaMalloc(&c->d_choose, tab.size() * 8)) != cudaSuccess) return bail("cudaMalloc(choose)", e);
+    if ((e = cudaMemcpy(c->d_choose, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail("cudaMemcpy(choose)", e);
+    *out = c;
+    return FEHT_OK;
+}
+
+extern "C" void feht_destroy(feht_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (int i = 0; i < 3; ++i) if (c->plane[i]) cudaFree(c->plane[i]);
+    release(c->rank); release(c->stage[0]); release(c->stage[1]);
+    release(c->masks); release(c->counts); release(c->descs); release(c->seg_count); release(c->seg_base);
+    release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
+    release(c->r_cnt); release(c->o_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
+    release(c->sw_perm_a); release(c->sw_perm_b); release(c->sw_hist);
+    release(c->sw_k0); release(c->sw_k1); release(c->sw_k2); release(c->sw_k3); release(c->sw_oa);
+    if (c->d_choose) cudaFree(c->d_choose);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_used[i]) cudaEventDestroy(c->ev_used[i]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+extern "C" const char *feht_last_error(const feht_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int feht_set_stream(feht_ctx *c, void *cuda_stream) {
+    if (!c) return FEHT_E_INVALID;
+    c->st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return FEHT_OK;
+}
+
+// ============================================================================== data matrix ==
+extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
+    if (!c) return FEHT_E_INVALID;
+    if (n_samples <= 0 || n_samples > (int64_t(1) << 24))
+        return fail(c, FEHT_E_INVALID, "n_samples must be in [1, 2^24]");
+    if (int rc = use_device(c)) return rc;
+    CU(c, cudaStreamSynchronize(c->st));
+    for (int i = 0; i < 3; ++i) { if (c->plane[i]) cudaFree(c->plane[i]); c->plane[i] = nullptr; }
+    c->S = n_samples;
+    c->W = ((n_samples + 63) / 64 + 1) & ~int64_t(1);  // even number of 64-bit words: 16-byte rows
+    c->snp = -1;
+    c->n_units = c->cap_units = 0;
+    c->have_rank = -1;
+    c->min_row_len = std::numeric_limits<int64_t>::max();
+    c->has_results = false;
+    return FEHT_OK;
+}
+
+extern "C" int feht_reserve_rows(feht_ctx *c, int64_t n_rows) {
+    if (!c) return FEHT_E_INVALID;
+    if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
+    if (int rc = use_device(c)) return rc;
+    // planes are allocated lazily per mode; remember the wish
+    if (c->snp == -1) { c->cap_units = 0; }
+    const int n_planes = c->snp == 1 ? 3 : 2;
+    if (c->snp == -1) {
+        // allocate the two planes every mode needs; the SNP lo plane follows on first use
+        return grow_rows(c, n_rows, 2);
+    }
+    return grow_rows(c, n_rows, n_planes);
+}
+
+extern "C" int feht_clear_rows(feht_ctx *c) {
+    if (!c) return FEHT_E_INVALID;
+    c->n_units = 0;
+    c->snp = -1;
+    c->have_rank = -1;
+    c->min_row_len = std::numeric_limits<int64_t>::max();
+    c->has_results = false;
+    return FEHT_OK;
+}
+
+extern "C" int feht_add_rows_chars(feht_ctx *c, const uint8_t *chars, const int64_t *row_offsets,
+                                   int64_t n_rows, const int32_t *name_rank) {
+    return add_chars_common(c, chars, row_offsets, n_rows, name_rank, 0);
+}
+
+extern "C" int feht_add_snp_chars(feht_ctx *c, const uint8_t *chars, const int64_t *row_offsets,
+                                  int64_t n_sites, const int32_t *name_rank) {
+    return add_chars_common(c, chars, row_offsets, n_sites, name_rank, 1);
+}
+
+extern "C" int feht_add_rows_packed(feht_ctx *c, const uint64_t *value_plane, const uint64_t *valid_plane,
+                                    int64_t n_rows, int64_t row_stride_words, const int32_t *name_rank) {
+    const uint64_t *src[2] = {valid_plane, value_plane};
+    const int dst[2] = {1, 0};
+    return add_packed_common(c, src, dst, 2, n_rows, row_stride_words, name_rank, 0);
+}
+
+extern "C" int feht_add_snp_packed(feht_ctx *c, const uint64_t *hi_plane, const uint64_t *lo_plane,
+                                   const uint64_t *valid_plane, int64_t n_sites, int64_t row_stride_words,
+                                   const int32_t *name_rank) {
+    const uint64_t *src[3] = {valid_plane, hi_plane, lo_plane};
+    const int dst[3] = {1, 0, 2};
+    return add_packed_common(c, src, dst, 3, n_sites, row_stride_words, name_rank, 1);
+}
+
+extern "C" int feht_generate_synthetic(feht_ctx *c, const feht_synth_spec *spec, int snp_mode,
+                                       int64_t first_row, int64_t n_rows) {
+    if (!c || !spec) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    if (int rc = check_mode(c, snp_mode ? 1 : 0)) return rc;
+    if (spec->n_samples != c->S) return fail(c, FEHT_E_INVALID, "spec.n_samples != feht_set_samples");
+    if (n_rows < 0) return fail(c, FEHT_E_INVALID, "n_rows < 0");
+    if (c->have_rank == 1) return fail(c, FEHT_E_INVALID, "synthetic rows carry no name_rank");
+    c->have_rank = 0;
+    if (int rc = grow_rows(c, c->n_units + n_rows, snp_mode ? 3 : 2)) return rc;
+    feht_synth_spec *d_spec = nullptr;
+    CU(c, cudaMalloc(&d_spec, sizeof(feht_synth_spec)));
+    CU(c, cudaMemcpyAsync(d_spec, spec, sizeof(feht_synth_spec), cudaMemcpyHostToDevice, c->st));
+    const int64_t u0 = c->n_units;
+    cudaError_t e = launch_synth(d_spec, snp_mode ? 1 : 0, first_row, n_rows, c->S, c->W,
+                                 c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W,
+                                 snp_mode ? c->plane[2] + u0 * c->W : nullptr, c->st);
+    cudaError_t e2 = cudaStreamSynchronize(c->st);
+    cudaFree(d_spec);
+    CU(c, e);
+    CU(c, e2);
+    c->min_row_len = std::min(c->min_row_len, c->S);
+    c->n_units += n_rows;
+    c->has_results = false;
+    return FEHT_OK;
+}
+
+extern "C" int feht_read_plane(feht_ctx *c, int plane, int64_t row0, int64_t n, uint64_t *out) {
+    if (!c || !out) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    if (plane < 0 || plane > 2 || !c->plane[plane] || (plane == 2 && c->snp != 1))
+        return fail(c, FEHT_E_INVALID, "no such plane");
+    if (row0 < 0 || n < 0 || row0 + n > c->n_units) return fail(c, FEHT_E_INVALID, "row range");
+    CU(c, cudaMemcpyAsync(out, c->plane[plane] + row0 * c->W, size_t(n) * c->W * 8, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    return FEHT_OK;
+}
+
+extern "C" int64_t feht_row_stride_words(const feht_ctx *c) { return c ? c->W : 0; }
+extern "C" int64_t feht_num_rows(const feht_ctx *c) { return c ? marker_rows(c) : 0; }
+
+// ============================================================================== comparisons ==
+extern "C" int64_t feht_add_comparison(feht_ctx *c, const int32_t *g1, int64_t n1, const int32_t *g2, int64_t n2) {
+    if (!c) return FEHT_E_INVALID;
+    if (n1 < 0 || n2 < 0 || (n1 && !g1) || (n2 && !g2)) return fail(c, FEHT_E_INVALID, "null group");
+    Comp cp;
+    cp.kind = 0;
+    cp.g1.assign(g1, g1 + n1);
+    cp.g2.assign(g2, g2 + n2);
+    for (int32_t v : cp.g1) { if (v < 0) return fail(c, FEHT_E_BOUNDS, "negative column index"); cp.max_col = std::max<int64_t>(cp.max_col, v); }
+    for (int32_t v : cp.g2) { if (v < 0) return fail(c, FEHT_E_BOUNDS, "negative column index"); cp.max_col = std::max<int64_t>(cp.max_col, v); }
+    c->comps.push_back(std::move(cp));
+    c->has_results = false;
+    return int64_t(c->comps.size()) - 1;
+}
+
+extern "C" int64_t feht_add_category(feht_ctx *c, const int32_t *value_of_sample, int32_t n_values) {
+    if (!c || !value_of_sample) return FEHT_E_INVALID;
+    if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
+    if (n_values < 2) return fail(c, FEHT_E_INVALID, "a category needs at least 2 values");
+    Cat cat;
+    cat.n_values = n_values;
+    cat.value_of_sample.assign(value_of_sample, value_of_sample + c->S);
+    for (int64_t s = 0; s < c->S; ++s) {
+        const int32_t v = cat.value_of_sample[size_t(s)];
+        if (v >= n_values || v < -1) return fail(c, FEHT_E_INVALID, "value_of_sample[%lld] = %d out of range", (long long)s, v);
+        if (v >= 0) cat.max_col = s;
+    }
+    const int ci = int(c->cats.size());
+    c->cats.push_back(std::move(cat));
+    const int64_t first = int64_t(c->comps.size());
+    for (int i = 0; i < n_values; ++i)
+        for (int j = i + 1; j < n_values; ++j) {
+            Comp cp; cp.kind = 1; cp.cat = ci; cp.v1 = i; cp.v2 = j; cp.max_col = c->cats[ci].max_col;
+            c->comps.push_back(std::move(cp));
+        }
+    if (n_values > 2)  // Comparison.hs:329
+        for (int v = 0; v < n_values; ++v) {
+            Comp cp; cp.kind = 2; cp.cat = ci; cp.v1 = v; cp.v2 = -1; cp.max_col = c->cats[ci].max_col;
+            c->comps.push_back(std::move(cp));
+        }
+    c->has_results = false;
+    return first;
+}
+
+extern "C" int feht_clear_comparisons(feht_ctx *c) {
+    if (!c) return FEHT_E_INVALID;
+    c->comps.clear();
+    c->cats.clear();
+    c->has_results = false;
+    return FEHT_OK;
+}
+
+extern "C" int64_t feht_num_comparisons(const feht_ctx *c) { return c ? int64_t(c->comps.size()) : 0; }
+
+extern "C" int feht_comparison_info(const feht_ctx *c, int64_t i, int32_t *kind, int32_t *category, int32_t *v1, int32_t *v2) {
+    if (!c || i < 0 || i >= int64_t(c->comps.size())) return FEHT_E_INVALID;
+    const Comp &cp = c->comps[size_t(i)];
+    if (kind) *kind = cp.kind;
+    if (category) *category = cp.cat;
+    if (v1) *v1 = cp.v1;
+    if (v2) *v2 = cp.v2;
+    return FEHT_OK;
+}
+
+extern "C" int feht_set_count_engine(feht_ctx *c, int engine) {
+    if (!c) return FEHT_E_INVALID;
+    if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM) return fail(c, FEHT_E_INVALID, "unknown engine");
+    c->engine = engine;
+    return FEHT_OK;
+}
+
+extern "C" int feht_set_row_base(feht_ctx *c, int64_t row_base) {
+    if (!c) return FEHT_E_INVALID;
+    c->row_base = row_base;
+    return FEHT_OK;
+}
+
+// ====================================================================================== run ==
+extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
+    if (!c) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    c->has_results = false;
+    if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
+    if (correction != FEHT_CORRECTION_NONE && correction != FEHT_CORRECTION_BONFERRONI)
+        return fail(c, FEHT_E_INVALID, "unknown correction %d", correction);
+    if (sort_key != FEHT_SORT_ABS_RATIO_DESC && sort_key != FEHT_SORT_PVALUE_ASC)
+        return fail(c, FEHT_E_INVALID, "unknown sort key %d", sort_key);
+    if (ratio_filter != ratio_filter) return fail(c, FEHT_E_INVALID, "ratio_filter is NaN");
+    const int n_comps = int(c->comps.size());
+    const int64_t R = marker_rows(c);
+    if (n_comps > 65535) return fail(c, FEHT_E_INVALID, "more than 65535 comparisons in one run");
+    if (R > int64_t(0x7fffffff)) return fail(c, FEHT_E_INVALID, "more than 2^31-1 marker rows in one context");
+    if (bonferroni_n <= 0) bonferroni_n = R;
+    c->seg_off.assign(size_t(n_comps) + 1, 0);
+    c->n_surv = 0;
+    c->tm = Timings();
+    if (n_comps == 0 || R == 0) { c->has_results = true; return FEHT_OK; }
+
+    // V.! bounds (Comparison.hs:123): every referenced column must exist in every row
+    const int64_t row_len = std::min(c->min_row_len, c->S);
+    for (const Comp &cp : c->comps)
+        if (cp.max_col >= row_len)
+            return fail(c, FEHT_E_BOUNDS, "index out of bounds: column %lld referenced, shortest row has %lld characters",
+                        (long long)cp.max_col, (long long)row_len);
+
+    // ---- slots and descriptors
+    const PopcPlan plan = make_popc_plan(c->W);
+    const size_t mrow = size_t(plan.w4pad) * 2;  // 64-bit words per padded mask row
+    std::vector<CompDesc> descs(static_cast<size_t>(n_comps));
+    std::vector<int> cat_slot0(c->cats.size(), -1), cat_tot(c->cats.size(), -1);
+    int n_slots = 0;
+    for (int i = 0; i < n_comps; ++i) if (c->comps[size_t(i)].kind == 0) ++n_slots;
+    const int n_explicit = n_slots;
+    for (size_t k = 0; k < c->cats.size(); ++k) {
+        cat_slot0[k] = n_slots;
+        n_slots += (c->cats[k].n_values + 1) / 2;
+        if (c->cats[k].n_values > 2) cat_tot[k] = n_slots++;
+    }
+    if (size_t(n_slots) * 2 * plan.w4pad * 16 > (size_t(1) << 31))
+        return fail(c, FEHT_E_INVALID, "mask storage too large");
+    std::vector<uint64_t> hmask(size_t(n_slots) * 2 * mrow, 0);
+    auto mask_row = [&](int slot, int which) { return hmask.data() + (size_t(slot) * 2 + which) * mrow; };
+    {
+        int e = 0;
+        for (int i = 0; i < n_comps; ++i) {
+            const Comp &cp = c->comps[size_t(i)];
+            CompDesc d{};
+            d.kind = cp.kind;
+            if (cp.kind == 0) {
+                uint64_t *m1 = mask_row(e, 0), *m2 = mask_row(e, 1);
+                for (int32_t col : cp.g1) m1[col >> 6] |= 1ULL << (col & 63);
+                for (int32_t col : cp.g2) m2[col >> 6] |= 1ULL << (col & 63);
+                d.slot_a = e; d.sel_a = 0; d.slot_b = e; d.sel_b = 1; d.slot_tot = e;
+                ++e;
+            } else {
+                const int s0 = cat_slot0[size_t(cp.cat)];
+                d.slot_a = s0 + cp.v1 / 2; d.sel_a = cp.v1 & 1;
+                if (cp.kind == 1) { d.slot_b = s0 + cp.v2 / 2; d.sel_b = cp.v2 & 1; d.slot_tot = d.slot_a; }
+                else { d.slot_b = d.slot_a; d.sel_b = d.sel_a; d.slot_tot = cat_tot[size_t(cp.cat)]; }
+            }
+            descs[size_t(i)] = d;
+        }
+        (void)n_explicit;
+        for (size_t k = 0; k < c->cats.size(); ++k) {
+            const Cat &cat = c->cats[k];
+            for (int64_t s = 0; s < c->S; ++s) {
+                const int v = cat.value_of_sample[size_t(s)];
+                if (v < 0) continue;
+                mask_row(cat_slot0[k] + v / 2, v & 1)[s >> 6] |= 1ULL << (s & 63);
+                if (cat_tot[k] >= 0) mask_row(cat_tot[k], 0)[s >> 6] |= 1ULL << (s & 63);
+            }
+        }
+    }
+    CU(c, ensure(c->masks, size_t(n_slots) * 2 * plan.w4pad));
+    CU(c, ensure(c->descs, size_t(n_comps)));
+    CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
+    CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
+    CU(c, ensure(c->seg_base, size_t(n_comps)));
+    CU(c, cudaMemcpyAsync(c->masks.p, hmask.data(), hmask.size() * 8, cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->descs.p, descs.data(), descs.size() * sizeof(CompDesc), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
+
+    int launches = 0, count_launches = 0;
+    // ---- K1 count
+    CU(c, cudaEventRecord(c->ev[0], c->st));
+    if (c->snp == 1)
+        CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
+                                    c->masks.p, n_slots, c->counts.p, c->num_sms, c->st, &count_launches));
+    else
+        CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_slots,
+                                c->counts.p, c->num_sms, c->st, &count_launches));
+    launches += count_launches;
+    CU(c, cudaEventRecord(c->ev[1], c->st));
+
+    // ---- K3 test + correct + filter
+    TestParams tp{};
+    tp.counts = c->counts.p;
+    tp.comps = c->descs.p;
+    tp.n_rows = R;
+    tp.n_comps = n_comps;
+    tp.ratio_filter = ratio_filter;
+    tp.correction = correction;
+    tp.bonferroni_n = double(bonferroni_n);
+    tp.choose = c->d_choose;
+    tp.name_rank = c->have_rank == 1 ? c->rank.p : nullptr;
+    tp.dense = ratio_filter <= 0.0 ? 1 : 0;
+    std::vector<long long> base(static_cast<size_t>(n_comps), 0);
+    if (tp.dense) {
+        for (int i = 0; i <= n_comps; ++i) c->seg_off[size_t(i)] = int64_t(i) * R;
+    } else {
+        tp.seg_count = c->seg_count.p;
+        CU(c, launch_test_count(tp, c->st));
+        ++launches;
+        std::vector<unsigned long long> cnt(static_cast<size_t>(n_comps));
+        CU(c, cudaMemcpyAsync(cnt.data(), c->seg_count.p, size_t(n_comps) * 8, cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+        for (int i = 0; i < n_comps; ++i) c->seg_off[size_t(i) + 1] = c->seg_off[size_t(i)] + int64_t(cnt[size_t(i)]);
+        for (int i = 0; i < n_comps; ++i) base[size_t(i)] = c->seg_off[size_t(i)];
+        CU(c, cudaMemcpyAsync(c->seg_base.p, base.data(), size_t(n_comps) * 8, cudaMemcpyHostToDevice, c->st));
+    }
+    const int64_t n = c->seg_off[size_t(n_comps)];
+    if (n > int64_t(0xfffffff0u)) return fail(c, FEHT_E_INVALID, "more than 2^32 surviving rows in one run");
+    c->n_surv = n;
+    const size_t nn = size_t(n);
+    CU(c, ensure(c->r_comp, nn)); CU(c, ensure(c->r_row, nn)); CU(c, ensure(c->r_rank, nn));
+    CU(c, ensure(c->r_cnt, nn)); CU(c, ensure(c->r_p, nn)); CU(c, ensure(c->r_ratio, nn));
+    CU(c, ensure(c->o_row, nn)); CU(c, ensure(c->o_rank, nn)); CU(c, ensure(c->o_cnt, nn));
+    CU(c, ensure(c->o_p, nn)); CU(c, ensure(c->o_ratio, nn));
+    tp.r_comp = c->r_comp.p; tp.r_row = c->r_row.p; tp.r_rank = c->r_rank.p;
+    tp.r_cnt = c->r_cnt.p; tp.r_p = c->r_p.p; tp.r_ratio = c->r_ratio.p;
+    tp.seg_count = c->seg_count.p + n_comps;  // cursors (zeroed above)
+    tp.seg_base = c->seg_base.p;
+    if (n > 0) {
+        CU(c, launch_test_emit(tp, c->st));
+        ++launches;
+    }
+    CU(c, cudaEventRecord(c->ev[2], c->st));
+
+    // ---- K4 order
+    if (n > 0) {
+        const int64_t n_blocks = (n + 2047) / 2048;
+        CU(c, ensure(c->sw_perm_a, nn)); CU(c, ensure(c->sw_perm_b, nn));
+        CU(c, ensure(c->sw_hist, size_t(n_blocks) * 256));
+        CU(c, ensure(c->sw_k0, nn)); CU(c, ensure(c->sw_k1, nn)); CU(c, ensure(c->sw_k2, nn)); CU(c, ensure(c->sw_k3, nn));
+        CU(c, ensure(c->sw_oa, 8));
+        c->sw.perm_a = c->sw_perm_a.p; c->sw.perm_b = c->sw_perm_b.p; c->sw.block_hist = c->sw_hist.p;
+        c->sw.keys[0] = c->sw_k0.p; c->sw.keys[1] = c->sw_k1.p; c->sw.keys[2] = c->sw_k2.p; c->sw.keys[3] = c->sw_k3.p;
+        c->sw.or_and = c->sw_oa.p;
+        CU(c, launch_build_keys(c->r_ratio.p, c->r_p.p, c->r_rank.p, c->r_comp.p, sort_key, n, c->sw, c->st));
+        ++launches;
+        uint32_t *perm = nullptr;
+        CU(c, radix_sort_perm(c->sw, n, c->st, &perm, &launches));
+        CU(c, launch_gather_results(perm, n, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p, c->r_ratio.p,
+                                    c->o_row.p, c->o_rank.p, c->o_cnt.p, c->o_p.p, c->o_ratio.p, c->st));
+        ++launches;
+    }
+    CU(c, cudaEventRecord(c->ev[3], c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->tm.count_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->tm.test_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->tm.order_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[3])); c->tm.total_ms = ms;
+    c->tm.launches = launches;
+    c->tm.count_launches = count_launches;
+    const int n_planes = c->snp == 1 ? 3 : 2;
+    c->tm.count_bytes = double(c->n_units) * double((c->S + 63) / 64) * 8.0 * n_planes;
+    c->has_results = true;
+    return FEHT_OK;
+}
+
+extern "C" int64_t feht_result_count(const feht_ctx *c, int64_t comparison) {
+    if (!c || !c->has_results || comparison < 0 || comparison + 1 >= int64_t(c->seg_off.size())) return FEHT_E_INVALID;
+    return c->seg_off[size_t(comparison) + 1] - c->seg_off[size_t(comparison)];
+}
+
+extern "C" int64_t feht_result_total(const feht_ctx *c) { return (c && c->has_results) ? c->n_surv : FEHT_E_INVALID; }
+
+extern "C" int feht_result_fetch(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob,
+                                 int32_t *gta, int32_t *gtb, double *p, double *ratio, int32_t *name_rank) {
+    if (!c) return FEHT_E_INVALID;
+    if (!c->has_results) return fail(c, FEHT_E_INVALID, "no results: call feht_run first");
+    if (comparison < 0 || comparison + 1 >= int64_t(c->seg_off.size())) return fail(c, FEHT_E_INVALID, "comparison index");
+    if (int rc = use_device(c)) return rc;
+    const int64_t o = c->seg_off[size_t(comparison)];
+    const int64_t n = c->seg_off[size_t(comparison) + 1] - o;
+    if (n == 0) return FEHT_OK;
+    const size_t nn = size_t(n);
+    if (p) CU(c, cudaMemcpyAsync(p, c->o_p.p + o, nn * 8, cudaMemcpyDeviceToHost, c->st));
+    if (ratio) CU(c, cudaMemcpyAsync(ratio, c->o_ratio.p + o, nn * 8, cudaMemcpyDeviceToHost, c->st));
+    if (name_rank) CU(c, cudaMemcpyAsync(name_rank, c->o_rank.p + o, nn * 4, cudaMemcpyDeviceToHost, c->st));
+    std::vector<int32_t> hrow;
+    std::vector<int4> hcnt;
+    if (row) { hrow.resize(nn); CU(c, cudaMemcpyAsync(hrow.data(), c->o_row.p + o, nn * 4, cudaMemcpyDeviceToHost, c->st)); }
+    if (goa || gob || gta || gtb) { hcnt.resize(nn); CU(c, cudaMemcpyAsync(hcnt.data(), c->o_cnt.p + o, nn * 16, cudaMemcpyDeviceToHost, c->st)); }
+    CU(c, cudaStreamSynchronize(c->st));
+    if (row) for (size_t i = 0; i < nn; ++i) row[i] = c->row_base + hrow[i];
+    if (!hcnt.empty())
+        for (size_t i = 0; i < nn; ++i) {
+            if (goa) goa[i] = hcnt[i].x;
+            if (gob) gob[i] = hcnt[i].y;
+            if (gta) gta[i] = hcnt[i].z;
+            if (gtb) gtb[i] = hcnt[i].w;
+        }
+    return FEHT_OK;
+}
+
+extern "C" int feht_last_timings(const feht_ctx *c, double *out, int n) {
+    if (!c || !out) return FEHT_E_INVALID;
+    const double v[7] = {c->tm.count_ms, c->tm.test_ms, c->tm.order_ms, c->tm.total_ms,
+                         c->tm.launches, c->tm.count_launches, c->tm.count_bytes};
+    for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+    return FEHT_OK;
+}
+
+// ==================================================================================== merge ==
+extern "C" int feht_merge_sorted(int n_shards, const int64_t *n, const double *const *key,
+                                 const int32_t *const *name_rank, int sort_key, int32_t *out_shard,
+                                 int64_t *out_index) {
+    if (n_shards < 0 || (n_shards && (!n || !key || !name_rank))) return FEHT_E_INVALID;
+    struct Item { uint64_t k; int32_t rank; int32_t shard; int64_t idx; };
+    auto key_bits = [&](double v) -> uint64_t {
+        uint64_t b;
+        if (sort_key == FEHT_SORT_PVALUE_ASC) { std::memcpy(&b, &v, 8); return b; }
+        const double a = v < 0 ? -v : v;
+        std::memcpy(&b, &a, 8);
+        b &= 0x7fffffffffffffffULL;
+        return ~b;
+    };
+    auto later = [](const Item &x, const Item &y) {
+        if (x.k != y.k) return x.k > y.k;
+        if (x.rank != y.rank) return uint32_t(x.rank) > uint32_t(y.rank);
+        return x.shard > y.shard;
+    };
+    std::priority_queue<Item, std::vector<Item>, decltype(later)> heap(later);
+    for (int s = 0; s < n_shards; ++s)
+        if (n[s] > 0) heap.push(Item{key_bits(key[s][0]), name_rank[s][0], s, 0});
+    int64_t o = 0;
+    while (!heap.empty()) {
+        Item it = heap.top();
+        heap.pop();
+        if (out_shard) out_shard[o] = it.shard;
+        if (out_index) out_index[o] = it.idx;
+        ++o;
+        const int64_t nx = it.idx + 1;
+        if (nx < n[it.shard])
+            heap.push(Item{key_bits(key[it.shard][nx]), name_rank[it.shard][nx], it.shard, nx});
+    }
+    return FEHT_OK;
+}
+
+// ============================================================================== test hooks ==
+extern "C" int64_t feht_choose_table(double *out, int64_t cap) {
+    const std::vector<double> &t = host_choose_table();
+    if (out && cap > 0) std::memcpy(out, t.data(), size_t(std::min<int64_t>(cap, int64_t(t.size()))) * 8);
+    return int64_t(t.size());
+}
+
+extern "C" int feht_eval_tables(feht_ctx *c, const int32_t *goa, const int32_t *gob, const int32_t *gta,
+                                const int32_t *gtb, int64_t n, double *p_out, double *ratio_out) {
+    if (!c) return FEHT_E_INVALID;
+    if (n < 0 || (n && (!goa || !gob || !gta || !gtb))) return fail(c, FEHT_E_INVALID, "null table arrays");
+    if (n == 0) return FEHT_OK;
+    if (int rc = use_device(c)) return rc;
+    std::vector<int4> h(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) {
+        if (goa[i] < 0 || gob[i] < 0 || gta[i] < 0 || gtb[i] < 0)
+            return fail(c, FEHT_E_INVALID, "negative count (the device path only sees popcounts)");
+        h[size_t(i)] = make_int4(goa[i], gob[i], gta[i], gtb[i]);
+    }
+    DevBuf<int4> dt; DevBuf<double> dp, dr;
+    CU(c, ensure(dt, size_t(n))); CU(c, ensure(dp, size_t(n))); CU(c, ensure(dr, size_t(n)));
+    CU(c, cudaMemcpyAsync(dt.p, h.data(), size_t(n) * 16, cudaMemcpyHostToDevice, c->st));
+    CU(c, launch_eval_tables(dt.p, n, c->d_choose, dp.p, dr.p, c->st));
+    if (p_out) CU(c, cudaMemcpyAsync(p_out, dp.p, size_t(n) * 8, cudaMemcpyDeviceToHost, c->st));
+    if (ratio_out) CU(c, cudaMemcpyAsync(ratio_out, dr.p, size_t(n) * 8, cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    release(dt); release(dp); release(dr);
+    return FEHT_OK;
+}

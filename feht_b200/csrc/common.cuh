@@ -1,0 +1,124 @@
+// common.cuh -- shared declarations of libfeht_cuda (B200 / sm_100a).
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   binary mode : two bit-planes, value and valid, each [rows][W] 64-bit words, W = ceil(S/64)
+//                 rounded up to an even number so that every row starts on a 16-byte boundary
+//                 (128-bit loads).  Bit s%64 of word s/64 = sample s.  Padding bits are 0.
+//   SNP mode    : three planes hi, valid, lo per site (2-bit nucleotide code A=0 C=1 G=2 T=3).
+//   counts      : int4 per (pair-slot, marker row): (P_first, N_first, P_second, N_second) where
+//                 P = #'1' and N = #('1' or '0') inside a column mask.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/feht_cuda.h"
+
+namespace feht {
+
+constexpr int kChooseN = 1000;          // FET.hs:105,109: hypergeometric branch only for l < 1000
+constexpr int64_t kChooseEntries = 250500;  // sum_{n<1000} (n/2 + 1)
+
+// index of C[n][k'] (k' <= n/2) in the folded triangular table
+__host__ __device__ inline int choose_offset(int n) { return n + ((n - 1) * (n - 1)) / 4; }
+
+// One comparison as the device sees it: where its two (P,N) pairs live in the counts array.
+struct CompDesc {
+    int32_t kind;       // 0 explicit, 1 pair, 2 one-vs-rest
+    int32_t slot_a;     // pair-slot index holding group one
+    int32_t sel_a;      // 0: (x,y) components, 1: (z,w) components
+    int32_t slot_b;     // pair-slot of group two (kind 2: the value itself, subtracted from total)
+    int32_t sel_b;
+    int32_t slot_tot;   // kind 2: pair-slot holding the category total in (x,y)
+    int32_t pad0, pad1;
+};
+
+struct Timings {
+    double count_ms = 0, test_ms = 0, order_ms = 0, total_ms = 0;
+    double launches = 0, count_launches = 0, count_bytes = 0;
+};
+
+// ---- kernels / launchers (defined in the .cu files) ----------------------------------------
+
+// pack.cu
+cudaError_t launch_pack_chars(const uint8_t *d_chars, const int64_t *d_row_offsets, int64_t n_rows,
+                              int64_t S, int64_t W, uint64_t *d_value, uint64_t *d_valid,
+                              cudaStream_t st);
+cudaError_t launch_pack_snp_chars(const uint8_t *d_chars, const int64_t *d_row_offsets,
+                                  int64_t n_sites, int64_t S, int64_t W, uint64_t *d_hi,
+                                  uint64_t *d_valid, uint64_t *d_lo, cudaStream_t st);
+cudaError_t launch_synth(const feht_synth_spec *d_spec, int snp_mode, int64_t first_row,
+                         int64_t n_rows, int64_t S, int64_t W, uint64_t *d_p0, uint64_t *d_valid,
+                         uint64_t *d_lo, cudaStream_t st);
+cudaError_t launch_repack_rows(const uint64_t *d_src, int64_t src_stride, uint64_t *d_dst,
+                               int64_t W, int64_t S, int64_t n_rows, const uint64_t *d_and_with,
+                               cudaStream_t st);
+
+// count_popc.cu  (K1)
+struct PopcPlan {
+    int logL;      // lanes per row = 1 << logL
+    int ncol;      // 16-byte columns per lane per chunk
+    int nchunk;    // chunks per row
+    int w4pad;     // padded 16-byte columns per mask row = (1<<logL) * ncol * nchunk
+};
+PopcPlan make_popc_plan(int64_t W);
+// masks: [n_slots][2][w4pad] uint4 (zero padded).  counts: [n_slots][n_rows_out] int4.
+cudaError_t launch_count_popc(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows,
+                              int64_t W, const PopcPlan &plan, const uint4 *d_masks, int n_slots,
+                              int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
+cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
+                                  const uint64_t *d_lo, int64_t n_sites, int64_t W,
+                                  const PopcPlan &plan, const uint4 *d_masks, int n_slots,
+                                  int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
+
+// fet.cu  (K3)
+struct TestParams {
+    const int4 *counts;       // [n_slots][n_rows]
+    const CompDesc *comps;    // [n_comps]
+    int64_t n_rows;
+    int n_comps;
+    double ratio_filter;
+    int correction;
+    double bonferroni_n;
+    const double *choose;     // folded table
+    const int32_t *name_rank; // may be null
+    // survivors (SoA)
+    int32_t *r_comp, *r_row, *r_rank;
+    int4 *r_cnt;
+    double *r_p, *r_ratio;
+    unsigned long long *seg_count;   // [n_comps] (count mode) / cursors (emit mode)
+    const long long *seg_base;       // [n_comps] exclusive offsets (emit mode, filtered)
+    int dense;                       // 1: every test survives, index = comp*n_rows + row
+};
+cudaError_t launch_test_count(const TestParams &p, cudaStream_t st);
+cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
+cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose,
+                               double *d_p, double *d_ratio, cudaStream_t st);
+
+// sort.cu  (K4)
+struct SortWorkspace {
+    uint32_t *perm_a = nullptr, *perm_b = nullptr;
+    uint32_t *block_hist = nullptr;
+    uint32_t *keys[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *or_and = nullptr;   // 8 words
+    int64_t cap_items = 0, cap_hist = 0;
+};
+// Sorts n survivors by (comp asc, key asc, rank asc) where key = keys[2]:keys[1] (hi:lo);
+// returns the permutation (device pointer inside ws) and the number of kernel launches.
+cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, cudaStream_t st, uint32_t **perm_out,
+                            int *launches);
+cudaError_t launch_build_keys(const double *r_ratio, const double *r_p, const int32_t *r_rank,
+                              const int32_t *r_comp, int sort_key, int64_t n, SortWorkspace &ws,
+                              cudaStream_t st);
+cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, const int32_t *r_row,
+                                  const int32_t *r_rank, const int4 *r_cnt, const double *r_p,
+                                  const double *r_ratio, int32_t *o_row, int32_t *o_rank,
+                                  int4 *o_cnt, double *o_p, double *o_ratio, cudaStream_t st);
+
+// choose_table.cpp
+const std::vector<double> &host_choose_table();
+
+}  // namespace feht

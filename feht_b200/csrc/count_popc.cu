@@ -1,0 +1,362 @@
+// count_popc.cu -- K1: popcount contingency scan (few comparisons).
+//
+// Replaces Comparison.hs:46-68,116-125 (/root/reference/src): four countCharInVectorByIndices walks
+// per (marker, comparison) become, per 128 bits of each bit-plane,
+//     P1 += popc(value & M1)   N1 += popc(valid & M1)   P2 += popc(value & M2)   N2 += popc(valid & M2)
+// so that goa = P1, gob = N1 - P1, gta = P2, gtb = N2 - P2 (bit-exact integers).
+//
+// Mapping (DESIGN.md "K1"): a row is split over L = 2^logL lanes, every lane owning NCOL 16-byte
+// columns per chunk, so a warp covers 32/L rows at once and all 2*NCOL 128-bit loads of a lane are
+// issued back to back before the first use (memory-level parallelism).  Loads are coalesced
+// (L consecutive lanes read L*16 contiguous bytes of a row) and bypass L1 allocation: the planes
+// are read exactly once.  The group masks are staged ONCE per CTA into shared memory with a TMA
+// bulk copy (cp.async.bulk + mbarrier) and re-read from there for every row (zero-padded to the
+// lane grid, so no bounds test in the inner loop).  L-lane partial counts are combined with
+// shuffles; lane 0 of each row writes one int4.
+//
+// Bound: HBM.  Algorithmic bytes per marker row = 2 planes * 8 * ceil(S/64);
+// the kernel reads 2 * 8 * W (W = that, rounded up to even) and writes 16 B per (row, pair-slot).
+#include "common.cuh"
+
+namespace feht {
+namespace {
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+        : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int popc_and(const uint4 &a, const uint4 &m) {
+    return __popc(a.x & m.x) + __popc(a.y & m.y) + __popc(a.z & m.z) + __popc(a.w & m.w);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// TMA bulk copy global -> shared of `bytes` (multiple of 16) signalled on an mbarrier.
+__device__ __forceinline__ void stage_masks_tma(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                                uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                     "r"(bytes)
+                     : "memory");
+        // bulk copies are limited in size per instruction; issue in <= 32 KiB pieces
+        uint32_t done = 0;
+        while (done < bytes) {
+            uint32_t n = bytes - done;
+            if (n > 32768u) n = 32768u;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(smem_u32(static_cast<char *>(smem_dst) + done)),
+                "l"(static_cast<const char *>(gmem_src) + done), "r"(n), "r"(smem_u32(bar))
+                : "memory");
+            done += n;
+        }
+    }
+    // every thread waits for phase 0 to complete
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar))
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// binary planes
+// ---------------------------------------------------------------------------------------------
+template <int NCOL, int CB>
+__global__ void __launch_bounds__(256)
+count_popc_kernel(const uint4 *__restrict__ value, const uint4 *__restrict__ valid, int64_t n_rows,
+                  int w4, int logL, int nchunk, int w4pad, const uint4 *__restrict__ masks,
+                  int4 *__restrict__ counts) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    uint4 *sm = reinterpret_cast<uint4 *>(smem_raw);  // [CB][2][w4pad]
+
+    const int slot0 = blockIdx.y * CB;
+    stage_masks_tma(sm, masks + size_t(slot0) * 2 * w4pad, uint32_t(CB) * 2u * uint32_t(w4pad) * 16u,
+                    &bar);
+
+    const int lane = threadIdx.x & 31;
+    const int L = 1 << logL;
+    const int sub = lane & (L - 1);
+    const int rsub = lane >> logL;
+    const int rpw = 32 >> logL;  // rows per warp iteration
+    const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int64_t ngroups = (n_rows + rpw - 1) / rpw;
+
+    for (int64_t g = gwarp; g < ngroups; g += nwarps) {
+        const int64_t row = g * rpw + rsub;
+        const bool ok = row < n_rows;
+        const uint4 *vrow = value + row * w4;
+        const uint4 *drow = valid + row * w4;
+        int acc[CB][4];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+
+        for (int ch = 0; ch < nchunk; ++ch) {
+            uint4 v[NCOL], d[NCOL];
+            const int col0 = ch * (NCOL << logL) + sub;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                const int col = col0 + (j << logL);
+                if (ok && col < w4) {
+                    v[j] = ldg_stream(vrow + col);
+                    d[j] = ldg_stream(drow + col);
+                } else {
+                    v[j] = make_uint4(0, 0, 0, 0);
+                    d[j] = make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                const uint4 *m1p = sm + (c * 2 + 0) * w4pad + col0;
+                const uint4 *m2p = sm + (c * 2 + 1) * w4pad + col0;
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) {
+                    const uint4 m1 = m1p[j << logL];
+                    const uint4 m2 = m2p[j << logL];
+                    acc[c][0] += popc_and(v[j], m1);
+                    acc[c][1] += popc_and(d[j], m1);
+                    acc[c][2] += popc_and(v[j], m2);
+                    acc[c][3] += popc_and(d[j], m2);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int x = acc[c][q];
+                for (int o = L >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                acc[c][q] = x;
+            }
+            if (ok && sub == 0)
+                counts[size_t(slot0 + c) * n_rows + row] =
+                    make_int4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SNP planes: per site four marker rows _a,_t,_c,_g (Table.hs:184-191), valid shared by all four.
+// ---------------------------------------------------------------------------------------------
+template <int NCOL, int CB>
+__global__ void __launch_bounds__(256)
+count_popc_snp_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ valid,
+                      const uint4 *__restrict__ lo, int64_t n_sites, int w4, int logL, int nchunk,
+                      int w4pad, const uint4 *__restrict__ masks, int4 *__restrict__ counts) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    uint4 *sm = reinterpret_cast<uint4 *>(smem_raw);
+
+    const int slot0 = blockIdx.y * CB;
+    stage_masks_tma(sm, masks + size_t(slot0) * 2 * w4pad, uint32_t(CB) * 2u * uint32_t(w4pad) * 16u,
+                    &bar);
+
+    const int lane = threadIdx.x & 31;
+    const int L = 1 << logL;
+    const int sub = lane & (L - 1);
+    const int rsub = lane >> logL;
+    const int rpw = 32 >> logL;
+    const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int64_t ngroups = (n_sites + rpw - 1) / rpw;
+    const int64_t n_rows = 4 * n_sites;
+
+    for (int64_t g = gwarp; g < ngroups; g += nwarps) {
+        const int64_t site = g * rpw + rsub;
+        const bool ok = site < n_sites;
+        // acc[c][mask][0..3] = A, T, C, N
+        int acc[CB][2][4];
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) acc[c][m][0] = acc[c][m][1] = acc[c][m][2] = acc[c][m][3] = 0;
+
+        for (int ch = 0; ch < nchunk; ++ch) {
+            uint4 a[NCOL], t[NCOL], cc[NCOL], d[NCOL];
+            const int col0 = ch * (NCOL << logL) + sub;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                const int col = col0 + (j << logL);
+                uint4 h = make_uint4(0, 0, 0, 0), l = h, v = h;
+                if (ok && col < w4) {
+                    h = ldg_stream(hi + site * w4 + col);
+                    l = ldg_stream(lo + site * w4 + col);
+                    v = ldg_stream(valid + site * w4 + col);
+                }
+                d[j] = v;
+                a[j] = make_uint4(~h.x & ~l.x & v.x, ~h.y & ~l.y & v.y, ~h.z & ~l.z & v.z, ~h.w & ~l.w & v.w);
+                t[j] = make_uint4(h.x & l.x & v.x, h.y & l.y & v.y, h.z & l.z & v.z, h.w & l.w & v.w);
+                cc[j] = make_uint4(~h.x & l.x & v.x, ~h.y & l.y & v.y, ~h.z & l.z & v.z, ~h.w & l.w & v.w);
+            }
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const uint4 *mp = sm + (c * 2 + m) * w4pad + col0;
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) {
+                        const uint4 mk = mp[j << logL];
+                        acc[c][m][0] += popc_and(a[j], mk);
+                        acc[c][m][1] += popc_and(t[j], mk);
+                        acc[c][m][2] += popc_and(cc[j], mk);
+                        acc[c][m][3] += popc_and(d[j], mk);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int x = acc[c][m][q];
+                    for (int o = L >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                    acc[c][m][q] = x;
+                }
+            if (ok && sub == 0) {
+                int4 *out = counts + size_t(slot0 + c) * n_rows + 4 * site;
+                const int n1 = acc[c][0][3], n2 = acc[c][1][3];
+                const int g1 = n1 - acc[c][0][0] - acc[c][0][1] - acc[c][0][2];
+                const int g2 = n2 - acc[c][1][0] - acc[c][1][1] - acc[c][1][2];
+                out[0] = make_int4(acc[c][0][0], n1, acc[c][1][0], n2);  // _a
+                out[1] = make_int4(acc[c][0][1], n1, acc[c][1][1], n2);  // _t
+                out[2] = make_int4(acc[c][0][2], n1, acc[c][1][2], n2);  // _c
+                out[3] = make_int4(g1, n1, g2, n2);                      // _g
+            }
+        }
+    }
+}
+
+template <int CB, bool SNP>
+cudaError_t dispatch(int ncol, dim3 grid, size_t smem, cudaStream_t st, const uint4 *p0,
+                     const uint4 *p1, const uint4 *p2, int64_t n, int w4, const PopcPlan &pl,
+                     const uint4 *masks, int4 *counts) {
+#define FEHT_CASE(NC)                                                                              \
+    case NC:                                                                                       \
+        if constexpr (SNP) {                                                                       \
+            if (smem > 48 * 1024)                                                                  \
+                cudaFuncSetAttribute(count_popc_snp_kernel<NC, CB>,                                \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
+            count_popc_snp_kernel<NC, CB><<<grid, 256, smem, st>>>(p0, p1, p2, n, w4, pl.logL,     \
+                                                                    pl.nchunk, pl.w4pad, masks,    \
+                                                                    counts);                       \
+        } else {                                                                                   \
+            if (smem > 48 * 1024)                                                                  \
+                cudaFuncSetAttribute(count_popc_kernel<NC, CB>,                                    \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
+            count_popc_kernel<NC, CB><<<grid, 256, smem, st>>>(p0, p1, n, w4, pl.logL, pl.nchunk,  \
+                                                                pl.w4pad, masks, counts);          \
+        }                                                                                          \
+        break;
+    switch (ncol) {
+        FEHT_CASE(1)
+        FEHT_CASE(2)
+        FEHT_CASE(3)
+        FEHT_CASE(4)
+        FEHT_CASE(5)
+        FEHT_CASE(6)
+        FEHT_CASE(7)
+        FEHT_CASE(8)
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef FEHT_CASE
+    return cudaGetLastError();
+}
+
+template <bool SNP>
+cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p2, int64_t n,
+                       int64_t W, const PopcPlan &plan, const uint4 *d_masks, int n_slots,
+                       int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+    if (n == 0 || n_slots == 0) return cudaSuccess;
+    const int w4 = int(W / 2);
+    const int rpw = 32 >> plan.logL;
+    const int64_t ngroups = (n + rpw - 1) / rpw;
+    int64_t want = (ngroups + 7) / 8;  // CTAs if every warp did one group
+    const int64_t persistent = int64_t(num_sms) * 6;
+    const int gx = int(want < persistent ? (want < 1 ? 1 : want) : persistent);
+    const uint4 *a = reinterpret_cast<const uint4 *>(p0);
+    const uint4 *b = reinterpret_cast<const uint4 *>(p1);
+    const uint4 *c = reinterpret_cast<const uint4 *>(p2);
+    // batches of 4 pair-slots share one read of the planes; the remainder goes one at a time
+    int done = 0;
+    const int n4 = n_slots / 4;
+    if (n4 > 0) {
+        const size_t smem = size_t(4) * 2 * plan.w4pad * 16;
+        cudaError_t e = dispatch<4, SNP>(plan.ncol, dim3(gx, n4), smem, st, a, b, c, n, w4, plan,
+                                         d_masks, d_counts);
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+        done = n4 * 4;
+    }
+    if (done < n_slots) {
+        const size_t smem = size_t(2) * plan.w4pad * 16;
+        const size_t rows_out = SNP ? size_t(4) * n : size_t(n);
+        cudaError_t e = dispatch<1, SNP>(plan.ncol, dim3(gx, n_slots - done), smem, st, a, b, c, n, w4,
+                                         plan, d_masks + size_t(done) * 2 * plan.w4pad,
+                                         d_counts + size_t(done) * rows_out);
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace
+
+PopcPlan make_popc_plan(int64_t W) {
+    const int w4 = int(W / 2);
+    PopcPlan best{0, 1, 1, 1};
+    long best_cost = -1;
+    for (int logL = 0; logL <= 5; ++logL) {
+        const int L = 1 << logL;
+        if (L < 8 && w4 >= 8) continue;  // keep >= 128 contiguous bytes per row segment
+        for (int ncol = 1; ncol <= 8; ++ncol) {
+            const int per_chunk = L * ncol;
+            const int nchunk = (w4 + per_chunk - 1) / per_chunk;
+            const long slots = long(per_chunk) * nchunk;
+            // cost: wasted lane-slots first, then fewer chunks, then wider rows-per-warp split
+            const long cost = (slots - w4) * 1000 + nchunk * 10 + (5 - logL);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = PopcPlan{logL, ncol, nchunk, int(slots)};
+            }
+        }
+    }
+    return best;
+}
+
+cudaError_t launch_count_popc(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows,
+                              int64_t W, const PopcPlan &plan, const uint4 *d_masks, int n_slots,
+                              int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+    return launch_any<false>(d_value, d_valid, nullptr, n_rows, W, plan, d_masks, n_slots, d_counts,
+                             num_sms, st, launches);
+}
+
+cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
+                                  const uint64_t *d_lo, int64_t n_sites, int64_t W,
+                                  const PopcPlan &plan, const uint4 *d_masks, int n_slots,
+                                  int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+    return launch_any<true>(d_hi, d_valid, d_lo, n_sites, W, plan, d_masks, n_slots, d_counts,
+                            num_sms, st, launches);
+}
+
+}  // namespace feht
