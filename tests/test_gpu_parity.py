@@ -1,0 +1,397 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200.
+
+Bars (BASELINE.json north_star): contingency counts bit-exact; p-values bit-exact on the
+hypergeometric branch (l < 1000) and within 1e-12 relative / 2^-52 absolute on the chi-square
+branch; ratio bit-exact; row order identical (|ratio| descending, ties by marker-name rank).
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from feht_b200 import capi
+from oracle import frontend
+
+from helpers import copy_spec, make_spec, p_close, pack_rows, pack_snp, snp_expand
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_chars(rng, n_rows, n_samples, p_missing=0.05, ragged=False):
+    freq = rng.beta(0.3, 0.3, size=(n_rows, 1))
+    cells = np.where(rng.random((n_rows, n_samples)) < freq, ord("1"), ord("0")).astype(np.uint8)
+    miss = rng.random((n_rows, n_samples)) < p_missing
+    cells[miss] = rng.choice(np.frombuffer(b"-?Nx ", dtype=np.uint8), size=int(miss.sum()))
+    return cells
+
+
+def _check_against_oracle(ctx, rows, comps, correction, ratio_filter, name_rank=None, bonf_n=None):
+    """rows: 2-D uint8 or list of bytes as held by the reference host; comps: list of (g1, g2)."""
+    n_rows = len(rows)
+    for ci, (g1, g2) in enumerate(comps):
+        want = oracle.run_comparison(rows, g1, g2, correction=correction,
+                                     bonferroni_n=n_rows if bonf_n is None else bonf_n)
+        order = oracle.filter_and_order(want["ratio"], name_rank, ratio_filter)
+        got = ctx.fetch(ci)
+        assert len(got["row"]) == len(order), (ci, len(got["row"]), len(order))
+        assert (got["row"] == order).all(), f"comparison {ci}: row order differs"
+        for k in ("goa", "gob", "gta", "gtb"):
+            assert (got[k] == want[k][order]).all(), (ci, k)
+        assert (got["ratio"] == want["ratio"][order]).all(), (ci, "ratio")
+        l = (want["goa"] + want["gob"] + want["gta"] + want["gtb"])[order]
+        ok = p_close(got["p"], want["p"][order], l >= 1000)
+        assert ok.all(), (ci, got["p"][~ok][:5], want["p"][order][~ok][:5])
+
+
+# ------------------------------------------------------------------------------------ K0 pack
+def test_pack_chars_matches_numpy(ctx):
+    rng = np.random.default_rng(1)
+    for s in (1, 12, 63, 64, 65, 127, 128, 300, 5000):
+        cells = _random_chars(rng, 37, s)
+        ctx.set_samples(s)
+        ctx.add_rows_chars(cells)
+        v, d = pack_rows(cells)
+        w = v.shape[1]
+        gv, gd = ctx.read_plane(0, 0, 37), ctx.read_plane(1, 0, 37)
+        assert ctx.row_stride_words % 2 == 0
+        assert (gv[:, :w] == v).all() and (gd[:, :w] == d).all()
+        assert (gv[:, w:] == 0).all() and (gd[:, w:] == 0).all()
+
+
+def test_packed_upload_sanitises_padding_and_value_bits(ctx):
+    rng = np.random.default_rng(2)
+    s = 200
+    cells = _random_chars(rng, 19, s)
+    v, d = pack_rows(cells)
+    # caller stride 6 words with garbage in the tail bits and value bits set where invalid
+    vv = np.full((19, 6), np.uint64(0xFFFFFFFFFFFFFFFF))
+    dd = np.full((19, 6), np.uint64(0xFFFFFFFFFFFFFFFF))
+    vv[:, : v.shape[1]] = v | ~d
+    dd[:, : v.shape[1]] = d
+    tailmask = np.uint64((1 << (s % 64)) - 1)
+    vv[:, -3] |= ~tailmask
+    dd[:, 3] |= ~tailmask
+    ctx.set_samples(s)
+    ctx.add_rows_packed(vv, dd)
+    gv, gd = ctx.read_plane(0, 0, 19), ctx.read_plane(1, 0, 19)
+    assert (gv[:, :4] == v).all() and (gd[:, :4] == d).all()
+
+
+def test_device_generator_equals_oracle_generator(ctx):
+    for snp in (False, True):
+        sp_o = make_spec(oracle.SynthSpec, 333, law="uniform_half" if snp else "beta")
+        sp_g = copy_spec(sp_o, capi.SynthSpec)
+        ctx.set_samples(333)
+        ctx.generate_synthetic(sp_g, snp, 12345, 100)
+        cells = oracle.synth_fill(sp_o, snp, 12345, 100)
+        if snp:
+            hi, lo, valid = pack_snp(cells)
+            w = hi.shape[1]
+            assert (ctx.read_plane(0, 0, 100)[:, :w] == hi).all()
+            assert (ctx.read_plane(1, 0, 100)[:, :w] == valid).all()
+            assert (ctx.read_plane(2, 0, 100)[:, :w] == lo).all()
+        else:
+            v, d = pack_rows(cells)
+            w = v.shape[1]
+            assert (ctx.read_plane(0, 0, 100)[:, :w] == v).all()
+            assert (ctx.read_plane(1, 0, 100)[:, :w] == d).all()
+
+
+# ------------------------------------------------------------------------ K3 arithmetic alone
+def test_fet_exhaustive_small_tables_bit_exact(ctx):
+    tabs = [t for t in itertools.product(range(0, 11), repeat=4)]
+    a, b, c, d = (np.array(x, dtype=np.int32) for x in zip(*tabs))
+    p, r = ctx.eval_tables(a, b, c, d)
+    want_p = np.array([oracle.fet(*t) for t in tabs])
+    want_r = np.array([oracle.calculate_ratio(*t) for t in tabs])
+    assert (p == want_p).all()
+    assert (r == want_r).all()
+
+
+def test_fet_random_hypergeometric_branch_bit_exact(ctx, golden):
+    rng = np.random.default_rng(7)
+    tabs = []
+    for _ in range(1500):
+        l = int(rng.integers(50, 1000))
+        k = int(rng.integers(1, l))
+        if rng.random() < 0.4:
+            k = l // 2                      # balanced designs: structural ties
+        m = int(rng.integers(0, l + 1))
+        lo, hi = max(0, m + k - l), min(m, k)
+        goa = int(rng.integers(lo, hi + 1))
+        tabs.append((goa, k - goa, m - goa, l - k - m + goa))
+    tabs += [(46, 0, 229, 5)]               # exact mathematical tie broken by rounding
+    tabs += [tuple(t[:4]) for t in golden["derived_two_tail"]]
+    tabs += [(250, 249, 260, 240), (499, 0, 0, 500), (0, 499, 500, 0), (1, 0, 0, 998), (333, 333, 333, 0)]
+    a, b, c, d = (np.array(x, dtype=np.int32) for x in zip(*tabs))
+    assert ((a + b + c + d) < 1000).all()
+    p, r = ctx.eval_tables(a, b, c, d)
+    want = np.array([oracle.fet(*t) for t in tabs])
+    assert (p == want).all(), np.flatnonzero(p != want)[:10]
+    for t, w in zip(golden["derived_two_tail"], p[-5 - len(golden["derived_two_tail"]):-5]):
+        assert w == t[4]
+
+
+def test_fetspec_known_answers_on_device(ctx, golden):
+    two = [g for g in golden["fetspec"] if g[4] == "two"]
+    a, b, c, d = (np.array([g[i] for g in two], dtype=np.int32) for i in range(4))
+    p, _ = ctx.eval_tables(a, b, c, d)
+    want = np.array([g[5] for g in two])
+    ok = p_close(p, want, (a + b + c + d) >= 1000)
+    assert ok.all(), (p, want)
+    assert p[0] == want[0] and p[1] == want[1]          # hypergeometric KATs: bit-exact
+
+
+def test_chi_square_branch_sweep(ctx):
+    rng = np.random.default_rng(9)
+    tabs = []
+    # around the 999/1000 switch, the Pearson / continued-fraction switch (chi2 = 2) and the
+    # zero cut-off (chi2 ~ 72), plus random large tables and zero margins (NaN)
+    for l in (1000, 1001, 1500, 4950, 20000, 50000):
+        for _ in range(300):
+            k = int(rng.integers(1, l))
+            m = int(rng.integers(0, l + 1))
+            lo, hi = max(0, m + k - l), min(m, k)
+            e = m * k / l
+            goa = int(np.clip(round(e + rng.normal() * rng.choice([0.3, 1, 3, 9]) * max(1.0, (e * (1 - k / l)) ** 0.5)), lo, hi))
+            tabs.append((goa, k - goa, m - goa, l - k - m + goa))
+    tabs += [(0, 600, 0, 700), (600, 0, 700, 0), (500, 500, 500, 500), (1000, 0, 0, 1000), (999, 1, 0, 0)]
+    a, b, c, d = (np.array(x, dtype=np.int32) for x in zip(*tabs))
+    p, r = ctx.eval_tables(a, b, c, d)
+    want = np.array([oracle.fet(*t) for t in tabs])
+    l = a + b + c + d
+    ok = p_close(p, want, l >= 1000)
+    assert ok.all(), (np.array(tabs)[~ok][:5], p[~ok][:5], want[~ok][:5])
+    assert np.isnan(p[-5]) and np.isnan(p[-4])
+    # how many are bit-identical (reported, not asserted beyond the tolerance)
+    frac_exact = float(((p == want) | (np.isnan(p) & np.isnan(want))).mean())
+    assert frac_exact > 0.5
+
+
+# ------------------------------------------------------------------ K1 + K3 + K4 end to end
+@pytest.mark.parametrize("n_samples", [12, 64, 100, 257, 700, 1300, 5000])
+def test_random_matrix_explicit_comparisons(ctx, n_samples):
+    rng = np.random.default_rng(100 + n_samples)
+    n_rows = 257
+    cells = _random_chars(rng, n_rows, n_samples)
+    cols = rng.permutation(n_samples)
+    h = n_samples // 2
+    comps = [(cols[:h], cols[h:]),                                     # disjoint, covering
+             (cols[: max(1, h // 3)], cols[h: h + max(1, h // 2)]),   # disjoint, partial
+             (cols[: max(1, h)], cols[max(0, h // 2): n_samples]),    # overlapping (Comparison.hs:283-284)
+             (cols[:1], cols[1:2] if n_samples > 1 else cols[:1])]
+    rank = rng.permutation(n_rows).astype(np.int32)
+    ctx.set_samples(n_samples)
+    ctx.add_rows_chars(cells, rank)
+    for g1, g2 in comps:
+        ctx.add_comparison(g1, g2)
+    for correction, rf in ((1, 0.0), (0, 0.0), (1, 0.3), (0, 1.0)):
+        ctx.run(correction, rf)
+        _check_against_oracle(ctx, cells, comps, correction, rf, rank)
+
+
+def test_ragged_rows_and_bounds_error(ctx):
+    # rows longer / shorter than S, as Table.hs:170 produces from cells like "1 "
+    rows = [b"0101-1010101", b"11110000111100", b"1 01010101010", b"010101010101"]
+    ctx.set_samples(12)
+    ctx.add_rows_chars(rows)
+    g1, g2 = [0, 1, 2, 5], [3, 4, 11]
+    ctx.add_comparison(g1, g2)
+    ctx.run(capi.CORRECTION_NONE, 0.0)
+    _check_against_oracle(ctx, rows, [(g1, g2)], 0, 0.0)
+    # a short row + a comparison that indexes past its end = V.! error in the reference
+    ctx.add_rows_chars([b"0101"])
+    with pytest.raises(capi.FehtError) as e:
+        ctx.run(capi.CORRECTION_NONE, 0.0)
+    assert e.value.code == capi.E_BOUNDS
+    with pytest.raises(IndexError):
+        oracle.run_comparison(rows + [b"0101"], g1, g2)
+
+
+def test_empty_inputs(ctx):
+    ctx.set_samples(8)
+    ctx.add_comparison([0, 1], [2, 3])
+    ctx.run()
+    assert ctx.result_count(0) == 0 and ctx.result_total() == 0
+    ctx.add_rows_chars([b"01010101"])
+    ctx.clear_comparisons()
+    ctx.run()
+    assert ctx.result_total() == 0
+    # a group that is empty for every marker: p = 1, ratio = 0 (FET.hs:99,103; Comparison.hs:74-75)
+    ctx.add_comparison([], [0, 1])
+    ctx.run(capi.CORRECTION_NONE)
+    got = ctx.fetch(0)
+    assert got["p"][0] == 1.0 and got["ratio"][0] == 0.0
+
+
+def test_config1_fixture_end_to_end(ctx, fixture_bytes):
+    """BASELINE config 1: data/test_binary.txt + test_metadata.txt, all comparisons, both corrections,
+    rows packed from the concatenated cell string exactly as the host produces it."""
+    meta = fixture_bytes["test_metadata.txt"]
+    for fname, mode in (("test_binary.txt", "binary"), ("test_snps.txt", "snp")):
+        pd = frontend.parse_data_file(b"\t", mode, fixture_bytes[fname])
+        table = frontend.get_metadata_from_file(b"\t", pd, meta)
+        cl = frontend.get_comparison_list(table, frontend.generate_categories("all all", "all all"))
+        assert len(cl) == 16
+        names = list(pd.gene_vector_map.keys())
+        rows = [pd.gene_vector_map[n] for n in names]
+        rank = np.argsort(np.argsort(np.array(names, dtype=object))).astype(np.int32)
+        ctx.set_samples(12)
+        ctx.clear_comparisons()
+        ctx.add_rows_chars(rows, rank)
+        for comp in cl:
+            ctx.add_comparison(comp.g1, comp.g2)
+        for correction in (capi.CORRECTION_BONFERRONI, capi.CORRECTION_NONE):
+            for rf in (0.0, 0.8, 1.0):
+                ctx.run(correction, rf)
+                _check_against_oracle(ctx, rows, [(c.g1, c.g2) for c in cl], correction, rf, rank)
+                # and the formatted blocks agree with the oracle front-end's
+                _, structured = frontend.run_files(meta, fixture_bytes[fname], mode=mode,
+                                                   correction="bonferroni" if correction else "none",
+                                                   ratio_filter=rf)
+                for ci, s in enumerate(structured):
+                    got = ctx.fetch(ci)
+                    assert [names[i] for i in got["row"]] == s["names"]
+                    assert (got["p"] == s["p"]).all()      # l = 12 < 1000: bit-exact
+
+
+def test_category_api_equals_explicit_comparisons(ctx):
+    rng = np.random.default_rng(21)
+    n_samples, n_rows = 310, 200
+    cells = _random_chars(rng, n_rows, n_samples)
+    for n_values in (2, 3, 5, 8):
+        vos = rng.integers(-1, n_values, size=n_samples).astype(np.int32)   # -1: no metadata
+        ctx.set_samples(n_samples)
+        ctx.clear_comparisons()
+        ctx.add_rows_chars(cells)
+        first = ctx.add_category(vos, n_values)
+        assert first == 0
+        comps = []
+        for i in range(n_values):
+            for j in range(i + 1, n_values):
+                comps.append((np.flatnonzero(vos == i), np.flatnonzero(vos == j)))
+        if n_values > 2:
+            for v in range(n_values):
+                comps.append((np.flatnonzero(vos == v), np.flatnonzero((vos >= 0) & (vos != v))))
+        assert ctx.num_comparisons == len(comps)
+        ctx.run(capi.CORRECTION_BONFERRONI, 0.25)
+        _check_against_oracle(ctx, cells, comps, 1, 0.25)
+        kinds = [ctx.comparison_info(i)[0] for i in range(len(comps))]
+        assert kinds.count(2) == (n_values if n_values > 2 else 0)
+
+
+def test_snp_packed_equals_expanded_binary_rows(ctx):
+    rng = np.random.default_rng(33)
+    n_sites, n_samples = 150, 421
+    alphabet = np.frombuffer(b"ACGTacgt-N", dtype=np.uint8)
+    sites = rng.choice(alphabet, size=(n_sites, n_samples), p=[.3, .2, .2, .2, .02, .02, .02, .02, .01, .01])
+    expanded = snp_expand(sites)                       # what the Haskell host would hand over
+    vos = rng.integers(0, 4, size=n_samples).astype(np.int32)
+    comps = [(np.flatnonzero(vos == i), np.flatnonzero(vos == j)) for i in range(4) for j in range(i + 1, 4)]
+    comps += [(np.flatnonzero(vos == v), np.flatnonzero(vos != v)) for v in range(4)]
+    # (1) packed planes + category, (2) site characters + category, (3) expanded chars + explicit
+    hi, lo, valid = pack_snp(sites)
+    for variant in range(3):
+        ctx.set_samples(n_samples)
+        ctx.clear_comparisons()
+        if variant == 0:
+            ctx.add_snp_packed(hi, lo, valid)
+        elif variant == 1:
+            ctx.add_snp_chars(sites)
+        else:
+            ctx.add_rows_chars(expanded)
+        if variant < 2:
+            ctx.add_category(vos, 4)
+        else:
+            for g1, g2 in comps:
+                ctx.add_comparison(g1, g2)
+        assert ctx.num_rows == 4 * n_sites
+        ctx.run(capi.CORRECTION_BONFERRONI, 0.1)
+        _check_against_oracle(ctx, expanded, comps, 1, 0.1)
+
+
+def test_row_sharding_and_merge_equals_single_context(cuda_lib):
+    """shard marker rows, pass the global Bonferroni n, k-way merge the sorted shards."""
+    rng = np.random.default_rng(55)
+    n_samples, n_rows = 500, 1000
+    cells = _random_chars(rng, n_rows, n_samples)
+    rank = rng.permutation(n_rows).astype(np.int32)
+    g1, g2 = np.arange(0, 200), np.arange(250, 500)
+    want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=n_rows)
+    order = oracle.filter_and_order(want["ratio"], rank, 0.2)
+    shards = []
+    bounds = [0, 300, 301, 777, 1000]
+    for lo_, hi_ in zip(bounds[:-1], bounds[1:]):
+        c = capi.Context(0)
+        c.set_samples(n_samples)
+        c.set_row_base(lo_)
+        c.add_rows_chars(cells[lo_:hi_], rank[lo_:hi_])
+        c.add_comparison(g1, g2)
+        c.run(1, 0.2, capi.SORT_ABS_RATIO_DESC, n_rows)
+        shards.append(c.fetch(0))
+        c.close()
+    out_s, out_i = capi.merge_sorted([s["ratio"] for s in shards], [s["name_rank"] for s in shards])
+    merged_rows = np.array([shards[s]["row"][i] for s, i in zip(out_s, out_i)])
+    merged_p = np.array([shards[s]["p"][i] for s, i in zip(out_s, out_i)])
+    assert (merged_rows == order).all()
+    assert (merged_p == want["p"][order]).all()
+
+
+def test_pvalue_sort_key(ctx):
+    rng = np.random.default_rng(77)
+    cells = _random_chars(rng, 300, 90)
+    ctx.set_samples(90)
+    ctx.add_rows_chars(cells)
+    ctx.add_comparison(np.arange(0, 40), np.arange(40, 90))
+    ctx.run(capi.CORRECTION_NONE, 0.0, capi.SORT_PVALUE_ASC)
+    got = ctx.fetch(0)
+    keys = list(zip(got["p"], got["row"]))
+    assert keys == sorted(keys)
+
+
+# ------------------------------------------------------------- BASELINE sizes: properties
+def test_config2_full_size_properties(ctx):
+    """Config 2 (1M markers x 5k genomes, one comparison): too big for the oracle, so check
+    size-independent properties plus an oracle comparison on rows regenerated from the counter-based
+    generator."""
+    S, R = 5000, 1_000_000
+    sp_o = make_spec(oracle.SynthSpec, S)
+    sp_g = copy_spec(sp_o, capi.SynthSpec)
+    ctx.set_samples(S)
+    ctx.generate_synthetic(sp_g, False, 0, R)
+    g1, g2 = np.arange(0, 2500), np.arange(2500, 5000)
+    ctx.add_comparison(g1, g2)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.0)
+    got = ctx.fetch(0)
+    assert len(got["row"]) == R
+    assert (np.sort(got["row"]) == np.arange(R)).all()                     # a permutation of the rows
+    ar = np.abs(got["ratio"])
+    assert (ar[:-1] >= ar[1:]).all()                                        # |ratio| descending
+    ties = ar[:-1] == ar[1:]
+    assert (got["row"][:-1][ties] < got["row"][1:][ties]).all()             # ties by rank (= row)
+    n1 = got["goa"] + got["gob"]
+    n2 = got["gta"] + got["gtb"]
+    assert n1.max() <= 2500 and n2.max() <= 2500 and (n1 + n2).min() > 4500  # ~1% missing
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = got["goa"] / n1 - got["gta"] / n2
+    assert (r == got["ratio"]).all()                                        # ratio is two IEEE divisions
+    # l >= 1000 with an empty column margin: chiSquare = 0/0 = NaN, and NaN survives Bonferroni
+    # (FET.hs:132-133; Comparison.hs:262 `NaN > 1` is False) -- SURVEY.md Appendix A.4
+    zero_margin = ((got["goa"] + got["gta"]) == 0) | ((got["gob"] + got["gtb"]) == 0)
+    assert (np.isnan(got["p"]) == zero_margin).all()
+    assert ((got["p"] >= 0) & (got["p"] <= 1))[~zero_margin].all()
+    # planted rows (f = 0.9 vs 0.1) come out on top
+    assert ar[0] > 0.7
+    # oracle on a sample of rows, regenerated on the CPU
+    sample = np.concatenate([got["row"][:40], got["row"][-20:], np.array([0, 1, R - 1, 123456])])
+    for row in sample:
+        cells = oracle.synth_fill(sp_o, False, int(row), 1)
+        want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=R)
+        i = int(np.flatnonzero(got["row"] == row)[0])
+        assert (got["goa"][i], got["gob"][i], got["gta"][i], got["gtb"][i]) == \
+            (want["goa"][0], want["gob"][0], want["gta"][0], want["gtb"][0])
+        assert got["ratio"][i] == want["ratio"][0]
+        assert p_close(got["p"][i:i + 1], want["p"], np.array([True])).all()
+    t = ctx.timings()
+    assert t["count_launches"] >= 1 and t["total_ms"] > 0
