@@ -77,7 +77,9 @@ struct feht_ctx {
     DevBuf<int4> r_cnt, o_cnt;
     DevBuf<double> r_p, r_ratio, o_p, o_ratio;
     SortWorkspace sw;
-    DevBuf<uint32_t> sw_perm_a, sw_perm_b, sw_hist, sw_k0, sw_k1, sw_k2, sw_k3, sw_oa;
+    DevBuf<unsigned long long> sw_key_a, sw_key_b;
+    DevBuf<uint32_t> sw_val_a, sw_val_b, sw_control, sw_oa;
+    int rank_is_perm = -1;  // -1 unknown, 0 no, 1 name_rank is a permutation of [0, rows)
 
     bool has_results = false;
     int64_t n_surv = 0;
@@ -290,6 +292,7 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
     if (int rc = staged_upload(c, next_piece, consume)) return rc;
     c->n_units += n;
     c->has_results = false;
+    c->rank_is_perm = -1;
     return FEHT_OK;
 }
 
@@ -334,6 +337,7 @@ int add_packed_common(feht_ctx *c, const uint64_t *const *src_planes, const int 
     if (int rc = staged_upload(c, next_piece, consume)) return rc;
     c->n_units += n;
     c->has_results = false;
+    c->rank_is_perm = -1;
     return FEHT_OK;
 }
 
@@ -394,8 +398,8 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->masks); release(c->counts); release(c->descs); release(c->seg_count); release(c->seg_base);
     release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
     release(c->r_cnt); release(c->o_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
-    release(c->sw_perm_a); release(c->sw_perm_b); release(c->sw_hist);
-    release(c->sw_k0); release(c->sw_k1); release(c->sw_k2); release(c->sw_k3); release(c->sw_oa);
+    release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
+    release(c->sw_control); release(c->sw_oa);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
@@ -427,6 +431,7 @@ extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
     c->W = ((n_samples + 63) / 64 + 1) & ~int64_t(1);  // even number of 64-bit words: 16-byte rows
     c->snp = -1;
     c->n_units = c->cap_units = 0;
+    c->rank_is_perm = -1;
     c->have_rank = -1;
     c->min_row_len = std::numeric_limits<int64_t>::max();
     c->has_results = false;
@@ -451,6 +456,7 @@ extern "C" int feht_clear_rows(feht_ctx *c) {
     if (!c) return FEHT_E_INVALID;
     c->n_units = 0;
     c->snp = -1;
+    c->rank_is_perm = -1;
     c->have_rank = -1;
     c->min_row_len = std::numeric_limits<int64_t>::max();
     c->has_results = false;
@@ -709,6 +715,22 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     tp.choose = c->d_choose;
     tp.name_rank = c->have_rank == 1 ? c->rank.p : nullptr;
     tp.dense = ratio_filter <= 0.0 ? 1 : 0;
+    if (tp.dense && c->have_rank == 1) {
+        if (c->rank_is_perm == -1) {  // does name_rank enumerate [0, rows)?  (checked once per upload)
+            DevBuf<uint32_t> flags;
+            CU(c, ensure(flags, size_t((R + 31) / 32) + 2));
+            unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(c->seg_count.p);
+            CU(c, launch_count_distinct_ranks(c->rank.p, R, flags.p, d_cnt, c->st));
+            unsigned long long distinct = 0;
+            CU(c, cudaMemcpyAsync(&distinct, d_cnt, 8, cudaMemcpyDeviceToHost, c->st));
+            CU(c, cudaStreamSynchronize(c->st));
+            CU(c, cudaMemsetAsync(d_cnt, 0, 8, c->st));
+            release(flags);
+            c->rank_is_perm = distinct == (unsigned long long)R ? 1 : 0;
+        }
+        tp.dense_by_rank = c->rank_is_perm;
+    }
+    const bool rank_presorted = tp.dense && (c->have_rank != 1 || tp.dense_by_rank);
     std::vector<long long> base(static_cast<size_t>(n_comps), 0);
     if (tp.dense) {
         for (int i = 0; i <= n_comps; ++i) c->seg_off[size_t(i)] = int64_t(i) * R;
@@ -724,7 +746,7 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
         CU(c, cudaMemcpyAsync(c->seg_base.p, base.data(), size_t(n_comps) * 8, cudaMemcpyHostToDevice, c->st));
     }
     const int64_t n = c->seg_off[size_t(n_comps)];
-    if (n > int64_t(0xfffffff0u)) return fail(c, FEHT_E_INVALID, "more than 2^32 surviving rows in one run");
+    if (n >= (int64_t(1) << 30)) return fail(c, FEHT_E_INVALID, "2^30 or more surviving rows in one run");
     c->n_surv = n;
     const size_t nn = size_t(n);
     CU(c, ensure(c->r_comp, nn)); CU(c, ensure(c->r_row, nn)); CU(c, ensure(c->r_rank, nn));
@@ -743,18 +765,18 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
 
     // ---- K4 order
     if (n > 0) {
-        const int64_t n_blocks = (n + 2047) / 2048;
-        CU(c, ensure(c->sw_perm_a, nn)); CU(c, ensure(c->sw_perm_b, nn));
-        CU(c, ensure(c->sw_hist, size_t(n_blocks) * 256));
-        CU(c, ensure(c->sw_k0, nn)); CU(c, ensure(c->sw_k1, nn)); CU(c, ensure(c->sw_k2, nn)); CU(c, ensure(c->sw_k3, nn));
+        CU(c, ensure(c->sw_key_a, nn)); CU(c, ensure(c->sw_key_b, nn));
+        CU(c, ensure(c->sw_val_a, nn)); CU(c, ensure(c->sw_val_b, nn));
+        CU(c, ensure(c->sw_control, size_t(16) * 256 + 16 + size_t(16) * sort_status_words(n)));
         CU(c, ensure(c->sw_oa, 8));
-        c->sw.perm_a = c->sw_perm_a.p; c->sw.perm_b = c->sw_perm_b.p; c->sw.block_hist = c->sw_hist.p;
-        c->sw.keys[0] = c->sw_k0.p; c->sw.keys[1] = c->sw_k1.p; c->sw.keys[2] = c->sw_k2.p; c->sw.keys[3] = c->sw_k3.p;
+        c->sw.key_a = c->sw_key_a.p; c->sw.key_b = c->sw_key_b.p;
+        c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
+        c->sw.control = c->sw_control.p;
         c->sw.or_and = c->sw_oa.p;
         CU(c, launch_build_keys(c->r_ratio.p, c->r_p.p, c->r_rank.p, c->r_comp.p, sort_key, n, c->sw, c->st));
         ++launches;
         uint32_t *perm = nullptr;
-        CU(c, radix_sort_perm(c->sw, n, c->st, &perm, &launches));
+        CU(c, radix_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
         CU(c, launch_gather_results(perm, n, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p, c->r_ratio.p,
                                     c->o_row.p, c->o_rank.p, c->o_cnt.p, c->o_p.p, c->o_ratio.p, c->st));
         ++launches;

@@ -92,7 +92,11 @@ struct TestParams {
     unsigned long long *seg_count;   // [n_comps] (count mode) / cursors (emit mode)
     const long long *seg_base;       // [n_comps] exclusive offsets (emit mode, filtered)
     int dense;                       // 1: every test survives, index = comp*n_rows + row
+    int dense_by_rank;               // dense and name_rank is a permutation: index = comp*n_rows + rank
 };
+// counts how many distinct in-range values rank[0..n) holds (== n iff it is a permutation of [0,n))
+cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t *flags_words,
+                                        unsigned long long *out_count, cudaStream_t st);
 cudaError_t launch_test_count(const TestParams &p, cudaStream_t st);
 cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
 cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose,
@@ -100,16 +104,17 @@ cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_
 
 // sort.cu  (K4)
 struct SortWorkspace {
-    uint32_t *perm_a = nullptr, *perm_b = nullptr;
-    uint32_t *block_hist = nullptr;
-    uint32_t *keys[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *key_a = nullptr, *key_b = nullptr;  // 64-bit sort keys (ping-pong)
+    uint32_t *val_a = nullptr, *val_b = nullptr;            // survivor indices (ping-pong)
+    uint32_t *control = nullptr;  // [16][256] histograms, [16] tickets, [passes][tiles][256] status
     uint32_t *or_and = nullptr;   // 8 words
-    int64_t cap_items = 0, cap_hist = 0;
 };
-// Sorts n survivors by (comp asc, key asc, rank asc) where key = keys[2]:keys[1] (hi:lo);
-// returns the permutation (device pointer inside ws) and the number of kernel launches.
-cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, cudaStream_t st, uint32_t **perm_out,
-                            int *launches);
+size_t sort_status_words(int64_t n);
+// Sorts n survivors by (comp asc, key64 asc, rank asc); rank_presorted = the survivors already sit
+// in name-rank order inside every comparison (the stable sort then needs no rank passes).
+// Returns the permutation (device pointer inside ws) and adds the number of kernel launches.
+cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+                            bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches);
 cudaError_t launch_build_keys(const double *r_ratio, const double *r_p, const int32_t *r_rank,
                               const int32_t *r_comp, int sort_key, int64_t n, SortWorkspace &ws,
                               cudaStream_t st);

@@ -23,15 +23,45 @@ namespace {
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
     uint4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
         : "l"(p));
     return r;
 }
 
-__device__ __forceinline__ int popc_and(const uint4 &a, const uint4 &m) {
-    return __popc(a.x & m.x) + __popc(a.y & m.y) + __popc(a.z & m.z) + __popc(a.w & m.w);
+// POPC issues at 16 lanes/clk/SM (XU pipe) and LOP3 at 64 (ALU pipe), and a plain popcount of
+// every masked word needs 0.5 POPC per byte streamed -- ncu showed the XU pipe at 47% with DRAM at
+// only 50% (profiles/r1_count_popc.md), i.e. the scan would turn POPC-bound before HBM-bound.
+// So each count stream keeps a carry-save "ones" word: two masked words are folded into it with one
+// 3:2 compressor (2 LOP3) and only the carry word (weight 2) is popcounted:
+//     count = 2 * sum popc(carry) + popc(ones_final)
+// which halves the POPC work (2 per 16 bytes per stream instead of 4) for 4 extra LOP3.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+struct CountStream {
+    uint32_t ones;
+    int twos;
+    __device__ __forceinline__ void reset() { ones = 0u; twos = 0; }
+    // fold the 128 bits (a & m) into the stream
+    __device__ __forceinline__ void add(const uint4 &a, const uint4 &m) {
+        const uint32_t x = a.x & m.x, y = a.y & m.y, z = a.z & m.z, w = a.w & m.w;
+        const uint32_t c1 = lop3_maj(ones, x, y);
+        ones = lop3_xor3(ones, x, y);
+        const uint32_t c2 = lop3_maj(ones, z, w);
+        ones = lop3_xor3(ones, z, w);
+        twos += __popc(c1) + __popc(c2);
+    }
+    __device__ __forceinline__ int total() const { return 2 * twos + __popc(ones); }
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -105,9 +135,11 @@ count_popc_kernel(const uint4 *__restrict__ value, const uint4 *__restrict__ val
         const bool ok = row < n_rows;
         const uint4 *vrow = value + row * w4;
         const uint4 *drow = valid + row * w4;
-        int acc[CB][4];
+        CountStream st[CB][4];
 #pragma unroll
-        for (int c = 0; c < CB; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+        for (int c = 0; c < CB; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st[c][q].reset();
 
         for (int ch = 0; ch < nchunk; ++ch) {
             uint4 v[NCOL], d[NCOL];
@@ -123,6 +155,10 @@ count_popc_kernel(const uint4 *__restrict__ value, const uint4 *__restrict__ val
                     d[j] = make_uint4(0, 0, 0, 0);
                 }
             }
+            // Scheduling fence: without it ptxas sinks each load next to its first use (2 loads in
+            // flight per thread, long-scoreboard bound at 50% of DRAM); memory operations are not
+            // moved across a warp barrier, so all 2*NCOL loads are issued back to back.
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
                 const uint4 *m1p = sm + (c * 2 + 0) * w4pad + col0;
@@ -131,24 +167,24 @@ count_popc_kernel(const uint4 *__restrict__ value, const uint4 *__restrict__ val
                 for (int j = 0; j < NCOL; ++j) {
                     const uint4 m1 = m1p[j << logL];
                     const uint4 m2 = m2p[j << logL];
-                    acc[c][0] += popc_and(v[j], m1);
-                    acc[c][1] += popc_and(d[j], m1);
-                    acc[c][2] += popc_and(v[j], m2);
-                    acc[c][3] += popc_and(d[j], m2);
+                    st[c][0].add(v[j], m1);
+                    st[c][1].add(d[j], m1);
+                    st[c][2].add(v[j], m2);
+                    st[c][3].add(d[j], m2);
                 }
             }
         }
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
+            int acc[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                int x = acc[c][q];
+                int x = st[c][q].total();
                 for (int o = L >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                acc[c][q] = x;
+                acc[q] = x;
             }
             if (ok && sub == 0)
-                counts[size_t(slot0 + c) * n_rows + row] =
-                    make_int4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                counts[size_t(slot0 + c) * n_rows + row] = make_int4(acc[0], acc[1], acc[2], acc[3]);
         }
     }
 }
@@ -182,12 +218,14 @@ count_popc_snp_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ va
     for (int64_t g = gwarp; g < ngroups; g += nwarps) {
         const int64_t site = g * rpw + rsub;
         const bool ok = site < n_sites;
-        // acc[c][mask][0..3] = A, T, C, N
-        int acc[CB][2][4];
+        // st[c][mask][0..3] = A, T, C, N
+        CountStream st[CB][2][4];
 #pragma unroll
         for (int c = 0; c < CB; ++c)
 #pragma unroll
-            for (int m = 0; m < 2; ++m) acc[c][m][0] = acc[c][m][1] = acc[c][m][2] = acc[c][m][3] = 0;
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st[c][m][q].reset();
 
         for (int ch = 0; ch < nchunk; ++ch) {
             uint4 a[NCOL], t[NCOL], cc[NCOL], d[NCOL];
@@ -206,6 +244,7 @@ count_popc_snp_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ va
                 t[j] = make_uint4(h.x & l.x & v.x, h.y & l.y & v.y, h.z & l.z & v.z, h.w & l.w & v.w);
                 cc[j] = make_uint4(~h.x & l.x & v.x, ~h.y & l.y & v.y, ~h.z & l.z & v.z, ~h.w & l.w & v.w);
             }
+            __syncwarp();  // scheduling fence (see count_popc_kernel)
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
 #pragma unroll
@@ -214,59 +253,77 @@ count_popc_snp_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ va
 #pragma unroll
                     for (int j = 0; j < NCOL; ++j) {
                         const uint4 mk = mp[j << logL];
-                        acc[c][m][0] += popc_and(a[j], mk);
-                        acc[c][m][1] += popc_and(t[j], mk);
-                        acc[c][m][2] += popc_and(cc[j], mk);
-                        acc[c][m][3] += popc_and(d[j], mk);
+                        st[c][m][0].add(a[j], mk);
+                        st[c][m][1].add(t[j], mk);
+                        st[c][m][2].add(cc[j], mk);
+                        st[c][m][3].add(d[j], mk);
                     }
                 }
             }
         }
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
+            int acc[2][4];
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    int x = acc[c][m][q];
+                    int x = st[c][m][q].total();
                     for (int o = L >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                    acc[c][m][q] = x;
+                    acc[m][q] = x;
                 }
             if (ok && sub == 0) {
                 int4 *out = counts + size_t(slot0 + c) * n_rows + 4 * site;
-                const int n1 = acc[c][0][3], n2 = acc[c][1][3];
-                const int g1 = n1 - acc[c][0][0] - acc[c][0][1] - acc[c][0][2];
-                const int g2 = n2 - acc[c][1][0] - acc[c][1][1] - acc[c][1][2];
-                out[0] = make_int4(acc[c][0][0], n1, acc[c][1][0], n2);  // _a
-                out[1] = make_int4(acc[c][0][1], n1, acc[c][1][1], n2);  // _t
-                out[2] = make_int4(acc[c][0][2], n1, acc[c][1][2], n2);  // _c
-                out[3] = make_int4(g1, n1, g2, n2);                      // _g
+                const int n1 = acc[0][3], n2 = acc[1][3];
+                const int g1 = n1 - acc[0][0] - acc[0][1] - acc[0][2];
+                const int g2 = n2 - acc[1][0] - acc[1][1] - acc[1][2];
+                out[0] = make_int4(acc[0][0], n1, acc[1][0], n2);  // _a
+                out[1] = make_int4(acc[0][1], n1, acc[1][1], n2);  // _t
+                out[2] = make_int4(acc[0][2], n1, acc[1][2], n2);  // _c
+                out[3] = make_int4(g1, n1, g2, n2);                // _g
             }
         }
     }
 }
 
+// Launch one instantiation as a persistent grid: exactly (resident CTAs per SM) x (SMs) CTAs, each
+// looping over row groups, so there is no partial last wave (the first version launched 6 CTAs/SM
+// against an occupancy of 4 and lost a quarter of the time in a half-empty second wave).
+template <class Kernel, class... Args>
+cudaError_t launch_persistent(Kernel kernel, int64_t want_ctas, int n_batches, size_t smem,
+                              int num_sms, cudaStream_t st, Args... args) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    // all batches (blockIdx.y) are co-resident waves of the same kernel: share the SMs between them
+    int64_t resident = int64_t(num_sms) * per_sm;
+    int64_t gx = resident / n_batches;
+    if (gx < num_sms) gx = num_sms;
+    if (gx > want_ctas) gx = want_ctas;
+    if (gx < 1) gx = 1;
+    kernel<<<dim3(unsigned(gx), unsigned(n_batches)), 256, smem, st>>>(args...);
+    return cudaGetLastError();
+}
+
 template <int CB, bool SNP>
-cudaError_t dispatch(int ncol, dim3 grid, size_t smem, cudaStream_t st, const uint4 *p0,
-                     const uint4 *p1, const uint4 *p2, int64_t n, int w4, const PopcPlan &pl,
-                     const uint4 *masks, int4 *counts) {
+cudaError_t dispatch(int ncol, int64_t want_ctas, int n_batches, size_t smem, int num_sms,
+                     cudaStream_t st, const uint4 *p0, const uint4 *p1, const uint4 *p2, int64_t n,
+                     int w4, const PopcPlan &pl, const uint4 *masks, int4 *counts) {
 #define FEHT_CASE(NC)                                                                              \
     case NC:                                                                                       \
-        if constexpr (SNP) {                                                                       \
-            if (smem > 48 * 1024)                                                                  \
-                cudaFuncSetAttribute(count_popc_snp_kernel<NC, CB>,                                \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
-            count_popc_snp_kernel<NC, CB><<<grid, 256, smem, st>>>(p0, p1, p2, n, w4, pl.logL,     \
-                                                                    pl.nchunk, pl.w4pad, masks,    \
-                                                                    counts);                       \
-        } else {                                                                                   \
-            if (smem > 48 * 1024)                                                                  \
-                cudaFuncSetAttribute(count_popc_kernel<NC, CB>,                                    \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
-            count_popc_kernel<NC, CB><<<grid, 256, smem, st>>>(p0, p1, n, w4, pl.logL, pl.nchunk,  \
-                                                                pl.w4pad, masks, counts);          \
-        }                                                                                          \
-        break;
+        if constexpr (SNP)                                                                         \
+            return launch_persistent(count_popc_snp_kernel<NC, CB>, want_ctas, n_batches, smem,    \
+                                     num_sms, st, p0, p1, p2, n, w4, pl.logL, pl.nchunk, pl.w4pad, \
+                                     masks, counts);                                               \
+        else                                                                                       \
+            return launch_persistent(count_popc_kernel<NC, CB>, want_ctas, n_batches, smem,        \
+                                     num_sms, st, p0, p1, n, w4, pl.logL, pl.nchunk, pl.w4pad,     \
+                                     masks, counts);
     switch (ncol) {
         FEHT_CASE(1)
         FEHT_CASE(2)
@@ -280,8 +337,10 @@ cudaError_t dispatch(int ncol, dim3 grid, size_t smem, cudaStream_t st, const ui
             return cudaErrorInvalidValue;
     }
 #undef FEHT_CASE
-    return cudaGetLastError();
 }
+
+// pair-slots counted per read of the planes (register budget: 8 count streams per slot for SNP)
+template <bool SNP> constexpr int kBatch = SNP ? 2 : 4;
 
 template <bool SNP>
 cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p2, int64_t n,
@@ -291,28 +350,27 @@ cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p
     const int w4 = int(W / 2);
     const int rpw = 32 >> plan.logL;
     const int64_t ngroups = (n + rpw - 1) / rpw;
-    int64_t want = (ngroups + 7) / 8;  // CTAs if every warp did one group
-    const int64_t persistent = int64_t(num_sms) * 6;
-    const int gx = int(want < persistent ? (want < 1 ? 1 : want) : persistent);
+    const int64_t want = (ngroups + 7) / 8;  // CTAs if every warp did one group
     const uint4 *a = reinterpret_cast<const uint4 *>(p0);
     const uint4 *b = reinterpret_cast<const uint4 *>(p1);
     const uint4 *c = reinterpret_cast<const uint4 *>(p2);
-    // batches of 4 pair-slots share one read of the planes; the remainder goes one at a time
+    constexpr int B = kBatch<SNP>;
+    // batches of B pair-slots share one read of the planes; the remainder goes one at a time
     int done = 0;
-    const int n4 = n_slots / 4;
-    if (n4 > 0) {
-        const size_t smem = size_t(4) * 2 * plan.w4pad * 16;
-        cudaError_t e = dispatch<4, SNP>(plan.ncol, dim3(gx, n4), smem, st, a, b, c, n, w4, plan,
+    const int nb = n_slots / B;
+    if (nb > 0) {
+        const size_t smem = size_t(B) * 2 * plan.w4pad * 16;
+        cudaError_t e = dispatch<B, SNP>(plan.ncol, want, nb, smem, num_sms, st, a, b, c, n, w4, plan,
                                          d_masks, d_counts);
         if (e != cudaSuccess) return e;
         if (launches) ++*launches;
-        done = n4 * 4;
+        done = nb * B;
     }
     if (done < n_slots) {
         const size_t smem = size_t(2) * plan.w4pad * 16;
         const size_t rows_out = SNP ? size_t(4) * n : size_t(n);
-        cudaError_t e = dispatch<1, SNP>(plan.ncol, dim3(gx, n_slots - done), smem, st, a, b, c, n, w4,
-                                         plan, d_masks + size_t(done) * 2 * plan.w4pad,
+        cudaError_t e = dispatch<1, SNP>(plan.ncol, want, n_slots - done, smem, num_sms, st, a, b, c, n,
+                                         w4, plan, d_masks + size_t(done) * 2 * plan.w4pad,
                                          d_counts + size_t(done) * rows_out);
         if (e != cudaSuccess) return e;
         if (launches) ++*launches;

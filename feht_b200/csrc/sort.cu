@@ -7,26 +7,38 @@
 // the composite key  (comparison | key64 | name_rank), 8 bits per pass:
 //     key64 = ~bits(abs ratio)   (abs ratio in [0,1] => IEEE bits are monotone; inverted = descending)
 //           =  bits(p)           for FEHT_SORT_PVALUE_ASC
-// A pass whose digit is identical in every key is skipped (decided from an OR/AND reduction of the
-// key words), so a single comparison costs no "comparison" passes and small jobs cost few
-// name-rank passes.  The sort permutes 4-byte indices; the 40-byte records are gathered once.
 //
-// Bound: HBM/L2 (per pass: read index + gathered key word, write index).
+// Each pass is ONE kernel ("onesweep"): a CTA claims the next 4096-item tile from an atomic ticket,
+// ranks its items stably per digit (warp match-any + per-warp counters in shared memory), publishes
+// its per-digit counts and resolves the counts of all earlier tiles with a decoupled look-back over
+// a status word per (tile, digit), then scatters (key64, index) to the final positions.  The digit
+// histogram the NEXT pass needs is accumulated by the current pass while it has the keys in
+// registers, so there is no separate histogram/scan kernel per pass (the first version spent 63 us
+// per pass in a single-block scan; profiles/r1_launches.md).  A pass whose digit is identical in
+// every key is skipped (OR/AND reduction of the key words), so a single comparison costs no
+// "comparison" passes; when the survivors are emitted in name-rank order (dense output) the stable
+// sort needs no name-rank passes either.  The sort moves (8-byte key, 4-byte index) pairs; the
+// 40-byte records are gathered once at the end.
+//
+// Bound: HBM/L2 traffic, 24 B per item per pass.
 #include "common.cuh"
 
 namespace feht {
 namespace {
 
-constexpr int kSortThreads = 256;
-constexpr int kItemsPerThread = 8;
-constexpr int kTile = kSortThreads * kItemsPerThread;  // 2048 items per block
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;  // 4096
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagPrefix = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1u;
 
 __global__ void __launch_bounds__(256)
 build_keys_kernel(const double *__restrict__ r_ratio, const double *__restrict__ r_p,
                   const int32_t *__restrict__ r_rank, const int32_t *__restrict__ r_comp,
-                  int sort_key, int64_t n, uint32_t *__restrict__ k0, uint32_t *__restrict__ k1,
-                  uint32_t *__restrict__ k2, uint32_t *__restrict__ k3,
-                  uint32_t *__restrict__ perm, uint32_t *__restrict__ or_and) {
+                  int sort_key, int64_t n, unsigned long long *__restrict__ key,
+                  uint32_t *__restrict__ val, uint32_t *__restrict__ or_and) {
     uint32_t o[4] = {0, 0, 0, 0}, a[4] = {~0u, ~0u, ~0u, ~0u};
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += int64_t(gridDim.x) * blockDim.x) {
@@ -36,113 +48,103 @@ build_keys_kernel(const double *__restrict__ r_ratio, const double *__restrict__
         } else {
             bits = ~(unsigned long long)__double_as_longlong(fabs(r_ratio[i]));
         }
-        const uint32_t w0 = uint32_t(r_rank[i]);
-        const uint32_t w1 = uint32_t(bits);
-        const uint32_t w2 = uint32_t(bits >> 32);
-        const uint32_t w3 = uint32_t(r_comp[i]);
-        k0[i] = w0; k1[i] = w1; k2[i] = w2; k3[i] = w3;
-        perm[i] = uint32_t(i);
+        key[i] = bits;
+        val[i] = uint32_t(i);
+        const uint32_t w0 = uint32_t(r_rank[i]), w3 = uint32_t(r_comp[i]);
+        const uint32_t w1 = uint32_t(bits), w2 = uint32_t(bits >> 32);
         o[0] |= w0; o[1] |= w1; o[2] |= w2; o[3] |= w3;
         a[0] &= w0; a[1] &= w1; a[2] &= w2; a[3] &= w3;
     }
+    __shared__ uint32_t so[4], sa[4];
+    if (threadIdx.x < 4) { so[threadIdx.x] = 0; sa[threadIdx.x] = ~0u; }
+    __syncthreads();
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         for (int s = 16; s > 0; s >>= 1) {
             o[w] |= __shfl_xor_sync(0xffffffffu, o[w], s);
             a[w] &= __shfl_xor_sync(0xffffffffu, a[w], s);
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicOr(or_and + w, o[w]);
-            atomicAnd(or_and + 4 + w, a[w]);
-        }
+        if ((threadIdx.x & 31) == 0) { atomicOr(&so[w], o[w]); atomicAnd(&sa[w], a[w]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        atomicOr(or_and + threadIdx.x, so[threadIdx.x]);
+        atomicAnd(or_and + 4 + threadIdx.x, sa[threadIdx.x]);
     }
 }
 
-// Per-block digit histogram: block_hist[digit * n_blocks + block].
-__global__ void __launch_bounds__(kSortThreads)
-hist_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ key, int shift, int64_t n,
-            int n_blocks, uint32_t *__restrict__ block_hist) {
+// digit of item for a pass: src 0 = byte of the carried 64-bit key, src 1 = byte of word[val]
+__device__ __forceinline__ uint32_t digit_of(int src, int shift, unsigned long long k, uint32_t v,
+                                             const uint32_t *__restrict__ word) {
+    return src == 0 ? uint32_t(k >> shift) & 255u : (__ldg(word + v) >> shift) & 255u;
+}
+
+// global histogram of the first pass
+__global__ void __launch_bounds__(256)
+first_hist_kernel(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val,
+                  int64_t n, int src, int shift, const uint32_t *__restrict__ word,
+                  uint32_t *__restrict__ hist) {
     __shared__ unsigned int h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = int64_t(blockIdx.x) * kTile;
-#pragma unroll
-    for (int it = 0; it < kItemsPerThread; ++it) {
-        const int64_t i = base + it * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&h[(key[perm[i]] >> shift) & 255u], 1u);
-    }
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += int64_t(gridDim.x) * blockDim.x)
+        atomicAdd(&h[digit_of(src, shift, key[i], val[i], word)], 1u);
     __syncthreads();
-    block_hist[size_t(threadIdx.x) * n_blocks + blockIdx.x] = h[threadIdx.x];
+    if (h[threadIdx.x]) atomicAdd(hist + threadIdx.x, h[threadIdx.x]);
 }
 
-// Exclusive scan of block_hist (digit-major) in place; one block walks 4096 entries per step.
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ data, int64_t n) {
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t chunk_total;
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024 * 4) {
-        const int64_t i0 = base + int64_t(threadIdx.x) * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < n) ? data[i0 + j] : 0u;
-        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
-        uint32_t inc = mine;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) warp_tot[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            const uint32_t w = warp_tot[lane];
-            uint32_t winc = w;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            warp_tot[lane] = winc - w;  // exclusive prefix of the warp totals
-            if (lane == 31) chunk_total = winc;
-        }
-        __syncthreads();
-        uint32_t run = carry + warp_tot[wid] + (inc - mine);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i0 + j < n) data[i0 + j] = run;
-            run += v[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += chunk_total;
-        __syncthreads();
-    }
-}
+struct PassArgs {
+    const unsigned long long *kin;
+    const uint32_t *vin;
+    unsigned long long *kout;
+    uint32_t *vout;
+    int64_t n;
+    int src, shift;              // this pass's digit
+    const uint32_t *word;        // gather source when src == 1
+    const uint32_t *hist;        // [256] global digit counts of this pass
+    uint32_t *ticket;            // tile ticket of this pass
+    uint32_t *status;            // [n_tiles][256]
+    int has_next, nsrc, nshift;  // next pass's digit (its histogram is accumulated here)
+    const uint32_t *nword;
+    uint32_t *nhist;
+};
 
-// Stable scatter of one 8-bit digit.  Tile element order = (warp, iteration, lane).
-__global__ void __launch_bounds__(kSortThreads)
-scatter_kernel(const uint32_t *__restrict__ perm_in, uint32_t *__restrict__ perm_out,
-               const uint32_t *__restrict__ key, int shift, int64_t n, int n_blocks,
-               const uint32_t *__restrict__ block_off) {
-    __shared__ unsigned int cnt[kSortThreads / 32][256];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads)
-        (&cnt[0][0])[i] = 0;
-    __syncthreads();
-
-    const int64_t warp_base = int64_t(blockIdx.x) * kTile + int64_t(wid) * (32 * kItemsPerThread);
-    uint32_t idx[kItemsPerThread];
-    uint32_t dig[kItemsPerThread];
-    uint32_t rnk[kItemsPerThread];
+__global__ void __launch_bounds__(kThreads) onesweep_pass_kernel(PassArgs A) {
+    __shared__ unsigned int cnt[kWarps][256];
+    __shared__ unsigned int goff[256];
+    __shared__ unsigned int nh[256];
+    __shared__ unsigned int wsum[kWarps];
+    __shared__ unsigned int tile_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) tile_s = atomicAdd(A.ticket, 1u);
+    nh[tid] = 0;
 #pragma unroll
-    for (int it = 0; it < kItemsPerThread; ++it) {
+    for (int w = 0; w < kWarps; ++w) cnt[w][tid] = 0;
+    __syncthreads();
+    const unsigned int tile = tile_s;
+
+    const int64_t warp_base = int64_t(tile) * kTile + int64_t(wid) * (32 * kItems);
+    unsigned long long k[kItems];
+    uint32_t v[kItems];
+    uint32_t dig[kItems];
+    uint32_t rnk[kItems];
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
         const int64_t i = warp_base + it * 32 + lane;
-        const bool in = i < n;
-        idx[it] = in ? perm_in[i] : 0u;
-        dig[it] = in ? ((key[idx[it]] >> shift) & 255u) : 256u;  // 256 = out of range
+        const bool in = i < A.n;
+        k[it] = in ? A.kin[i] : 0ull;
+        v[it] = in ? A.vin[i] : 0u;
     }
 #pragma unroll
-    for (int it = 0; it < kItemsPerThread; ++it) {
+    for (int it = 0; it < kItems; ++it) {
+        const bool in = warp_base + it * 32 + lane < A.n;
+        dig[it] = in ? digit_of(A.src, A.shift, k[it], v[it], A.word) : 256u;
+        if (A.has_next && in) atomicAdd(&nh[digit_of(A.nsrc, A.nshift, k[it], v[it], A.nword)], 1u);
+    }
+    // stable rank inside the warp's 32*kItems items, per digit
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
         const uint32_t d = dig[it];
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const unsigned lower = peers & ((1u << lane) - 1u);
@@ -154,21 +156,60 @@ scatter_kernel(const uint32_t *__restrict__ perm_in, uint32_t *__restrict__ perm
         rnk[it] = base + __popc(lower);
     }
     __syncthreads();
-    // exclusive prefix over the warps of the block, per digit, plus the global block offset
+
+    // thread d owns digit d: prefix over the warps, digit base, look-back over earlier tiles
     {
-        const int d = threadIdx.x;  // 256 threads = 256 digits
-        unsigned run = block_off[size_t(d) * n_blocks + blockIdx.x];
+        const int d = tid;
+        unsigned run = 0;
 #pragma unroll
-        for (int w = 0; w < kSortThreads / 32; ++w) {
+        for (int w = 0; w < kWarps; ++w) {
             const unsigned c = cnt[w][d];
             cnt[w][d] = run;
             run += c;
         }
+        volatile uint32_t *st = A.status + size_t(tile) * 256 + d;
+        *st = (tile == 0 ? kFlagPrefix : kFlagAggregate) | run;
+
+        // exclusive scan of the global digit histogram across the 256 threads
+        const unsigned hcount = A.hist[d];
+        unsigned inc = hcount;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        unsigned wbase = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+            if (w < wid) wbase += wsum[w];
+        const unsigned digit_base = wbase + inc - hcount;
+
+        unsigned excl = 0;
+        if (tile > 0) {
+            int64_t t = int64_t(tile) - 1;
+            for (;;) {
+                const volatile uint32_t *ps = A.status + size_t(t) * 256 + d;
+                uint32_t s;
+                do { s = *ps; } while ((s >> 30) == 0u);
+                excl += s & kValueMask;
+                if (s & kFlagPrefix) break;
+                --t;
+            }
+            *st = kFlagPrefix | (excl + run);
+        }
+        goff[d] = digit_base + excl;
+        if (A.has_next && nh[d]) atomicAdd(A.nhist + d, nh[d]);
     }
     __syncthreads();
 #pragma unroll
-    for (int it = 0; it < kItemsPerThread; ++it) {
-        if (dig[it] < 256u) perm_out[cnt[wid][dig[it]] + rnk[it]] = idx[it];
+    for (int it = 0; it < kItems; ++it) {
+        const uint32_t d = dig[it];
+        if (d < 256u) {
+            const uint32_t pos = goff[d] + cnt[wid][d] + rnk[it];
+            A.kout[pos] = k[it];
+            A.vout[pos] = v[it];
+        }
     }
 }
 
@@ -192,11 +233,13 @@ gather_kernel(const uint32_t *__restrict__ perm, int64_t n, const int32_t *__res
 inline int blocks_for(int64_t n, int per) {
     int64_t b = (n + per - 1) / per;
     if (b < 1) b = 1;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > 148 * 8) b = 148 * 8;
     return int(b);
 }
 
 }  // namespace
+
+size_t sort_status_words(int64_t n) { return size_t((n + kTile - 1) / kTile) * 256; }
 
 cudaError_t launch_build_keys(const double *r_ratio, const double *r_p, const int32_t *r_rank,
                               const int32_t *r_comp, int sort_key, int64_t n, SortWorkspace &ws,
@@ -205,37 +248,66 @@ cudaError_t launch_build_keys(const double *r_ratio, const double *r_p, const in
     cudaError_t e = cudaMemcpyAsync(ws.or_and, init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     if (n == 0) return cudaSuccess;
-    build_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(r_ratio, r_p, r_rank, r_comp, sort_key, n,
-                                                         ws.keys[0], ws.keys[1], ws.keys[2],
-                                                         ws.keys[3], ws.perm_a, ws.or_and);
+    build_keys_kernel<<<blocks_for(n, 1024), 256, 0, st>>>(r_ratio, r_p, r_rank, r_comp, sort_key, n,
+                                                          ws.key_a, ws.val_a, ws.or_and);
     return cudaGetLastError();
 }
 
-cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, cudaStream_t st, uint32_t **perm_out,
-                            int *launches) {
-    *perm_out = ws.perm_a;
+cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+                            bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches) {
+    *perm_out = ws.val_a;
     if (n <= 1) return cudaSuccess;
     uint32_t oa[8];
     cudaError_t e = cudaMemcpyAsync(oa, ws.or_and, sizeof(oa), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
-    const int n_blocks = int((n + kTile - 1) / kTile);
-    uint32_t *in = ws.perm_a, *out = ws.perm_b;
-    for (int w = 0; w < 4; ++w) {
-        const uint32_t varying = oa[w] ^ oa[4 + w];  // bits that differ somewhere
-        for (int b = 0; b < 4; ++b) {
-            if (((varying >> (8 * b)) & 255u) == 0) continue;  // constant digit: order unchanged
-            hist_kernel<<<n_blocks, kSortThreads, 0, st>>>(in, ws.keys[w], 8 * b, n, n_blocks,
-                                                           ws.block_hist);
-            scan_kernel<<<1, 1024, 0, st>>>(ws.block_hist, int64_t(256) * n_blocks);
-            scatter_kernel<<<n_blocks, kSortThreads, 0, st>>>(in, out, ws.keys[w], 8 * b, n, n_blocks,
-                                                              ws.block_hist);
-            if (launches) *launches += 3;
-            uint32_t *t = in; in = out; out = t;
+
+    struct Pass { int src, shift; const uint32_t *word; };
+    Pass passes[16];
+    int np = 0;
+    auto varying = [&](int w, int b) { return (((oa[w] ^ oa[4 + w]) >> (8 * b)) & 255u) != 0; };
+    if (!rank_presorted)
+        for (int b = 0; b < 4; ++b)
+            if (varying(0, b)) passes[np++] = Pass{1, 8 * b, reinterpret_cast<const uint32_t *>(r_rank)};
+    for (int b = 0; b < 8; ++b)
+        if (varying(1 + b / 4, b % 4)) passes[np++] = Pass{0, 8 * b, nullptr};
+    for (int b = 0; b < 4; ++b)
+        if (varying(3, b)) passes[np++] = Pass{1, 8 * b, reinterpret_cast<const uint32_t *>(r_comp)};
+    if (np == 0) return cudaSuccess;
+
+    const int n_tiles = int((n + kTile - 1) / kTile);
+    const size_t status_words = size_t(n_tiles) * 256;
+    // control block: [16][256] histograms, [16] tickets, then per-pass status arrays
+    e = cudaMemsetAsync(ws.control, 0, (size_t(16) * 256 + 16) * 4 + size_t(np) * status_words * 4, st);
+    if (e != cudaSuccess) return e;
+    uint32_t *hist = ws.control;
+    uint32_t *ticket = ws.control + 16 * 256;
+    uint32_t *status = ws.control + 16 * 256 + 16;
+
+    first_hist_kernel<<<blocks_for(n, 2048), 256, 0, st>>>(ws.key_a, ws.val_a, n, passes[0].src,
+                                                           passes[0].shift, passes[0].word, hist);
+    if (launches) ++*launches;
+    unsigned long long *kin = ws.key_a, *kout = ws.key_b;
+    uint32_t *vin = ws.val_a, *vout = ws.val_b;
+    for (int p = 0; p < np; ++p) {
+        PassArgs a{};
+        a.kin = kin; a.vin = vin; a.kout = kout; a.vout = vout; a.n = n;
+        a.src = passes[p].src; a.shift = passes[p].shift; a.word = passes[p].word;
+        a.hist = hist + p * 256;
+        a.ticket = ticket + p;
+        a.status = status + size_t(p) * status_words;
+        a.has_next = p + 1 < np;
+        if (a.has_next) {
+            a.nsrc = passes[p + 1].src; a.nshift = passes[p + 1].shift; a.nword = passes[p + 1].word;
+            a.nhist = hist + (p + 1) * 256;
         }
+        onesweep_pass_kernel<<<n_tiles, kThreads, 0, st>>>(a);
+        if (launches) ++*launches;
+        unsigned long long *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
     }
-    *perm_out = in;
+    *perm_out = vin;
     return cudaGetLastError();
 }
 
