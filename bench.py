@@ -57,33 +57,99 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md).
+    NVML is polled from a thread every ~1 ms (the C-ABI calls release the GIL); a timed region of a
+    few milliseconds is far too short for `nvidia-smi -lms`, which is only the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None):
         self.gpu = gpu_index
+        self.uuid = uuid
+        self.samples = []      # (sm_mhz, reasons bitmask, power_w)
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nv = None
+        self.handle = None
+        self.sm_max = None
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(self.uuid.encode() if hasattr(self.uuid, "encode") else self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = self.gpu
+                if vis:
+                    ent = vis.split(",")[self.gpu].strip()
+                    if ent.isdigit():
+                        idx = int(ent)
+                    else:
+                        h = nv.nvmlDeviceGetHandleByUUID(ent.encode())
+                if h is None:
+                    h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.handle = nv, h
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((sm, rs, pw))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self) -> dict:
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.thread.join(2)
+            nv = self.nv
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                     "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+            reasons = sorted(n for n, bit in names.items() if any(s[1] & bit for s in self.samples))
+            sm = [s[0] for s in self.samples]
+            pw = [s[2] for s in self.samples if s[2] is not None]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(sm), "power_w_max": max(pw) if pw else None, "reasons": reasons,
+                    "source": "NVML polled every ~1 ms during the timed region"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -104,7 +170,7 @@ class ClockSampler:
                 if v.lower() == "active":
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 def cpu_baseline(sample_rows: int, threads: int, reference_style: bool = True):
@@ -164,7 +230,7 @@ def run_reference(args):
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="marker rows per GPU")
@@ -215,7 +281,11 @@ def main() -> int:
     for _ in range(args.warmup):
         ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, total_rows)
     barrier()
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

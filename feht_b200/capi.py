@@ -319,9 +319,10 @@ class Context:
                                               g("p"), g("ratio"), g("name_rank")))
 
     def timings(self) -> dict:
-        buf = (C.c_double * 7)()
-        self._check(self._L.feht_last_timings(self._h, buf, 7))
-        keys = ["count_ms", "test_ms", "order_ms", "total_ms", "launches", "count_launches", "count_bytes"]
+        buf = (C.c_double * 8)()
+        self._check(self._L.feht_last_timings(self._h, buf, 8))
+        keys = ["count_ms", "test_ms", "order_ms", "total_ms", "launches", "count_launches", "count_bytes",
+                "engine"]
         return dict(zip(keys, list(buf)))
 
     def eval_tables(self, goa, gob, gta, gtb):

@@ -69,6 +69,11 @@ struct feht_ctx {
 
     // scratch for a run
     DevBuf<uint4> masks;
+    DevBuf<uint8_t> gemm_b;          // baked one-hot B blocks of all GEMM passes
+    DevBuf<unsigned char> gemm_passes;
+    int gemm_n_passes = 0;
+    bool gemm_ready = false;         // gemm_b / gemm_passes match the current categories
+    int last_engine = 0;             // engine the last run counted categories with
     DevBuf<int4> counts;
     DevBuf<CompDesc> descs;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
@@ -190,6 +195,8 @@ int check_mode(feht_ctx *c, int snp) {
 }
 
 constexpr size_t kStageBytes = size_t(96) << 20;
+// AUTO engine: categories go to the GEMM from this many pair-slots on (measured crossover)
+constexpr int kGemmAutoMinSlots = 8;
 
 // Upload `total` bytes from host in pieces chosen by `next_piece` and hand each staged piece to
 // `consume(dev_ptr, piece_index)` on the context stream; two staging buffers so that the copy of
@@ -344,7 +351,7 @@ int add_packed_common(feht_ctx *c, const uint64_t *const *src_planes, const int 
 }  // namespace
 
 // =================================================================================== context ==
-extern "C" const char *feht_version(void) { return "feht_b200 0.1 (sm_100a; K0 pack, K1 popc, K3 fet, K4 sort)"; }
+extern "C" const char *feht_version(void) { return "feht_b200 0.2 (sm_100a; K0 pack, K1 popc, K2 i8 tcgen05 gemm, K3 fet, K4 sort)"; }
 
 extern "C" int feht_create(feht_ctx **out, int device) {
     if (!out) return fail(nullptr, FEHT_E_INVALID, "out is null");
@@ -395,6 +402,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int i = 0; i < 3; ++i) if (c->plane[i]) cudaFree(c->plane[i]);
     release(c->rank); release(c->stage[0]); release(c->stage[1]);
+    release(c->gemm_b); release(c->gemm_passes);
     release(c->masks); release(c->counts); release(c->descs); release(c->seg_count); release(c->seg_base);
     release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
     release(c->r_cnt); release(c->o_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
@@ -427,6 +435,7 @@ extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
     if (int rc = use_device(c)) return rc;
     CU(c, cudaStreamSynchronize(c->st));
     for (int i = 0; i < 3; ++i) { if (c->plane[i]) cudaFree(c->plane[i]); c->plane[i] = nullptr; }
+    c->gemm_ready = false;
     c->S = n_samples;
     c->W = ((n_samples + 63) / 64 + 1) & ~int64_t(1);  // even number of 64-bit words: 16-byte rows
     c->snp = -1;
@@ -540,6 +549,7 @@ extern "C" int64_t feht_add_comparison(feht_ctx *c, const int32_t *g1, int64_t n
     for (int32_t v : cp.g1) { if (v < 0) return fail(c, FEHT_E_BOUNDS, "negative column index"); cp.max_col = std::max<int64_t>(cp.max_col, v); }
     for (int32_t v : cp.g2) { if (v < 0) return fail(c, FEHT_E_BOUNDS, "negative column index"); cp.max_col = std::max<int64_t>(cp.max_col, v); }
     c->comps.push_back(std::move(cp));
+    c->gemm_ready = false;  // explicit slots come first: the categories' slot base moves
     c->has_results = false;
     return int64_t(c->comps.size()) - 1;
 }
@@ -558,6 +568,7 @@ extern "C" int64_t feht_add_category(feht_ctx *c, const int32_t *value_of_sample
     }
     const int ci = int(c->cats.size());
     c->cats.push_back(std::move(cat));
+    c->gemm_ready = false;
     const int64_t first = int64_t(c->comps.size());
     for (int i = 0; i < n_values; ++i)
         for (int j = i + 1; j < n_values; ++j) {
@@ -577,6 +588,7 @@ extern "C" int feht_clear_comparisons(feht_ctx *c) {
     if (!c) return FEHT_E_INVALID;
     c->comps.clear();
     c->cats.clear();
+    c->gemm_ready = false;
     c->has_results = false;
     return FEHT_OK;
 }
@@ -671,8 +683,7 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
             }
             descs[size_t(i)] = d;
         }
-        (void)n_explicit;
-        for (size_t k = 0; k < c->cats.size(); ++k) {
+                for (size_t k = 0; k < c->cats.size(); ++k) {
             const Cat &cat = c->cats[k];
             for (int64_t s = 0; s < c->S; ++s) {
                 const int v = cat.value_of_sample[size_t(s)];
@@ -692,14 +703,74 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
 
     int launches = 0, count_launches = 0;
-    // ---- K1 count
+    // ---- counting engine: explicit comparisons always go to K1; whole categories go to the int8
+    // tcgen05 GEMM (K2) when asked for, or by default once there are enough value columns for the
+    // tensor pipe to beat one masked popcount stream per value pair.
+    const int n_cat_slots = n_slots - n_explicit;
+    bool use_gemm = false;
+    if (c->engine == FEHT_ENGINE_GEMM) {
+        if (c->snp == 1) return fail(c, FEHT_E_INVALID, "the GEMM counting engine handles binary rows only");
+        if (n_cat_slots == 0) return fail(c, FEHT_E_INVALID, "the GEMM counting engine needs a category (feht_add_category)");
+        use_gemm = true;
+    } else if (c->engine == FEHT_ENGINE_AUTO) {
+        use_gemm = c->snp != 1 && n_cat_slots >= kGemmAutoMinSlots;
+    }
+    if (use_gemm && !c->gemm_ready) {
+        const int per_pass = gemm_max_pairs_per_pass();
+        const int n_passes = (n_cat_slots + per_pass - 1) / per_pass;
+        const int n_stages = gemm_stage_count(c->S);
+        // GEMM column gc = 2 * (slot - n_explicit) + sel  ->  list of samples with a 1
+        std::vector<std::vector<int32_t>> cols(size_t(n_cat_slots) * 2);
+        for (size_t k = 0; k < c->cats.size(); ++k) {
+            const Cat &cat = c->cats[k];
+            for (int64_t s = 0; s < c->S; ++s) {
+                const int v = cat.value_of_sample[size_t(s)];
+                if (v < 0) continue;
+                cols[size_t(cat_slot0[k] - n_explicit + v / 2) * 2 + size_t(v & 1)].push_back(int32_t(s));
+                if (cat_tot[k] >= 0) cols[size_t(cat_tot[k] - n_explicit) * 2].push_back(int32_t(s));
+            }
+        }
+        std::vector<unsigned char> hpass(size_t(n_passes) * gemm_pass_desc_bytes());
+        std::vector<int> pad(static_cast<size_t>(n_passes));
+        size_t total = 0;
+        for (int p = 0; p < n_passes; ++p) {
+            const int pairs = std::min(per_pass, n_cat_slots - p * per_pass);
+            pad[size_t(p)] = ((2 * pairs + 15) / 16) * 16;
+            gemm_fill_pass(hpass.data() + size_t(p) * gemm_pass_desc_bytes(), n_explicit + p * per_pass, pairs,
+                           pad[size_t(p)], int64_t(total));
+            total += size_t(n_stages) * size_t(pad[size_t(p)]) * 128;
+        }
+        std::vector<uint8_t> hb(total);
+        size_t off = 0;
+        for (int p = 0; p < n_passes; ++p) {
+            const int pairs = std::min(per_pass, n_cat_slots - p * per_pass);
+            std::vector<std::vector<int32_t>> pc(cols.begin() + size_t(p) * per_pass * 2,
+                                                 cols.begin() + size_t(p) * per_pass * 2 + size_t(pairs) * 2);
+            gemm_bake_b(pc, pad[size_t(p)], c->S, hb.data() + off);
+            off += size_t(n_stages) * size_t(pad[size_t(p)]) * 128;
+        }
+        CU(c, ensure(c->gemm_b, total));
+        CU(c, ensure(c->gemm_passes, hpass.size()));
+        CU(c, cudaMemcpyAsync(c->gemm_b.p, hb.data(), total, cudaMemcpyHostToDevice, c->st));
+        CU(c, cudaMemcpyAsync(c->gemm_passes.p, hpass.data(), hpass.size(), cudaMemcpyHostToDevice, c->st));
+        CU(c, cudaStreamSynchronize(c->st));  // the host vectors die here
+        c->gemm_n_passes = n_passes;
+        c->gemm_ready = true;
+    }
+    c->last_engine = use_gemm ? FEHT_ENGINE_GEMM : FEHT_ENGINE_POPC;
+
     CU(c, cudaEventRecord(c->ev[0], c->st));
+    const int n_popc_slots = use_gemm ? n_explicit : n_slots;
     if (c->snp == 1)
         CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
-                                    c->masks.p, n_slots, c->counts.p, c->num_sms, c->st, &count_launches));
+                                    c->masks.p, n_popc_slots, c->counts.p, c->num_sms, c->st, &count_launches));
     else
-        CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_slots,
+        CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_popc_slots,
                                 c->counts.p, c->num_sms, c->st, &count_launches));
+    if (use_gemm)
+        CU(c, launch_count_gemm(c->plane[0], c->plane[1], c->n_units, c->W, c->S, c->gemm_b.p,
+                                c->gemm_passes.p, c->gemm_n_passes, c->counts.p, c->num_sms, c->st,
+                                &count_launches));
     launches += count_launches;
     CU(c, cudaEventRecord(c->ev[1], c->st));
 
@@ -834,9 +905,9 @@ extern "C" int feht_result_fetch(feht_ctx *c, int64_t comparison, int64_t *row, 
 
 extern "C" int feht_last_timings(const feht_ctx *c, double *out, int n) {
     if (!c || !out) return FEHT_E_INVALID;
-    const double v[7] = {c->tm.count_ms, c->tm.test_ms, c->tm.order_ms, c->tm.total_ms,
-                         c->tm.launches, c->tm.count_launches, c->tm.count_bytes};
-    for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+    const double v[8] = {c->tm.count_ms, c->tm.test_ms, c->tm.order_ms, c->tm.total_ms,
+                         c->tm.launches, c->tm.count_launches, c->tm.count_bytes, double(c->last_engine)};
+    for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
     return FEHT_OK;
 }
 

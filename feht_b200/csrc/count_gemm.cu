@@ -1,0 +1,444 @@
+// count_gemm.cu -- K2: contingency counts of whole metadata categories as an int8 tcgen05 GEMM.
+//
+// Replaces the same reference code as K1 (Comparison.hs:46-68,116-125 under /root/reference/src) for
+// the many-comparison case (getAllPermutations, Comparison.hs:319-331): a category with V values
+// yields V(V-1)/2 pairs + V one-vs-rest comparisons, but every one of their 2x2 tables is a sum or
+// difference of the per-value counts
+//     P[row][v] = #{s : value(s) = v, call(row,s) = '1'}      N[row][v] = #{s : value(s) = v, call valid}
+// i.e. two dense contractions  [rows x samples](bits) . [samples x values](one-hot)  -- a GEMM with
+// M = marker rows, K = samples, N = value columns (+ one "whole category" column per category for
+// the one-vs-rest tables), exact in s32.  This is the only use of tensor cores in the library.
+//
+// Mapping onto sm_100a (DESIGN.md "K2"):
+//   * A (1 bit per call in HBM) is never expanded in memory.  A TMA tensor map streams a
+//     [256 rows x 128 B] box of each bit-plane into 128B-swizzled shared memory; 8 "expander" warps
+//     (one thread per marker row = one TMEM lane) read 16 B of their row, blow the bits up to 0/1
+//     bytes in registers (2 ALU ops per 4 calls) and write them straight into TENSOR MEMORY with
+//     tcgen05.st, where tcgen05.mma takes its A operand from ([a_tmem] form).  Shared-memory
+//     bandwidth is therefore spent on the 1-bit data and the B tiles only.
+//   * B (one-hot, int8, K-major) is baked by the host into the exact 128B-swizzled core-matrix
+//     byte order the UMMA shared-memory descriptor expects, one contiguous N x 128 B block per
+//     128-sample stage, so a plain 1-D bulk copy (cp.async.bulk, UBLKCP) per stage suffices; the
+//     K order inside a stage is permuted to match the cheap bit expansion (see bake_b()).
+//   * D: four s32 accumulators (2 row tiles x {value, valid} plane) x N <= 64 columns live in TMEM
+//     (256 of the 512 columns; the other 256 are the double-buffered A stages).  One elected thread
+//     issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32); completion is tracked with
+//     tcgen05.commit on mbarriers.  The epilogue reads the accumulators back with tcgen05.ld and
+//     writes the int4 (P_even, N_even, P_odd, N_odd) pair-slot records K3 consumes -- the same
+//     layout K1 produces, so K3/K4 do not care which engine counted.
+//   * warp roles: 0-7 expand + epilogue, 8 TMA producer for the planes, 9 bulk-copy producer for
+//     B, 10 MMA issuer (+ TMEM allocation).  Persistent CTAs, one per SM, static tile round-robin.
+//
+// Bounds: int8 tensor pipe (2 planes x 2*S*N ops per row), the expanders' ALU issue rate
+// (~36 instructions per 32 calls per row) and HBM (planes read once per pass of <= 32 value pairs).
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace feht {
+namespace {
+
+constexpr int kTileRows = 256;        // two M = 128 MMA tiles per CTA tile
+constexpr int kChunkBytes = 128;      // bytes of a plane row per TMA box = 1024 samples
+constexpr int kStageSamples = 128;    // samples per pipeline stage = 16 B of a plane row = 4 MMA K steps
+constexpr int kStagesPerChunk = kChunkBytes * 8 / kStageSamples;  // 8
+constexpr int kNMax = 64;             // value columns per pass
+constexpr int kBStageBytes = kNMax * 128;
+constexpr int kBStages = 6;
+constexpr int kPlaneTileBytes = kTileRows * kChunkBytes;  // 32 KiB
+constexpr int kExpandWarps = 8;
+constexpr int kThreads = (kExpandWarps + 3) * 32;
+constexpr int kTmemCols = 512;
+constexpr int kTmemAccBase = 0;       // + (mt * 2 + plane) * 64
+constexpr int kTmemABase = 256;       // + buf * 128 + (mt * 2 + plane) * 32
+
+// shared memory carve-up (dynamic, 1024-byte aligned base)
+constexpr int kSmemPlanes = 0;                                     // [2 buf][2 plane][32 KiB]
+constexpr int kSmemB = kSmemPlanes + 4 * kPlaneTileBytes;          // [kBStages][8 KiB]
+constexpr int kSmemBars = kSmemB + kBStages * kBStageBytes;        // mbarriers
+constexpr int kNumBars = 2 + 2 + kBStages * 2 + 2 + 2 + 2;
+constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
+constexpr int kSmemTotal = kSmemTmemPtr + 16 + 1024;               // + slack for manual alignment
+
+struct GemmPass {
+    int32_t slot_base;   // first pair-slot written by this pass
+    int32_t n_pairs;     // pair-slots written (<= n_pad / 2)
+    int32_t n_pad;       // GEMM N of this pass: multiple of 16, <= 64
+    int32_t pad;
+    int64_t b_offset;    // byte offset of the pass's baked B blocks: [n_stages][n_pad * 128]
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *map, int x, int y,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void *gsrc, uint32_t bytes,
+                                             uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]; one thread issues for the CTA
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
+}
+
+// 32 calls (one word of a bit-plane row) -> 8 TMEM columns of 4 int8 each.  Column j, byte b holds
+// call (8*b + j): y_j = (w >> j) & 0x01010101.  bake_b() orders B's K dimension the same way.
+__device__ __forceinline__ void expand_store(uint32_t taddr, uint32_t w) {
+    uint32_t y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = (w >> j) & 0x01010101u;
+    tmem_st8(taddr, y);
+}
+
+// UMMA shared-memory descriptor: K-major, 128B swizzle, 8-row core-matrix groups 1024 B apart
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);       // start address, 16-byte units
+    d |= uint64_t(1) << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= uint64_t(1024 >> 4) << 32;                   // stride byte offset: 8 rows x 128 B
+    d |= uint64_t(1) << 46;                           // descriptor version (sm_100)
+    d |= uint64_t(2) << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tm_valid,
+                  const uint8_t *__restrict__ bmat, const GemmPass *__restrict__ passes, int n_stages,
+                  int64_t n_rows, int n_tiles, int4 *__restrict__ counts) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char *base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t bars = base + kSmemBars;
+    // barrier indices
+    const uint32_t a_full = bars + 0 * 8;             // [2]  planes landed in smem
+    const uint32_t a_empty = bars + 2 * 8;            // [2]  expanders done with a plane buffer
+    const uint32_t b_full = bars + 4 * 8;             // [kBStages]
+    const uint32_t b_empty = b_full + kBStages * 8;   // [kBStages]
+    const uint32_t ta_full = b_empty + kBStages * 8;  // [2]  A stage written to TMEM
+    const uint32_t ta_empty = ta_full + 2 * 8;        // [2]  MMAs of the stage retired
+    const uint32_t acc_full = ta_empty + 2 * 8;       // accumulators complete
+    const uint32_t acc_empty = acc_full + 8;          // epilogue drained TMEM
+    volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(base_ptr + kSmemTmemPtr);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GemmPass pass = passes[blockIdx.y];
+    const int n_pad = pass.n_pad;
+    const uint32_t b_bytes = uint32_t(n_pad) * 128u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(a_full + i * 8, 1);
+            mbar_init(a_empty + i * 8, kExpandWarps);
+            mbar_init(ta_full + i * 8, kExpandWarps);
+            mbar_init(ta_empty + i * 8, 1);
+        }
+        for (int i = 0; i < kBStages; ++i) {
+            mbar_init(b_full + i * 8, 1);
+            mbar_init(b_empty + i * 8, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, kExpandWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kExpandWarps + 2) {  // the MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(const_cast<uint32_t *>(tmem_ptr_smem))), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n_chunks = (n_stages + kStagesPerChunk - 1) / kStagesPerChunk;
+
+    if (warp < kExpandWarps) {
+        // =============================================== expanders + epilogue: thread = marker row
+        const int r = threadIdx.x;                 // row inside the 256-row tile
+        const int mt = r >> 7;                     // M tile
+        const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+        const uint32_t row_off = uint32_t(r) * kChunkBytes;
+        const uint32_t sw = uint32_t(r & 7);
+        uint32_t chunk_ctr = 0, stage_ctr = 0, tile_ctr = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
+            for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+                const uint32_t cb = chunk_ctr & 1;
+                mbar_wait(a_full + cb * 8, (chunk_ctr >> 1) & 1);
+                const unsigned char *pv = base_ptr + kSmemPlanes + (cb * 2 + 0) * kPlaneTileBytes + row_off;
+                const unsigned char *pd = base_ptr + kSmemPlanes + (cb * 2 + 1) * kPlaneTileBytes + row_off;
+                const int st_n = min(kStagesPerChunk, n_stages - ch * kStagesPerChunk);
+                for (int st = 0; st < st_n; ++st, ++stage_ctr) {
+                    const uint32_t phys = (uint32_t(st) ^ sw) << 4;  // TMA 128B swizzle: chunk ^= row % 8
+                    const uint4 v = *reinterpret_cast<const uint4 *>(pv + phys);
+                    const uint4 d = *reinterpret_cast<const uint4 *>(pd + phys);
+                    const uint32_t tb = stage_ctr & 1;
+                    mbar_wait(ta_empty + tb * 8, ((stage_ctr >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + lane_addr + kTmemABase + tb * 128 + (mt * 2) * 32;
+                    expand_store(ta + 0, v.x);
+                    expand_store(ta + 8, v.y);
+                    expand_store(ta + 16, v.z);
+                    expand_store(ta + 24, v.w);
+                    expand_store(ta + 32 + 0, d.x);
+                    expand_store(ta + 32 + 8, d.y);
+                    expand_store(ta + 32 + 16, d.z);
+                    expand_store(ta + 32 + 24, d.w);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ta_full + tb * 8);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_empty + cb * 8);
+            }
+            // ---- epilogue: accumulators -> pair-slot records
+            mbar_wait(acc_full, tile_ctr & 1);
+            tc_fence_after();
+            const int64_t row = int64_t(tile) * kTileRows + r;
+            const uint32_t acc_p = tmem_base + lane_addr + kTmemAccBase + (mt * 2 + 0) * 64;
+            const uint32_t acc_n = tmem_base + lane_addr + kTmemAccBase + (mt * 2 + 1) * 64;
+            for (int c0 = 0; c0 < n_pad; c0 += 16) {
+                uint32_t P[16], N[16];
+                tmem_ld16(acc_p + c0, P);
+                tmem_ld16(acc_n + c0, N);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < n_rows) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int pair = (c0 >> 1) + j;
+                        if (pair < pass.n_pairs)
+                            counts[size_t(pass.slot_base + pair) * size_t(n_rows) + size_t(row)] =
+                                make_int4(int(P[2 * j]), int(N[2 * j]), int(P[2 * j + 1]), int(N[2 * j + 1]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    } else if (warp == kExpandWarps) {
+        // =============================================== TMA producer: bit-plane boxes
+        if (lane == 0) {
+            uint32_t chunk_ctr = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+                    const uint32_t cb = chunk_ctr & 1;
+                    mbar_wait(a_empty + cb * 8, ((chunk_ctr >> 1) & 1) ^ 1);
+                    mbar_expect_tx(a_full + cb * 8, 2u * kPlaneTileBytes);
+                    tma_load_2d(base + kSmemPlanes + (cb * 2 + 0) * kPlaneTileBytes, &tm_value,
+                                ch * kChunkBytes, tile * kTileRows, a_full + cb * 8);
+                    tma_load_2d(base + kSmemPlanes + (cb * 2 + 1) * kPlaneTileBytes, &tm_valid,
+                                ch * kChunkBytes, tile * kTileRows, a_full + cb * 8);
+                }
+            }
+        }
+    } else if (warp == kExpandWarps + 1) {
+        // =============================================== bulk-copy producer: baked one-hot B blocks
+        if (lane == 0) {
+            uint32_t stage_ctr = 0;
+            const uint8_t *bsrc = bmat + pass.b_offset;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                    const uint32_t bs = stage_ctr % kBStages;
+                    mbar_wait(b_empty + bs * 8, ((stage_ctr / kBStages) & 1) ^ 1);
+                    mbar_expect_tx(b_full + bs * 8, b_bytes);
+                    bulk_load_1d(base + kSmemB + bs * kBStageBytes, bsrc + size_t(s) * b_bytes, b_bytes,
+                                 b_full + bs * 8);
+                }
+            }
+        }
+    } else {
+        // =============================================== MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D s32, A/B unsigned 8-bit, both K-major, N = n_pad, M = 128
+            const uint32_t idesc = (2u << 4) | (uint32_t(n_pad >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+            uint32_t stage_ctr = 0, tile_ctr = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
+                mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
+                tc_fence_after();
+                for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                    const uint32_t tb = stage_ctr & 1;
+                    const uint32_t bs = stage_ctr % kBStages;
+                    mbar_wait(ta_full + tb * 8, (stage_ctr >> 1) & 1);
+                    mbar_wait(b_full + bs * 8, (stage_ctr / kBStages) & 1);
+                    tc_fence_after();
+                    const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kBStageBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {  // q = mt * 2 + plane
+                            mma_i8_ts(tmem_base + kTmemAccBase + q * 64,
+                                      tmem_base + kTmemABase + tb * 128 + q * 32 + ks * 8,
+                                      bdesc + uint64_t(ks * 2), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(ta_empty + tb * 8);
+                    tc_commit(b_empty + bs * 8);
+                }
+                tc_commit(acc_full);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kExpandWarps + 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// [rows][W*8 bytes] plane -> boxes of [256 rows][128 bytes], 128B swizzle, zero fill outside
+bool make_plane_map(CUtensorMap *map, const uint64_t *plane, int64_t n_rows, int64_t W) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cuuint64_t(W) * 8, cuuint64_t(n_rows)};
+    const cuuint64_t strides[1] = {cuuint64_t(W) * 8};
+    const cuuint32_t box[2] = {cuuint32_t(kChunkBytes), cuuint32_t(kTileRows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint64_t *>(plane), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int gemm_stage_count(int64_t S) { return int((S + kStageSamples - 1) / kStageSamples); }
+size_t gemm_pass_desc_bytes() { return sizeof(GemmPass); }
+int gemm_max_pairs_per_pass() { return kNMax / 2; }
+
+// One pass = up to 32 consecutive pair-slots (64 value columns).  columns[c] lists, for GEMM column c
+// of the pass, which samples carry a 1 (built by capi.cu from the categories).  Writes the baked B
+// blocks [n_stages][n_pad][128] (128B-swizzled, K permuted to the expander's order) at `out`.
+void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, uint8_t *out) {
+    const int n_stages = gemm_stage_count(S);
+    std::memset(out, 0, size_t(n_stages) * size_t(n_pad) * 128);
+    for (size_t n = 0; n < columns.size(); ++n) {
+        for (int32_t s : columns[n]) {
+            const int64_t g = s / kStageSamples;       // stage
+            const int w = int(s % kStageSamples);
+            const int i = w >> 5, bit = w & 31;        // word of the 16-byte stage row, bit in the word
+            const int b = bit >> 3, j = bit & 7;       // expander: column j, byte b holds call 8*b + j
+            const int kk = 32 * i + 4 * j + b;         // K position inside the stage
+            const size_t off = size_t(g) * size_t(n_pad) * 128 + n * 128 +
+                               size_t((((kk >> 4) ^ int(n & 7)) << 4) + (kk & 15));
+            out[off] = 1;
+        }
+    }
+}
+
+void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_offset) {
+    GemmPass p{};
+    p.slot_base = slot_base;
+    p.n_pairs = n_pairs;
+    p.n_pad = n_pad;
+    p.b_offset = b_offset;
+    std::memcpy(dst, &p, sizeof(p));
+}
+
+cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
+                              int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
+                              int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+    if (n_rows == 0 || n_passes == 0) return cudaSuccess;
+    CUtensorMap tm_value, tm_valid;
+    if (!make_plane_map(&tm_value, d_value, n_rows, W) || !make_plane_map(&tm_valid, d_valid, n_rows, W))
+        return cudaErrorNotSupported;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(count_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int n_tiles = int((n_rows + kTileRows - 1) / kTileRows);
+    int gx = num_sms / n_passes;
+    if (gx < 1) gx = 1;
+    if (gx > n_tiles) gx = n_tiles;
+    // every pass gets its own set of persistent CTAs; with one pass this is one CTA per SM
+    count_gemm_kernel<<<dim3(unsigned(gx), unsigned(n_passes)), kThreads, kSmemTotal, st>>>(
+        tm_value, tm_valid, d_bmat, static_cast<const GemmPass *>(d_passes), gemm_stage_count(S), n_rows,
+        n_tiles, d_counts);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace feht

@@ -181,7 +181,8 @@ int feht_set_row_base(feht_ctx *ctx, int64_t row_base);
 
 /* Device-side milliseconds of the last feht_run, by stage (CUDA events on the run's stream):
  * out[0] count, out[1] test+correct+filter, out[2] order, out[3] total, out[4] launches (count),
- * out[5] count-kernel launches, out[6] algorithmic bytes read by the count stage. */
+ * out[5] count-kernel launches, out[6] algorithmic bytes read by the count stage,
+ * out[7] engine that counted the categories (FEHT_ENGINE_POPC or FEHT_ENGINE_GEMM). */
 int feht_last_timings(const feht_ctx *ctx, double *out, int n);
 
 /*
