@@ -75,7 +75,9 @@ struct feht_ctx {
     bool gemm_ready = false;         // gemm_b / gemm_passes match the current categories
     int last_engine = 0;             // engine the last run counted categories with
     DevBuf<int4> counts;
-    DevBuf<CompDesc> descs;
+    DevBuf<ScreenGroup> groups;
+    DevBuf<FracDef> fracs;
+    DevBuf<GroupComp> gcomps;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
     DevBuf<long long> seg_base;
     DevBuf<int32_t> r_comp, r_row, r_rank, o_row, o_rank;
@@ -403,7 +405,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     for (int i = 0; i < 3; ++i) if (c->plane[i]) cudaFree(c->plane[i]);
     release(c->rank); release(c->stage[0]); release(c->stage[1]);
     release(c->gemm_b); release(c->gemm_passes);
-    release(c->masks); release(c->counts); release(c->descs); release(c->seg_count); release(c->seg_base);
+    release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->seg_count); release(c->seg_base);
     release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
     release(c->r_cnt); release(c->o_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
@@ -646,10 +648,9 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
             return fail(c, FEHT_E_BOUNDS, "index out of bounds: column %lld referenced, shortest row has %lld characters",
                         (long long)cp.max_col, (long long)row_len);
 
-    // ---- slots and descriptors
+    // ---- pair-slots (what K1/K2 count) and screen groups (what K3a tests)
     const PopcPlan plan = make_popc_plan(c->W);
     const size_t mrow = size_t(plan.w4pad) * 2;  // 64-bit words per padded mask row
-    std::vector<CompDesc> descs(static_cast<size_t>(n_comps));
     std::vector<int> cat_slot0(c->cats.size(), -1), cat_tot(c->cats.size(), -1);
     int n_slots = 0;
     for (int i = 0; i < n_comps; ++i) if (c->comps[size_t(i)].kind == 0) ++n_slots;
@@ -663,43 +664,96 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
         return fail(c, FEHT_E_INVALID, "mask storage too large");
     std::vector<uint64_t> hmask(size_t(n_slots) * 2 * mrow, 0);
     auto mask_row = [&](int slot, int which) { return hmask.data() + (size_t(slot) * 2 + which) * mrow; };
+    std::vector<ScreenGroup> groups;
+    std::vector<FracDef> fracs;
+    std::vector<GroupComp> gcomps;
+    int max_frac = 0, max_comp = 0;
     {
+        // explicit comparisons: one pair-slot each, groups of up to 64
+        constexpr int kExplicitPerGroup = 64;
+        std::vector<int> cat_first(c->cats.size(), -1);  // first comparison index of each category
         int e = 0;
         for (int i = 0; i < n_comps; ++i) {
             const Comp &cp = c->comps[size_t(i)];
-            CompDesc d{};
-            d.kind = cp.kind;
-            if (cp.kind == 0) {
-                uint64_t *m1 = mask_row(e, 0), *m2 = mask_row(e, 1);
-                for (int32_t col : cp.g1) m1[col >> 6] |= 1ULL << (col & 63);
-                for (int32_t col : cp.g2) m2[col >> 6] |= 1ULL << (col & 63);
-                d.slot_a = e; d.sel_a = 0; d.slot_b = e; d.sel_b = 1; d.slot_tot = e;
-                ++e;
-            } else {
-                const int s0 = cat_slot0[size_t(cp.cat)];
-                d.slot_a = s0 + cp.v1 / 2; d.sel_a = cp.v1 & 1;
-                if (cp.kind == 1) { d.slot_b = s0 + cp.v2 / 2; d.sel_b = cp.v2 & 1; d.slot_tot = d.slot_a; }
-                else { d.slot_b = d.slot_a; d.sel_b = d.sel_a; d.slot_tot = cat_tot[size_t(cp.cat)]; }
+            if (cp.kind != 0) {
+                if (cat_first[size_t(cp.cat)] < 0) cat_first[size_t(cp.cat)] = i;
+                continue;
             }
-            descs[size_t(i)] = d;
+            uint64_t *m1 = mask_row(e, 0), *m2 = mask_row(e, 1);
+            for (int32_t col : cp.g1) m1[col >> 6] |= 1ULL << (col & 63);
+            for (int32_t col : cp.g2) m2[col >> 6] |= 1ULL << (col & 63);
+            if (groups.empty() || groups.back().n_comp >= kExplicitPerGroup || e % kExplicitPerGroup == 0)
+                groups.push_back(ScreenGroup{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0});
+            ScreenGroup &g = groups.back();
+            fracs.push_back(FracDef{e, 0, -1, 0});
+            fracs.push_back(FracDef{e, 1, -1, 0});
+            gcomps.push_back(GroupComp{i, int16_t(g.n_frac), int16_t(g.n_frac + 1)});
+            g.n_frac += 2;
+            g.n_comp += 1;
+            ++e;
         }
-                for (size_t k = 0; k < c->cats.size(); ++k) {
+        // categories: value blocks of 64; group (a,b) holds the pairs between blocks a <= b, the
+        // diagonal groups also hold the one-vs-rest comparisons of their block
+        constexpr int kValueBlock = 64;
+        for (size_t k = 0; k < c->cats.size(); ++k) {
             const Cat &cat = c->cats[k];
+            const int V = cat.n_values;
             for (int64_t s = 0; s < c->S; ++s) {
                 const int v = cat.value_of_sample[size_t(s)];
                 if (v < 0) continue;
                 mask_row(cat_slot0[k] + v / 2, v & 1)[s >> 6] |= 1ULL << (s & 63);
                 if (cat_tot[k] >= 0) mask_row(cat_tot[k], 0)[s >> 6] |= 1ULL << (s & 63);
             }
+            const int first = cat_first[k];
+            auto pair_index = [&](int i, int j) { return first + i * V - i * (i + 1) / 2 + (j - i - 1); };
+            const int ova_first = first + V * (V - 1) / 2;
+            const int nb = (V + kValueBlock - 1) / kValueBlock;
+            for (int a = 0; a < nb; ++a)
+                for (int b = a; b < nb; ++b) {
+                    ScreenGroup g{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0};
+                    const int a0 = a * kValueBlock, a1 = std::min(V, a0 + kValueBlock);
+                    const int b0 = b * kValueBlock, b1 = std::min(V, b0 + kValueBlock);
+                    auto plain = [&](int v) { return FracDef{cat_slot0[k] + v / 2, v & 1, -1, 0}; };
+                    for (int v = a0; v < a1; ++v) fracs.push_back(plain(v));
+                    g.n_frac = a1 - a0;
+                    const int boff = (b == a) ? 0 : g.n_frac;   // fraction id of value b0
+                    if (b != a) {
+                        for (int v = b0; v < b1; ++v) fracs.push_back(plain(v));
+                        g.n_frac += b1 - b0;
+                    }
+                    for (int i = a0; i < a1; ++i)
+                        for (int j = std::max(b0, i + 1); j < b1; ++j) {
+                            gcomps.push_back(GroupComp{pair_index(i, j), int16_t(i - a0), int16_t(boff + j - b0)});
+                            ++g.n_comp;
+                        }
+                    if (b == a && V > 2) {   // Comparison.hs:329: one-vs-rest only with more than two values
+                        const int roff = g.n_frac;
+                        for (int v = a0; v < a1; ++v) {
+                            fracs.push_back(FracDef{cat_slot0[k] + v / 2, v & 1, cat_tot[k], 0});
+                            gcomps.push_back(GroupComp{ova_first + v, int16_t(v - a0), int16_t(roff + v - a0)});
+                        }
+                        g.n_frac += a1 - a0;
+                        g.n_comp += a1 - a0;
+                    }
+                    if (g.n_comp > 0) groups.push_back(g);
+                }
+        }
+        for (const ScreenGroup &g : groups) {
+            max_frac = std::max(max_frac, g.n_frac);
+            max_comp = std::max(max_comp, g.n_comp);
         }
     }
     CU(c, ensure(c->masks, size_t(n_slots) * 2 * plan.w4pad));
-    CU(c, ensure(c->descs, size_t(n_comps)));
+    CU(c, ensure(c->groups, groups.size()));
+    CU(c, ensure(c->fracs, fracs.size()));
+    CU(c, ensure(c->gcomps, gcomps.size()));
     CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
     CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
     CU(c, ensure(c->seg_base, size_t(n_comps)));
     CU(c, cudaMemcpyAsync(c->masks.p, hmask.data(), hmask.size() * 8, cudaMemcpyHostToDevice, c->st));
-    CU(c, cudaMemcpyAsync(c->descs.p, descs.data(), descs.size() * sizeof(CompDesc), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->groups.p, groups.data(), groups.size() * sizeof(ScreenGroup), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->fracs.p, fracs.data(), fracs.size() * sizeof(FracDef), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->gcomps.p, gcomps.data(), gcomps.size() * sizeof(GroupComp), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
 
     int launches = 0, count_launches = 0;
@@ -777,13 +831,15 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     // ---- K3 test + correct + filter
     TestParams tp{};
     tp.counts = c->counts.p;
-    tp.comps = c->descs.p;
+    tp.groups = c->groups.p;
+    tp.fracs = c->fracs.p;
+    tp.gcomps = c->gcomps.p;
+    tp.n_groups = int(groups.size());
+    tp.max_frac = max_frac;
+    tp.max_comp = max_comp;
     tp.n_rows = R;
     tp.n_comps = n_comps;
     tp.ratio_filter = ratio_filter;
-    tp.correction = correction;
-    tp.bonferroni_n = double(bonferroni_n);
-    tp.choose = c->d_choose;
     tp.name_rank = c->have_rank == 1 ? c->rank.p : nullptr;
     tp.dense = ratio_filter <= 0.0 ? 1 : 0;
     if (tp.dense && c->have_rank == 1) {
@@ -825,16 +881,9 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     CU(c, ensure(c->o_row, nn)); CU(c, ensure(c->o_rank, nn)); CU(c, ensure(c->o_cnt, nn));
     CU(c, ensure(c->o_p, nn)); CU(c, ensure(c->o_ratio, nn));
     tp.r_comp = c->r_comp.p; tp.r_row = c->r_row.p; tp.r_rank = c->r_rank.p;
-    tp.r_cnt = c->r_cnt.p; tp.r_p = c->r_p.p; tp.r_ratio = c->r_ratio.p;
+    tp.r_cnt = c->r_cnt.p; tp.r_ratio = c->r_ratio.p;
     tp.seg_count = c->seg_count.p + n_comps;  // cursors (zeroed above)
     tp.seg_base = c->seg_base.p;
-    if (n > 0) {
-        CU(c, launch_test_emit(tp, c->st));
-        ++launches;
-    }
-    CU(c, cudaEventRecord(c->ev[2], c->st));
-
-    // ---- K4 order
     if (n > 0) {
         CU(c, ensure(c->sw_key_a, nn)); CU(c, ensure(c->sw_key_b, nn));
         CU(c, ensure(c->sw_val_a, nn)); CU(c, ensure(c->sw_val_b, nn));
@@ -844,8 +893,18 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
         c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
         c->sw.control = c->sw_control.p;
         c->sw.or_and = c->sw_oa.p;
-        CU(c, launch_build_keys(c->r_ratio.p, c->r_p.p, c->r_rank.p, c->r_comp.p, sort_key, n, c->sw, c->st));
+        CU(c, launch_test_emit(tp, c->st));
         ++launches;
+        // K3b: p-values of the survivors (+ Bonferroni) and the sort keys
+        CU(c, launch_pvalues(c->r_cnt.p, c->r_ratio.p, n, c->d_choose, correction, double(bonferroni_n),
+                             c->r_p.p, sort_key, c->sw.key_a, c->sw.val_a, c->sw.or_and, c->r_rank.p,
+                             c->r_comp.p, c->st));
+        ++launches;
+    }
+    CU(c, cudaEventRecord(c->ev[2], c->st));
+
+    // ---- K4 order
+    if (n > 0) {
         uint32_t *perm = nullptr;
         CU(c, radix_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
         CU(c, launch_gather_results(perm, n, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p, c->r_ratio.p,

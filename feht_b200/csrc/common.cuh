@@ -25,15 +25,22 @@ constexpr int64_t kChooseEntries = 250500;  // sum_{n<1000} (n/2 + 1)
 // index of C[n][k'] (k' <= n/2) in the folded triangular table
 __host__ __device__ inline int choose_offset(int n) { return n + ((n - 1) * (n - 1)) / 4; }
 
-// One comparison as the device sees it: where its two (P,N) pairs live in the counts array.
-struct CompDesc {
-    int32_t kind;       // 0 explicit, 1 pair, 2 one-vs-rest
-    int32_t slot_a;     // pair-slot index holding group one
-    int32_t sel_a;      // 0: (x,y) components, 1: (z,w) components
-    int32_t slot_b;     // pair-slot of group two (kind 2: the value itself, subtracted from total)
-    int32_t sel_b;
-    int32_t slot_tot;   // kind 2: pair-slot holding the category total in (x,y)
-    int32_t pad0, pad1;
+// K3a works on GROUPS of comparisons that share a small table of per-row positive fractions.
+// A fraction is P/N of one half of a pair-slot, or, for one-vs-rest, (T_P - P)/(T_N - N) with T the
+// category's total slot.  A comparison is then two fraction ids.
+struct FracDef {
+    int32_t slot;       // pair-slot holding (P,N)
+    int32_t sel;        // 0: (x,y) components, 1: (z,w) components
+    int32_t tot_slot;   // >= 0: "rest of the category" = total slot (x,y) minus this value
+    int32_t pad;
+};
+struct GroupComp {
+    int32_t comp;       // index of the comparison in the run
+    int16_t fa, fb;     // fraction ids (inside the group) of group one / group two
+};
+struct ScreenGroup {
+    int32_t frac_off, n_frac;   // slice of the FracDef array
+    int32_t comp_off, n_comp;   // slice of the GroupComp array
 };
 
 struct Timings {
@@ -89,18 +96,19 @@ cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, 
 // fet.cu  (K3)
 struct TestParams {
     const int4 *counts;       // [n_slots][n_rows]
-    const CompDesc *comps;    // [n_comps]
+    const ScreenGroup *groups;
+    const FracDef *fracs;
+    const GroupComp *gcomps;
+    int n_groups;
+    int max_frac, max_comp;   // largest group (shared-memory sizing)
     int64_t n_rows;
     int n_comps;
     double ratio_filter;
-    int correction;
-    double bonferroni_n;
-    const double *choose;     // folded table
     const int32_t *name_rank; // may be null
     // survivors (SoA)
     int32_t *r_comp, *r_row, *r_rank;
     int4 *r_cnt;
-    double *r_p, *r_ratio;
+    double *r_ratio;
     unsigned long long *seg_count;   // [n_comps] (count mode) / cursors (emit mode)
     const long long *seg_base;       // [n_comps] exclusive offsets (emit mode, filtered)
     int dense;                       // 1: every test survives, index = comp*n_rows + row
@@ -111,6 +119,11 @@ cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t
                                         unsigned long long *out_count, cudaStream_t st);
 cudaError_t launch_test_count(const TestParams &p, cudaStream_t st);
 cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
+// K3b over n compacted survivors: p (+ Bonferroni) and, when d_key != null, the sort keys + OR/AND words
+cudaError_t launch_pvalues(const int4 *d_tables, const double *d_ratio, int64_t n, const double *d_choose,
+                           int correction, double bonferroni_n, double *d_p, int sort_key,
+                           unsigned long long *d_key, uint32_t *d_val, uint32_t *d_or_and,
+                           const int32_t *r_rank, const int32_t *r_comp, cudaStream_t st);
 cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose,
                                double *d_p, double *d_ratio, cudaStream_t st);
 
@@ -127,9 +140,6 @@ size_t sort_status_words(int64_t n);
 // Returns the permutation (device pointer inside ws) and adds the number of kernel launches.
 cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
                             bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches);
-cudaError_t launch_build_keys(const double *r_ratio, const double *r_p, const int32_t *r_rank,
-                              const int32_t *r_comp, int sort_key, int64_t n, SortWorkspace &ws,
-                              cudaStream_t st);
 cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, const int32_t *r_row,
                                   const int32_t *r_rank, const int4 *r_cnt, const double *r_p,
                                   const double *r_ratio, int32_t *o_row, int32_t *o_rank,

@@ -34,45 +34,6 @@ constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
 
-__global__ void __launch_bounds__(256)
-build_keys_kernel(const double *__restrict__ r_ratio, const double *__restrict__ r_p,
-                  const int32_t *__restrict__ r_rank, const int32_t *__restrict__ r_comp,
-                  int sort_key, int64_t n, unsigned long long *__restrict__ key,
-                  uint32_t *__restrict__ val, uint32_t *__restrict__ or_and) {
-    uint32_t o[4] = {0, 0, 0, 0}, a[4] = {~0u, ~0u, ~0u, ~0u};
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += int64_t(gridDim.x) * blockDim.x) {
-        unsigned long long bits;
-        if (sort_key == FEHT_SORT_PVALUE_ASC) {
-            bits = (unsigned long long)__double_as_longlong(r_p[i]);
-        } else {
-            bits = ~(unsigned long long)__double_as_longlong(fabs(r_ratio[i]));
-        }
-        key[i] = bits;
-        val[i] = uint32_t(i);
-        const uint32_t w0 = uint32_t(r_rank[i]), w3 = uint32_t(r_comp[i]);
-        const uint32_t w1 = uint32_t(bits), w2 = uint32_t(bits >> 32);
-        o[0] |= w0; o[1] |= w1; o[2] |= w2; o[3] |= w3;
-        a[0] &= w0; a[1] &= w1; a[2] &= w2; a[3] &= w3;
-    }
-    __shared__ uint32_t so[4], sa[4];
-    if (threadIdx.x < 4) { so[threadIdx.x] = 0; sa[threadIdx.x] = ~0u; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        for (int s = 16; s > 0; s >>= 1) {
-            o[w] |= __shfl_xor_sync(0xffffffffu, o[w], s);
-            a[w] &= __shfl_xor_sync(0xffffffffu, a[w], s);
-        }
-        if ((threadIdx.x & 31) == 0) { atomicOr(&so[w], o[w]); atomicAnd(&sa[w], a[w]); }
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        atomicOr(or_and + threadIdx.x, so[threadIdx.x]);
-        atomicAnd(or_and + 4 + threadIdx.x, sa[threadIdx.x]);
-    }
-}
-
 // digit of item for a pass: src 0 = byte of the carried 64-bit key, src 1 = byte of word[val]
 __device__ __forceinline__ uint32_t digit_of(int src, int shift, unsigned long long k, uint32_t v,
                                              const uint32_t *__restrict__ word) {
@@ -240,18 +201,6 @@ inline int blocks_for(int64_t n, int per) {
 }  // namespace
 
 size_t sort_status_words(int64_t n) { return size_t((n + kTile - 1) / kTile) * 256; }
-
-cudaError_t launch_build_keys(const double *r_ratio, const double *r_p, const int32_t *r_rank,
-                              const int32_t *r_comp, int sort_key, int64_t n, SortWorkspace &ws,
-                              cudaStream_t st) {
-    static const uint32_t init[8] = {0, 0, 0, 0, ~0u, ~0u, ~0u, ~0u};
-    cudaError_t e = cudaMemcpyAsync(ws.or_and, init, sizeof(init), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    if (n == 0) return cudaSuccess;
-    build_keys_kernel<<<blocks_for(n, 1024), 256, 0, st>>>(r_ratio, r_p, r_rank, r_comp, sort_key, n,
-                                                          ws.key_a, ws.val_a, ws.or_and);
-    return cudaGetLastError();
-}
 
 cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
                             bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches) {

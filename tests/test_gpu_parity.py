@@ -281,6 +281,79 @@ def test_category_api_equals_explicit_comparisons(ctx):
         assert kinds.count(2) == (n_values if n_values > 2 else 0)
 
 
+@pytest.mark.parametrize("n_samples,n_values", [(130, 3), (1000, 7), (2600, 70), (5000, 50)])
+def test_gemm_engine_counts_equal_oracle(ctx, n_samples, n_values):
+    """K2 (int8 tcgen05 GEMM) against the oracle: same pair / one-vs-rest tables, bit-exact, for one and
+    for several passes (70 values = 36 pair-slots > 32 per pass), with an explicit comparison mixed in
+    (K1 counts that one) and samples that lack the category (-1)."""
+    rng = np.random.default_rng(400 + n_values)
+    n_rows = 300 if n_values < 50 else 140
+    cells = _random_chars(rng, n_rows, n_samples)
+    vos = rng.integers(-1, n_values, size=n_samples).astype(np.int32)
+    rank = rng.permutation(n_rows).astype(np.int32)
+    ctx.set_samples(n_samples)
+    ctx.add_rows_chars(cells, rank)
+    g1, g2 = np.arange(0, n_samples // 3), np.arange(n_samples // 4, n_samples // 2)
+    ctx.add_comparison(g1, g2)
+    ctx.add_category(vos, n_values)
+    comps = [(g1, g2)]
+    for i in range(n_values):
+        for j in range(i + 1, n_values):
+            comps.append((np.flatnonzero(vos == i), np.flatnonzero(vos == j)))
+    for v in range(n_values):
+        comps.append((np.flatnonzero(vos == v), np.flatnonzero((vos >= 0) & (vos != v))))
+    assert ctx.num_comparisons == len(comps)
+    ctx.set_count_engine(capi.ENGINE_GEMM)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.4)
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM
+    # every comparison for the small cases, a spread of them for the 2486 / 1276-comparison cases
+    pick = range(len(comps)) if len(comps) < 60 else sorted(set(rng.integers(0, len(comps), 60)) | {0, 1, len(comps) - 1})
+    for ci in pick:
+        g1_, g2_ = comps[ci]
+        want = oracle.run_comparison(cells, g1_, g2_, correction=1, bonferroni_n=n_rows)
+        order = oracle.filter_and_order(want["ratio"], rank, 0.4)
+        got = ctx.fetch(ci)
+        assert (got["row"] == order).all(), ci
+        for k in ("goa", "gob", "gta", "gtb", "ratio"):
+            assert (got[k] == want[k][order]).all(), (ci, k)
+        l = (want["goa"] + want["gob"] + want["gta"] + want["gtb"])[order]
+        assert p_close(got["p"], want["p"][order], l >= 1000).all(), ci
+
+
+def test_gemm_and_popcount_engines_agree_on_two_categories(ctx):
+    """Two categories in one GEMM pass (C5-style), row count not a multiple of the 256-row tile, rows
+    longer than one 1024-sample TMA chunk; dense output (ratio filter 0)."""
+    rng = np.random.default_rng(411)
+    n_samples, n_rows = 3100, 777
+    cells = _random_chars(rng, n_rows, n_samples)
+    ctx.set_samples(n_samples)
+    ctx.add_rows_chars(cells)
+    ctx.add_category(rng.integers(0, 5, size=n_samples).astype(np.int32), 5)
+    ctx.add_category(rng.integers(-1, 12, size=n_samples).astype(np.int32), 12)
+    res = {}
+    for eng in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_AUTO):
+        ctx.set_count_engine(eng)
+        ctx.run(capi.CORRECTION_NONE, 0.0)
+        res[eng] = [ctx.fetch(ci) for ci in range(ctx.num_comparisons)]
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM       # AUTO: 3+1+6+1 = 11 pair-slots >= 8
+    for ci in range(ctx.num_comparisons):
+        for k in ("row", "goa", "gob", "gta", "gtb", "p", "ratio"):
+            a, b, c = (res[e][ci][k] for e in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_AUTO))
+            same = (a == b) | ((a != a) & (b != b))
+            assert same.all() and ((b == c) | ((b != b) & (c != c))).all(), (ci, k)
+
+
+def test_gemm_engine_rejects_snp_and_explicit_only(ctx):
+    ctx.set_samples(64)
+    ctx.add_rows_chars([b"01" * 32])
+    ctx.add_comparison([0, 1], [2, 3])
+    ctx.set_count_engine(capi.ENGINE_GEMM)
+    with pytest.raises(capi.FehtError):
+        ctx.run()
+    ctx.set_count_engine(capi.ENGINE_AUTO)
+    ctx.run()
+
+
 def test_snp_packed_equals_expanded_binary_rows(ctx):
     rng = np.random.default_rng(33)
     n_sites, n_samples = 150, 421
