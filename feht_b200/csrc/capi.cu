@@ -78,6 +78,7 @@ struct feht_ctx {
     DevBuf<ScreenGroup> groups;
     DevBuf<FracDef> fracs;
     DevBuf<GroupComp> gcomps;
+    DevBuf<SlotDef> sdefs;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
     DevBuf<long long> seg_base;
     DevBuf<int32_t> r_comp, r_row, r_rank, o_row, o_rank;
@@ -405,7 +406,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     for (int i = 0; i < 3; ++i) if (c->plane[i]) cudaFree(c->plane[i]);
     release(c->rank); release(c->stage[0]); release(c->stage[1]);
     release(c->gemm_b); release(c->gemm_passes);
-    release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->seg_count); release(c->seg_base);
+    release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->sdefs); release(c->seg_count); release(c->seg_base);
     release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
     release(c->r_cnt); release(c->o_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
@@ -667,7 +668,8 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     std::vector<ScreenGroup> groups;
     std::vector<FracDef> fracs;
     std::vector<GroupComp> gcomps;
-    int max_frac = 0, max_comp = 0;
+    std::vector<SlotDef> sdefs;
+    int max_frac = 0, max_comp = 0, max_slot = 0;
     {
         // explicit comparisons: one pair-slot each, groups of up to 64
         constexpr int kExplicitPerGroup = 64;
@@ -683,13 +685,16 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
             for (int32_t col : cp.g1) m1[col >> 6] |= 1ULL << (col & 63);
             for (int32_t col : cp.g2) m2[col >> 6] |= 1ULL << (col & 63);
             if (groups.empty() || groups.back().n_comp >= kExplicitPerGroup || e % kExplicitPerGroup == 0)
-                groups.push_back(ScreenGroup{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0});
+                groups.push_back(ScreenGroup{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0,
+                                             int32_t(sdefs.size()), 0, -1, 0});
             ScreenGroup &g = groups.back();
             fracs.push_back(FracDef{e, 0, -1, 0});
             fracs.push_back(FracDef{e, 1, -1, 0});
+            sdefs.push_back(SlotDef{e, int16_t(g.n_frac), int16_t(g.n_frac + 1), -1, -1, 0});
             gcomps.push_back(GroupComp{i, int16_t(g.n_frac), int16_t(g.n_frac + 1)});
             g.n_frac += 2;
             g.n_comp += 1;
+            g.n_slot += 1;
             ++e;
         }
         // categories: value blocks of 64; group (a,b) holds the pairs between blocks a <= b, the
@@ -710,7 +715,8 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
             const int nb = (V + kValueBlock - 1) / kValueBlock;
             for (int a = 0; a < nb; ++a)
                 for (int b = a; b < nb; ++b) {
-                    ScreenGroup g{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0};
+                    ScreenGroup g{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0, int32_t(sdefs.size()), 0,
+                                  -1, 0};
                     const int a0 = a * kValueBlock, a1 = std::min(V, a0 + kValueBlock);
                     const int b0 = b * kValueBlock, b1 = std::min(V, b0 + kValueBlock);
                     auto plain = [&](int v) { return FracDef{cat_slot0[k] + v / 2, v & 1, -1, 0}; };
@@ -735,18 +741,39 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
                         g.n_frac += a1 - a0;
                         g.n_comp += a1 - a0;
                     }
-                    if (g.n_comp > 0) groups.push_back(g);
+                    if (g.n_comp > 0) {
+                        // slot view of the same fractions: one record load per pair-slot
+                        g.tot_slot = (b == a && V > 2) ? cat_tot[k] : -1;
+                        for (int f = 0; f < g.n_frac; ++f) {
+                            const FracDef &fd = fracs[size_t(g.frac_off + f)];
+                            SlotDef *sd = nullptr;
+                            for (int q = g.slot_off; q < int(sdefs.size()); ++q)
+                                if (sdefs[size_t(q)].slot == fd.slot) { sd = &sdefs[size_t(q)]; break; }
+                            if (!sd) {
+                                sdefs.push_back(SlotDef{fd.slot, -1, -1, -1, -1, 0});
+                                sd = &sdefs.back();
+                            }
+                            int16_t &dst = fd.tot_slot >= 0 ? (fd.sel ? sd->r_hi : sd->r_lo) : (fd.sel ? sd->f_hi : sd->f_lo);
+                            dst = int16_t(f);
+                        }
+                        g.n_slot = int(sdefs.size()) - g.slot_off;
+                        groups.push_back(g);
+                    } else {
+                        fracs.resize(size_t(g.frac_off));
+                    }
                 }
         }
         for (const ScreenGroup &g : groups) {
             max_frac = std::max(max_frac, g.n_frac);
             max_comp = std::max(max_comp, g.n_comp);
+            max_slot = std::max(max_slot, g.n_slot);
         }
     }
     CU(c, ensure(c->masks, size_t(n_slots) * 2 * plan.w4pad));
     CU(c, ensure(c->groups, groups.size()));
     CU(c, ensure(c->fracs, fracs.size()));
     CU(c, ensure(c->gcomps, gcomps.size()));
+    CU(c, ensure(c->sdefs, sdefs.size()));
     CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
     CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
     CU(c, ensure(c->seg_base, size_t(n_comps)));
@@ -754,6 +781,7 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     CU(c, cudaMemcpyAsync(c->groups.p, groups.data(), groups.size() * sizeof(ScreenGroup), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->fracs.p, fracs.data(), fracs.size() * sizeof(FracDef), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->gcomps.p, gcomps.data(), gcomps.size() * sizeof(GroupComp), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaMemcpyAsync(c->sdefs.p, sdefs.data(), sdefs.size() * sizeof(SlotDef), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
 
     int launches = 0, count_launches = 0;
@@ -834,6 +862,8 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     tp.groups = c->groups.p;
     tp.fracs = c->fracs.p;
     tp.gcomps = c->gcomps.p;
+    tp.slots = c->sdefs.p;
+    tp.max_slot = max_slot;
     tp.n_groups = int(groups.size());
     tp.max_frac = max_frac;
     tp.max_comp = max_comp;

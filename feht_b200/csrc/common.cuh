@@ -38,9 +38,20 @@ struct GroupComp {
     int32_t comp;       // index of the comparison in the run
     int16_t fa, fb;     // fraction ids (inside the group) of group one / group two
 };
+// One load of a pair-slot record feeds up to four fractions of the group: the plain fractions of
+// its two halves and, for one-vs-rest, "category total minus this value" of each half.
+struct SlotDef {
+    int32_t slot;
+    int16_t f_lo, f_hi;   // fraction ids of (x,y) / (z,w); -1 = not used by this group
+    int16_t r_lo, r_hi;   // fraction ids of the one-vs-rest complements; -1 = none
+    int32_t pad;
+};
 struct ScreenGroup {
-    int32_t frac_off, n_frac;   // slice of the FracDef array
+    int32_t frac_off, n_frac;   // slice of the FracDef array (emit path: fraction id -> counts)
     int32_t comp_off, n_comp;   // slice of the GroupComp array
+    int32_t slot_off, n_slot;   // slice of the SlotDef array (fraction fill)
+    int32_t tot_slot;           // the category's total slot, -1 = none
+    int32_t pad;
 };
 
 struct Timings {
@@ -99,8 +110,9 @@ struct TestParams {
     const ScreenGroup *groups;
     const FracDef *fracs;
     const GroupComp *gcomps;
+    const SlotDef *slots;
     int n_groups;
-    int max_frac, max_comp;   // largest group (shared-memory sizing)
+    int max_frac, max_comp, max_slot;   // largest group (shared-memory sizing)
     int64_t n_rows;
     int n_comps;
     double ratio_filter;

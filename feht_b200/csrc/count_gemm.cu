@@ -12,10 +12,12 @@
 // Mapping onto sm_100a (DESIGN.md "K2"):
 //   * A (1 bit per call in HBM) is never expanded in memory.  A TMA tensor map streams a
 //     [256 rows x 128 B] box of each bit-plane into 128B-swizzled shared memory; 8 "expander" warps
-//     (one thread per marker row = one TMEM lane) read 16 B of their row, blow the bits up to 0/1
-//     bytes in registers (2 ALU ops per 4 calls) and write them straight into TENSOR MEMORY with
-//     tcgen05.st, where tcgen05.mma takes its A operand from ([a_tmem] form).  Shared-memory
-//     bandwidth is therefore spent on the 1-bit data and the B tiles only.
+//     (one thread per marker row = one TMEM lane) read 16 B of their row, spread the bits over bytes
+//     in registers with ONE AND per 4 calls (byte = bit << j; the matching B entries are
+//     1 << (7-j), so every hit adds exactly 128 and the epilogue shifts the s32 sums right by 7)
+//     and write them straight into TENSOR MEMORY with tcgen05.st, where tcgen05.mma takes its A
+//     operand from ([a_tmem] form).  Shared-memory bandwidth is therefore spent on the 1-bit data
+//     and the B tiles only.
 //   * B (one-hot, int8, K-major) is baked by the host into the exact 128B-swizzled core-matrix
 //     byte order the UMMA shared-memory descriptor expects, one contiguous N x 128 B block per
 //     128-sample stage, so a plain 1-D bulk copy (cp.async.bulk, UBLKCP) per stage suffices; the
@@ -29,8 +31,11 @@
 //   * warp roles: 0-7 expand + epilogue, 8 TMA producer for the planes, 9 bulk-copy producer for
 //     B, 10 MMA issuer (+ TMEM allocation).  Persistent CTAs, one per SM, static tile round-robin.
 //
-// Bounds: int8 tensor pipe (2 planes x 2*S*N ops per row), the expanders' ALU issue rate
-// (~36 instructions per 32 calls per row) and HBM (planes read once per pass of <= 32 value pairs).
+// Bounds (measured, profiles/README.md r1c): one tcgen05.mma of this shape (M=128, K=32, A from
+// TMEM) costs ~85 cycles whatever N <= 64 is -- the tensor pipe itself is busy 32 of them at N=64 --
+// so the kernel runs at the instruction-issue floor of 16 MMAs per 128 samples per 256 rows, about
+// 1.8 int8 POP/s; the expanders (~10 instructions per 32 calls per row) and HBM (planes read once
+// per pass of <= 32 value pairs, 1.8 TB/s) are both under it.
 #include <cuda.h>
 
 #include <cstring>
@@ -141,12 +146,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
         : "memory");
 }
 
-// 32 calls (one word of a bit-plane row) -> 8 TMEM columns of 4 int8 each.  Column j, byte b holds
-// call (8*b + j): y_j = (w >> j) & 0x01010101.  bake_b() orders B's K dimension the same way.
+// 32 calls (one word of a bit-plane row) -> 8 TMEM columns of 4 uint8 each.  Column j, byte b holds
+// call (8*b + j) as the value (bit << j): y_j = w & (0x01010101 << j), ONE logic op per column.
+// bake_b() orders B's K dimension the same way and stores 1 << (7 - j) there, so a hit adds 128.
 __device__ __forceinline__ void expand_store(uint32_t taddr, uint32_t w) {
     uint32_t y[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = (w >> j) & 0x01010101u;
+    for (int j = 0; j < 8; ++j) y[j] = w & (0x01010101u << j);
     tmem_st8(taddr, y);
 }
 
@@ -267,9 +273,10 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int pair = (c0 >> 1) + j;
-                        if (pair < pass.n_pairs)
+                        if (pair < pass.n_pairs)   // every hit added 128 (expand_store / gemm_bake_b)
                             counts[size_t(pass.slot_base + pair) * size_t(n_rows) + size_t(row)] =
-                                make_int4(int(P[2 * j]), int(N[2 * j]), int(P[2 * j + 1]), int(N[2 * j + 1]));
+                                make_int4(int(P[2 * j] >> 7), int(N[2 * j] >> 7), int(P[2 * j + 1] >> 7),
+                                          int(N[2 * j + 1] >> 7));
                     }
                 }
             }
@@ -402,7 +409,7 @@ void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, in
             const int kk = 32 * i + 4 * j + b;         // K position inside the stage
             const size_t off = size_t(g) * size_t(n_pad) * 128 + n * 128 +
                                size_t((((kk >> 4) ^ int(n & 7)) << 4) + (kk & 15));
-            out[off] = 1;
+            out[off] = uint8_t(1u << (7 - j));
         }
     }
 }

@@ -28,7 +28,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = 16;
+constexpr int kItems = 8;
 constexpr int kTile = kThreads * kItems;  // 4096
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
@@ -65,7 +65,7 @@ struct PassArgs {
     const uint32_t *word;        // gather source when src == 1
     const uint32_t *hist;        // [256] global digit counts of this pass
     uint32_t *ticket;            // tile ticket of this pass
-    uint32_t *status;            // [n_tiles][256]
+    volatile uint32_t *status;   // [n_tiles][256]
     int has_next, nsrc, nshift;  // next pass's digit (its histogram is accumulated here)
     const uint32_t *nword;
     uint32_t *nhist;
@@ -148,14 +148,28 @@ __global__ void __launch_bounds__(kThreads) onesweep_pass_kernel(PassArgs A) {
 
         unsigned excl = 0;
         if (tile > 0) {
+            // Decoupled look-back, 8 predecessor tiles per step: the status loads of a step are issued
+            // together (one L2 latency per 8 tiles instead of per tile -- with a single wave of tiles
+            // the serial walk was most of a pass), then consumed nearest-first, spinning only on a
+            // status that is not published yet.
             int64_t t = int64_t(tile) - 1;
-            for (;;) {
-                const volatile uint32_t *ps = A.status + size_t(t) * 256 + d;
-                uint32_t s;
-                do { s = *ps; } while ((s >> 30) == 0u);
-                excl += s & kValueMask;
-                if (s & kFlagPrefix) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                uint32_t sv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int64_t tj = t - j;
+                    sv[j] = tj >= 0 ? *(A.status + size_t(tj) * 256 + d) : (2u << 30);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (done) break;
+                    uint32_t sj = sv[j];
+                    while ((sj >> 30) == 0u) sj = *(A.status + size_t(t - j) * 256 + d);
+                    excl += sj & kValueMask;
+                    if (sj & kFlagPrefix) done = true;
+                }
+                t -= 8;
             }
             *st = kFlagPrefix | (excl + run);
         }
