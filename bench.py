@@ -227,6 +227,15 @@ def run_reference(args):
     return 0
 
 
+def _guard_stdout():
+    """NCCL / torchrun chatter goes to fd 1; the driver wants ONE JSON line there.  Point fd 1 at
+    stderr for the whole run and return a file object on the real stdout for the final line."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,6 +252,7 @@ def main() -> int:
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
+    real_stdout = _guard_stdout()
 
     import torch
     import torch.distributed as dist
@@ -258,7 +268,7 @@ def main() -> int:
     gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        gloo = dist.new_group(backend="gloo")
+        gloo = None
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -328,17 +338,13 @@ def main() -> int:
             chars[r0:r0 + n].copy_(c)
             del v, d, vb, db, c
         torch.cuda.synchronize()
-        out = {"row": torch.empty(R, dtype=torch.int64, pin_memory=True),
-               "goa": torch.empty(R, dtype=torch.int32, pin_memory=True),
-               "gob": torch.empty(R, dtype=torch.int32, pin_memory=True),
-               "gta": torch.empty(R, dtype=torch.int32, pin_memory=True),
-               "gtb": torch.empty(R, dtype=torch.int32, pin_memory=True),
-               "p": torch.empty(R, dtype=torch.float64, pin_memory=True),
-               "ratio": torch.empty(R, dtype=torch.float64, pin_memory=True),
-               "name_rank": torch.empty(R, dtype=torch.int32, pin_memory=True)}
+        # result buffers: rank 0 receives the merged rows of the whole job
+        RO = total_rows if rank == 0 else 1
+        out = {k: torch.empty(RO, dtype=getattr(torch, dt), pin_memory=True)
+               for k, dt in sharding.DEV_DTYPES.items()}
         ptrs = {k: v.data_ptr() for k, v in out.items()}
         h2d = R * S + (R + 1) * 8 + (len(G1) + len(G2)) * 4
-        d2h = R * (8 + 4 * 4 + 8 + 8 + 4)
+        d2h = (total_rows if world > 1 else R) * (8 + 4 * 4 + 8 + 8 + 4)   # rank 0 reads the merged rows
         times = []
         for i in range(1 + args.e2e_steps):
             barrier()
@@ -348,12 +354,11 @@ def main() -> int:
             ctx.add_rows_chars_raw(chars.data_ptr(), offsets.data_ptr(), R)
             ctx.add_comparison(G1, G2)
             ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, total_rows)
-            ctx.fetch_raw(0, ptrs)
-            merged_n = R
-            if world > 1:
-                local = {k: v.numpy() for k, v in out.items()}
-                merged = sharding.gather_and_merge(local, group=gloo)
-                merged_n = len(merged["row"]) if merged is not None else 0
+            if world == 1:
+                ctx.fetch_raw(0, ptrs)
+            else:
+                merged = sharding.gather_and_merge_device(ctx, 0, capi.SORT_ABS_RATIO_DESC, 0, out)
+                assert merged is None or len(merged["row"]) == total_rows
             barrier()
             dt = time.perf_counter() - t0
             if i > 0:
@@ -363,8 +368,9 @@ def main() -> int:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e = {"value": total_rows / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(e2e_s.item()),
-               "path": "feht_add_rows_chars(pinned host chars, 1 B/call) -> feht_run -> feht_result_fetch"
-                       + (" -> gloo gather + feht_merge_sorted on rank 0" if world > 1 else ""),
+               "path": "feht_add_rows_chars(pinned host chars, 1 B/call) -> feht_run -> "
+                       + ("feht_result_fetch" if world == 1 else
+                          "feht_result_fetch_device, NCCL gather to rank 0, feht_merge_sorted_device (K5), one D2H"),
                "timer": "host perf_counter between barrier+synchronize (covers H2D, kernels, D2H)"}
         del chars
 
@@ -401,7 +407,8 @@ def main() -> int:
             "gpu_launches": int(stage["launches"]),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

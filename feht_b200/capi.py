@@ -28,7 +28,8 @@ EXPORTS = [
     "feht_add_category", "feht_clear_comparisons", "feht_num_comparisons", "feht_comparison_info",
     "feht_set_count_engine", "feht_run", "feht_result_count", "feht_result_total",
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
-    "feht_choose_table", "feht_eval_tables",
+    "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
+    "feht_scatter_rows_device",
 ]
 
 
@@ -105,6 +106,9 @@ def lib() -> C.CDLL:
     L.feht_result_total.argtypes = [vp]
     L.feht_result_total.restype = i64
     L.feht_result_fetch.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.feht_result_fetch_device.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.feht_merge_sorted_device.argtypes = [vp, C.c_int, P(i64), P(vp), P(vp), C.c_int, P(vp)]
+    L.feht_scatter_rows_device.argtypes = [vp, vp, vp, vp, i64, i32]
     L.feht_set_row_base.argtypes = [vp, i64]
     L.feht_last_timings.argtypes = [vp, P(f64), C.c_int]
     L.feht_merge_sorted.argtypes = [C.c_int, P(i64), P(vp), P(vp), C.c_int, vp, vp]
@@ -317,6 +321,24 @@ class Context:
         g = ptrs.get
         self._check(self._L.feht_result_fetch(self._h, c, g("row"), g("goa"), g("gob"), g("gta"), g("gtb"),
                                               g("p"), g("ratio"), g("name_rank")))
+
+    def fetch_device(self, c: int, ptrs: dict):
+        """ptrs: name -> DEVICE address on this context's GPU (caller-owned buffers)."""
+        g = ptrs.get
+        self._check(self._L.feht_result_fetch_device(self._h, c, g("row"), g("goa"), g("gob"), g("gta"),
+                                                     g("gtb"), g("p"), g("ratio"), g("name_rank")))
+
+    def merge_sorted_device(self, sizes, key_ptrs, rank_ptrs, dest_ptrs, sort_key=SORT_ABS_RATIO_DESC):
+        """K5: device k-way merge; all pointers are device addresses on this context's GPU."""
+        k = len(sizes)
+        n = (C.c_int64 * max(k, 1))(*[int(x) for x in sizes])
+        kp = (C.c_void_p * max(k, 1))(*key_ptrs)
+        rp = (C.c_void_p * max(k, 1))(*rank_ptrs)
+        dp = (C.c_void_p * max(k, 1))(*dest_ptrs)
+        self._check(self._L.feht_merge_sorted_device(self._h, k, n, kp, rp, sort_key, dp))
+
+    def scatter_rows_device(self, src_ptr: int, dst_ptr: int, dest_ptr: int, n: int, elem_bytes: int):
+        self._check(self._L.feht_scatter_rows_device(self._h, src_ptr, dst_ptr, dest_ptr, n, elem_bytes))
 
     def timings(self) -> dict:
         buf = (C.c_double * 8)()

@@ -81,8 +81,9 @@ struct feht_ctx {
     DevBuf<SlotDef> sdefs;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
     DevBuf<long long> seg_base;
-    DevBuf<int32_t> r_comp, r_row, r_rank, o_row, o_rank;
-    DevBuf<int4> r_cnt, o_cnt;
+    DevBuf<int32_t> r_comp, r_row, r_rank, o_rank, o_goa, o_gob, o_gta, o_gtb;
+    DevBuf<int64_t> o_row;
+    DevBuf<int4> r_cnt;
     DevBuf<double> r_p, r_ratio, o_p, o_ratio;
     SortWorkspace sw;
     DevBuf<unsigned long long> sw_key_a, sw_key_b;
@@ -408,7 +409,8 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->gemm_b); release(c->gemm_passes);
     release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->sdefs); release(c->seg_count); release(c->seg_base);
     release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
-    release(c->r_cnt); release(c->o_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
+    release(c->o_goa); release(c->o_gob); release(c->o_gta); release(c->o_gtb);
+    release(c->r_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa);
     if (c->d_choose) cudaFree(c->d_choose);
@@ -908,7 +910,8 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     const size_t nn = size_t(n);
     CU(c, ensure(c->r_comp, nn)); CU(c, ensure(c->r_row, nn)); CU(c, ensure(c->r_rank, nn));
     CU(c, ensure(c->r_cnt, nn)); CU(c, ensure(c->r_p, nn)); CU(c, ensure(c->r_ratio, nn));
-    CU(c, ensure(c->o_row, nn)); CU(c, ensure(c->o_rank, nn)); CU(c, ensure(c->o_cnt, nn));
+    CU(c, ensure(c->o_row, nn)); CU(c, ensure(c->o_rank, nn));
+    CU(c, ensure(c->o_goa, nn)); CU(c, ensure(c->o_gob, nn)); CU(c, ensure(c->o_gta, nn)); CU(c, ensure(c->o_gtb, nn));
     CU(c, ensure(c->o_p, nn)); CU(c, ensure(c->o_ratio, nn));
     tp.r_comp = c->r_comp.p; tp.r_row = c->r_row.p; tp.r_rank = c->r_rank.p;
     tp.r_cnt = c->r_cnt.p; tp.r_ratio = c->r_ratio.p;
@@ -937,8 +940,10 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     if (n > 0) {
         uint32_t *perm = nullptr;
         CU(c, radix_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
-        CU(c, launch_gather_results(perm, n, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p, c->r_ratio.p,
-                                    c->o_row.p, c->o_rank.p, c->o_cnt.p, c->o_p.p, c->o_ratio.p, c->st));
+        const ResultSoA out{c->o_row.p, c->o_rank.p, c->o_goa.p, c->o_gob.p, c->o_gta.p, c->o_gtb.p,
+                            c->o_p.p, c->o_ratio.p};
+        CU(c, launch_gather_results(perm, n, c->row_base, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p,
+                                    c->r_ratio.p, out, c->st));
         ++launches;
     }
     CU(c, cudaEventRecord(c->ev[3], c->st));
@@ -963,32 +968,66 @@ extern "C" int64_t feht_result_count(const feht_ctx *c, int64_t comparison) {
 
 extern "C" int64_t feht_result_total(const feht_ctx *c) { return (c && c->has_results) ? c->n_surv : FEHT_E_INVALID; }
 
-extern "C" int feht_result_fetch(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob,
-                                 int32_t *gta, int32_t *gtb, double *p, double *ratio, int32_t *name_rank) {
+namespace {
+// copy comparison c's ordered rows out of the result arrays (host or device destination)
+int fetch_common(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob, int32_t *gta,
+                 int32_t *gtb, double *p, double *ratio, int32_t *name_rank, cudaMemcpyKind kind) {
     if (!c) return FEHT_E_INVALID;
     if (!c->has_results) return fail(c, FEHT_E_INVALID, "no results: call feht_run first");
     if (comparison < 0 || comparison + 1 >= int64_t(c->seg_off.size())) return fail(c, FEHT_E_INVALID, "comparison index");
     if (int rc = use_device(c)) return rc;
     const int64_t o = c->seg_off[size_t(comparison)];
-    const int64_t n = c->seg_off[size_t(comparison) + 1] - o;
-    if (n == 0) return FEHT_OK;
-    const size_t nn = size_t(n);
-    if (p) CU(c, cudaMemcpyAsync(p, c->o_p.p + o, nn * 8, cudaMemcpyDeviceToHost, c->st));
-    if (ratio) CU(c, cudaMemcpyAsync(ratio, c->o_ratio.p + o, nn * 8, cudaMemcpyDeviceToHost, c->st));
-    if (name_rank) CU(c, cudaMemcpyAsync(name_rank, c->o_rank.p + o, nn * 4, cudaMemcpyDeviceToHost, c->st));
-    std::vector<int32_t> hrow;
-    std::vector<int4> hcnt;
-    if (row) { hrow.resize(nn); CU(c, cudaMemcpyAsync(hrow.data(), c->o_row.p + o, nn * 4, cudaMemcpyDeviceToHost, c->st)); }
-    if (goa || gob || gta || gtb) { hcnt.resize(nn); CU(c, cudaMemcpyAsync(hcnt.data(), c->o_cnt.p + o, nn * 16, cudaMemcpyDeviceToHost, c->st)); }
+    const size_t nn = size_t(c->seg_off[size_t(comparison) + 1] - o);
+    if (nn == 0) return FEHT_OK;
+    if (row) CU(c, cudaMemcpyAsync(row, c->o_row.p + o, nn * 8, kind, c->st));
+    if (goa) CU(c, cudaMemcpyAsync(goa, c->o_goa.p + o, nn * 4, kind, c->st));
+    if (gob) CU(c, cudaMemcpyAsync(gob, c->o_gob.p + o, nn * 4, kind, c->st));
+    if (gta) CU(c, cudaMemcpyAsync(gta, c->o_gta.p + o, nn * 4, kind, c->st));
+    if (gtb) CU(c, cudaMemcpyAsync(gtb, c->o_gtb.p + o, nn * 4, kind, c->st));
+    if (p) CU(c, cudaMemcpyAsync(p, c->o_p.p + o, nn * 8, kind, c->st));
+    if (ratio) CU(c, cudaMemcpyAsync(ratio, c->o_ratio.p + o, nn * 8, kind, c->st));
+    if (name_rank) CU(c, cudaMemcpyAsync(name_rank, c->o_rank.p + o, nn * 4, kind, c->st));
     CU(c, cudaStreamSynchronize(c->st));
-    if (row) for (size_t i = 0; i < nn; ++i) row[i] = c->row_base + hrow[i];
-    if (!hcnt.empty())
-        for (size_t i = 0; i < nn; ++i) {
-            if (goa) goa[i] = hcnt[i].x;
-            if (gob) gob[i] = hcnt[i].y;
-            if (gta) gta[i] = hcnt[i].z;
-            if (gtb) gtb[i] = hcnt[i].w;
-        }
+    return FEHT_OK;
+}
+}  // namespace
+
+extern "C" int feht_result_fetch(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob,
+                                 int32_t *gta, int32_t *gtb, double *p, double *ratio, int32_t *name_rank) {
+    return fetch_common(c, comparison, row, goa, gob, gta, gtb, p, ratio, name_rank, cudaMemcpyDeviceToHost);
+}
+
+extern "C" int feht_result_fetch_device(feht_ctx *c, int64_t comparison, int64_t *d_row, int32_t *d_goa,
+                                        int32_t *d_gob, int32_t *d_gta, int32_t *d_gtb, double *d_p,
+                                        double *d_ratio, int32_t *d_name_rank) {
+    return fetch_common(c, comparison, d_row, d_goa, d_gob, d_gta, d_gtb, d_p, d_ratio, d_name_rank,
+                        cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int feht_merge_sorted_device(feht_ctx *c, int n_shards, const int64_t *n, const double *const *d_key,
+                                        const int32_t *const *d_name_rank, int sort_key, int64_t *const *d_dest) {
+    if (!c) return FEHT_E_INVALID;
+    if (n_shards < 0 || n_shards > merge_max_shards())
+        return fail(c, FEHT_E_INVALID, "n_shards must be in [0, %d]", merge_max_shards());
+    if (n_shards && (!n || !d_key || !d_name_rank || !d_dest)) return fail(c, FEHT_E_INVALID, "null shard arrays");
+    if (sort_key != FEHT_SORT_ABS_RATIO_DESC && sort_key != FEHT_SORT_PVALUE_ASC)
+        return fail(c, FEHT_E_INVALID, "unknown sort key %d", sort_key);
+    for (int i = 0; i < n_shards; ++i)
+        if (n[i] < 0 || (n[i] > 0 && (!d_key[i] || !d_name_rank[i] || !d_dest[i])))
+            return fail(c, FEHT_E_INVALID, "shard %d: bad size or null pointer", i);
+    if (int rc = use_device(c)) return rc;
+    CU(c, launch_merge_rank(n_shards, n, d_key, d_name_rank, sort_key, d_dest, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    return FEHT_OK;
+}
+
+extern "C" int feht_scatter_rows_device(feht_ctx *c, const void *d_src, void *d_dst, const int64_t *d_dest,
+                                        int64_t n, int32_t elem_bytes) {
+    if (!c) return FEHT_E_INVALID;
+    if (n < 0 || elem_bytes <= 0 || (n && (!d_src || !d_dst || !d_dest))) return fail(c, FEHT_E_INVALID, "bad scatter arguments");
+    if (int rc = use_device(c)) return rc;
+    CU(c, launch_scatter_rows(d_src, d_dst, d_dest, n, elem_bytes, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
     return FEHT_OK;
 }
 

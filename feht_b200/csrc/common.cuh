@@ -152,10 +152,22 @@ size_t sort_status_words(int64_t n);
 // Returns the permutation (device pointer inside ws) and adds the number of kernel launches.
 cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
                             bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches);
-cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, const int32_t *r_row,
+// ordered results, final types (what feht_result_fetch copies out)
+struct ResultSoA {
+    int64_t *row;
+    int32_t *rank, *goa, *gob, *gta, *gtb;
+    double *p, *ratio;
+};
+cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, int64_t row_base, const int32_t *r_row,
                                   const int32_t *r_rank, const int4 *r_cnt, const double *r_p,
-                                  const double *r_ratio, int32_t *o_row, int32_t *o_rank,
-                                  int4 *o_cnt, double *o_p, double *o_ratio, cudaStream_t st);
+                                  const double *r_ratio, const ResultSoA &o, cudaStream_t st);
+// K5: device k-way merge by ranking (dest[i][j] = final position of element j of shard i)
+int merge_max_shards();
+cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *const *d_key,
+                              const int32_t *const *d_rank, int sort_key, int64_t *const *d_dest,
+                              cudaStream_t st);
+cudaError_t launch_scatter_rows(const void *d_src, void *d_dst, const int64_t *d_dest, int64_t n,
+                                int elem_bytes, cudaStream_t st);
 
 // choose_table.cpp
 const std::vector<double> &host_choose_table();

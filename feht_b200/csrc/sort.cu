@@ -189,19 +189,80 @@ __global__ void __launch_bounds__(kThreads) onesweep_pass_kernel(PassArgs A) {
 }
 
 __global__ void __launch_bounds__(256)
-gather_kernel(const uint32_t *__restrict__ perm, int64_t n, const int32_t *__restrict__ r_row,
+gather_kernel(const uint32_t *__restrict__ perm, int64_t n, int64_t row_base, const int32_t *__restrict__ r_row,
               const int32_t *__restrict__ r_rank, const int4 *__restrict__ r_cnt,
-              const double *__restrict__ r_p, const double *__restrict__ r_ratio,
-              int32_t *__restrict__ o_row, int32_t *__restrict__ o_rank, int4 *__restrict__ o_cnt,
-              double *__restrict__ o_p, double *__restrict__ o_ratio) {
+              const double *__restrict__ r_p, const double *__restrict__ r_ratio, ResultSoA o) {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += int64_t(gridDim.x) * blockDim.x) {
         const uint32_t s = perm[i];
-        o_row[i] = r_row[s];
-        o_rank[i] = r_rank[s];
-        o_cnt[i] = r_cnt[s];
-        o_p[i] = r_p[s];
-        o_ratio[i] = r_ratio[s];
+        const int4 t = r_cnt[s];
+        o.row[i] = row_base + r_row[s];
+        o.rank[i] = r_rank[s];
+        o.goa[i] = t.x; o.gob[i] = t.y; o.gta[i] = t.z; o.gtb[i] = t.w;
+        o.p[i] = r_p[s];
+        o.ratio[i] = r_ratio[s];
+    }
+}
+
+// ---- K5: k-way merge of sorted shards held on this device, rank-based: the final
+// position of an element is its index in its own shard plus, for every other shard, the number of
+// that shard's elements that come before it in the total order (key bits, name rank, shard) -- one
+// binary search per other shard.  No radix passes, deterministic, reads only sorted data.
+constexpr int kMaxShards = 32;
+struct MergeArgs {
+    int n_shards;
+    int sort_key;
+    const double *key[kMaxShards];
+    const int32_t *rank[kMaxShards];
+    long long *dest[kMaxShards];
+    long long n[kMaxShards];
+    long long off[kMaxShards + 1];
+};
+
+__device__ __forceinline__ unsigned long long merge_key_bits(double v, int sort_key) {
+    if (sort_key == FEHT_SORT_PVALUE_ASC) return (unsigned long long)__double_as_longlong(v);
+    return ~((unsigned long long)__double_as_longlong(fabs(v)) & 0x7fffffffffffffffULL);
+}
+
+__global__ void __launch_bounds__(256) merge_rank_kernel(const __grid_constant__ MergeArgs A) {
+    const long long total = A.off[A.n_shards];
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        int s = 0;
+        while (g >= A.off[s + 1]) ++s;
+        const long long i = g - A.off[s];
+        const unsigned long long kb = merge_key_bits(A.key[s][i], A.sort_key);
+        const uint32_t rk = uint32_t(A.rank[s][i]);
+        long long pos = i;
+        for (int t = 0; t < A.n_shards; ++t) {
+            if (t == s) continue;
+            // number of elements e of shard t with (kb_e, rk_e, t) < (kb, rk, s)
+            long long lo = 0, hi = A.n[t];
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                const unsigned long long ke = merge_key_bits(A.key[t][mid], A.sort_key);
+                const uint32_t re = uint32_t(A.rank[t][mid]);
+                const bool before = ke < kb || (ke == kb && (re < rk || (re == rk && t < s)));
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            pos += lo;
+        }
+        A.dest[s][i] = pos;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst,
+                    const long long *__restrict__ dest, int64_t n, int elem_bytes) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += int64_t(gridDim.x) * blockDim.x) {
+        const long long d = dest[i];
+        if (elem_bytes == 8)
+            reinterpret_cast<unsigned long long *>(dst)[d] = reinterpret_cast<const unsigned long long *>(src)[i];
+        else if (elem_bytes == 4)
+            reinterpret_cast<uint32_t *>(dst)[d] = reinterpret_cast<const uint32_t *>(src)[i];
+        else
+            for (int b = 0; b < elem_bytes; ++b) dst[size_t(d) * elem_bytes + b] = src[size_t(i) * elem_bytes + b];
     }
 }
 
@@ -274,13 +335,43 @@ cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank,
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, const int32_t *r_row,
+cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, int64_t row_base, const int32_t *r_row,
                                   const int32_t *r_rank, const int4 *r_cnt, const double *r_p,
-                                  const double *r_ratio, int32_t *o_row, int32_t *o_rank,
-                                  int4 *o_cnt, double *o_p, double *o_ratio, cudaStream_t st) {
+                                  const double *r_ratio, const ResultSoA &o, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(perm, n, r_row, r_rank, r_cnt, r_p, r_ratio,
-                                                     o_row, o_rank, o_cnt, o_p, o_ratio);
+    gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(perm, n, row_base, r_row, r_rank, r_cnt, r_p, r_ratio, o);
+    return cudaGetLastError();
+}
+
+int merge_max_shards() { return kMaxShards; }
+
+cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *const *d_key,
+                              const int32_t *const *d_rank, int sort_key, int64_t *const *d_dest,
+                              cudaStream_t st) {
+    MergeArgs a{};
+    a.n_shards = n_shards;
+    a.sort_key = sort_key;
+    long long off = 0;
+    for (int i = 0; i < n_shards; ++i) {
+        a.key[i] = d_key[i];
+        a.rank[i] = d_rank[i];
+        a.dest[i] = reinterpret_cast<long long *>(d_dest[i]);
+        a.n[i] = n[i];
+        a.off[i] = off;
+        off += n[i];
+    }
+    a.off[n_shards] = off;
+    if (off == 0) return cudaSuccess;
+    merge_rank_kernel<<<blocks_for(off, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_rows(const void *d_src, void *d_dst, const int64_t *d_dest, int64_t n,
+                                int elem_bytes, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    scatter_rows_kernel<<<blocks_for(n, 256), 256, 0, st>>>(
+        static_cast<const unsigned char *>(d_src), static_cast<unsigned char *>(d_dst),
+        reinterpret_cast<const long long *>(d_dest), n, elem_bytes);
     return cudaGetLastError();
 }
 

@@ -44,3 +44,56 @@ def gather_and_merge(local: dict, group=None, sort_key: int = capi.SORT_ABS_RATI
     for k in FIELDS:
         merged[k] = np.concatenate([s[k] for s in shards])[flat]
     return merged
+
+
+DEV_DTYPES = {"row": "int64", "goa": "int32", "gob": "int32", "gta": "int32", "gtb": "int32", "p": "float64",
+              "ratio": "float64", "name_rank": "int32"}
+
+
+def gather_and_merge_device(ctx, comparison: int, sort_key: int = capi.SORT_ABS_RATIO_DESC, dst: int = 0,
+                            host_out: dict | None = None):
+    """Multi-process, one GPU per rank (torch.distributed / NCCL is only the transport): every rank
+    copies its ordered rows of `comparison` into device tensors (feht_result_fetch_device), the
+    shards travel GPU-to-GPU to rank `dst` (NVLink), which merges them ON THE DEVICE with K5
+    (feht_merge_sorted_device + feht_scatter_rows_device) and does ONE device-to-host copy of the
+    merged rows.  Returns a dict of host tensors on `dst` (into `host_out` if given), None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_local = ctx.result_count(comparison)
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = n_local
+    dist.all_reduce(sizes)
+    sizes = [int(x) for x in sizes.tolist()]
+    n_max = max(sizes + [1])
+    local = {k: torch.empty(n_max, dtype=getattr(torch, dt), device=dev) for k, dt in DEV_DTYPES.items()}
+    ctx.fetch_device(comparison, {k: v.data_ptr() for k, v in local.items()})
+    gathered = {}
+    for k, v in local.items():
+        lst = [torch.empty_like(v) for _ in range(world)] if rank == dst else None
+        dist.gather(v, lst, dst=dst)
+        gathered[k] = lst
+    if rank != dst:
+        return None
+    total = sum(sizes)
+    key = "p" if sort_key == capi.SORT_PVALUE_ASC else "ratio"
+    dest = [torch.empty(max(n, 1), dtype=torch.int64, device=dev) for n in sizes]
+    torch.cuda.current_stream().synchronize()
+    ctx.merge_sorted_device(sizes, [t.data_ptr() for t in gathered[key]],
+                            [t.data_ptr() for t in gathered["name_rank"]], [t.data_ptr() for t in dest], sort_key)
+    out = {}
+    for k, dt in DEV_DTYPES.items():
+        merged = torch.empty(max(total, 1), dtype=getattr(torch, dt), device=dev)
+        for s, n in enumerate(sizes):
+            if n:
+                ctx.scatter_rows_device(gathered[k][s].data_ptr(), merged.data_ptr(), dest[s].data_ptr(), n,
+                                        merged.element_size())
+        if host_out is not None and k in host_out:
+            host_out[k][:total].copy_(merged[:total], non_blocking=True)
+            out[k] = host_out[k][:total]
+        else:
+            out[k] = merged[:total].cpu()
+    torch.cuda.current_stream().synchronize()
+    return out

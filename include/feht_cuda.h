@@ -176,7 +176,12 @@ int64_t feht_result_total(const feht_ctx *ctx);
  */
 int feht_result_fetch(feht_ctx *ctx, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob,
                       int32_t *gta, int32_t *gtb, double *p, double *ratio, int32_t *name_rank);
-/* Global index of this context's first row (row-sharded jobs); default 0. */
+/* The same, into DEVICE buffers on the context's GPU (e.g. to hand a shard's sorted rows to a
+ * GPU-to-GPU transport before feht_merge_sorted_device). */
+int feht_result_fetch_device(feht_ctx *ctx, int64_t comparison, int64_t *d_row, int32_t *d_goa,
+                             int32_t *d_gob, int32_t *d_gta, int32_t *d_gtb, double *d_p, double *d_ratio,
+                             int32_t *d_name_rank);
+/* Global index of this context's first row (row-sharded jobs); default 0 (set before feht_run). */
 int feht_set_row_base(feht_ctx *ctx, int64_t row_base);
 
 /* Device-side milliseconds of the last feht_run, by stage (CUDA events on the run's stream):
@@ -193,6 +198,18 @@ int feht_last_timings(const feht_ctx *ctx, double *out, int n);
 int feht_merge_sorted(int n_shards, const int64_t *n, const double *const *key,
                       const int32_t *const *name_rank, int sort_key, int32_t *out_shard,
                       int64_t *out_index);
+
+/*
+ * The same k-way merge on the device (K5), for shards that were moved to this context's GPU
+ * (NVLink / NCCL): all pointers are device pointers; d_dest[i][j] receives the final position of
+ * element j of shard i in the merged order of all sum(n) rows.  feht_scatter_rows_device then moves
+ * any per-row field (elem_bytes each) of a shard to its merged place: d_dst[d_dest[j]] = d_src[j].
+ * At most 32 shards.
+ */
+int feht_merge_sorted_device(feht_ctx *ctx, int n_shards, const int64_t *n, const double *const *d_key,
+                             const int32_t *const *d_name_rank, int sort_key, int64_t *const *d_dest);
+int feht_scatter_rows_device(feht_ctx *ctx, const void *d_src, void *d_dst, const int64_t *d_dest,
+                             int64_t n, int32_t elem_bytes);
 
 /* Host-built table of the reference's `choose` values C[n][k'], n < 1000, k' <= n/2 (the
  * arithmetic of math-functions 0.2.1.0), as uploaded to the device; for tests.

@@ -411,6 +411,58 @@ def test_row_sharding_and_merge_equals_single_context(cuda_lib):
     assert (merged_p == want["p"][order]).all()
 
 
+def test_device_kway_merge_equals_host_merge(cuda_lib):
+    """K5 (feht_merge_sorted_device + feht_scatter_rows_device): shards fetched into device buffers,
+    merged on the device, equal to the host k-way merge and to the oracle order; ties in |ratio|
+    across shards are broken by name rank."""
+    import torch
+    rng = np.random.default_rng(56)
+    n_samples, n_rows = 120, 3000                     # few samples -> many tied ratios
+    cells = _random_chars(rng, n_rows, n_samples)
+    rank = rng.permutation(n_rows).astype(np.int32)
+    g1, g2 = np.arange(0, 50), np.arange(60, 120)
+    want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=n_rows)
+    order = oracle.filter_and_order(want["ratio"], rank, 0.05)
+    bounds = [0, 700, 701, 1800, 3000]
+    dev = torch.device("cuda", 0)
+    shards, sizes, ctxs = [], [], []
+    for lo_, hi_ in zip(bounds[:-1], bounds[1:]):
+        c = capi.Context(0)
+        c.set_samples(n_samples)
+        c.set_row_base(lo_)
+        c.add_rows_chars(cells[lo_:hi_], rank[lo_:hi_])
+        c.add_comparison(g1, g2)
+        c.run(1, 0.05, capi.SORT_ABS_RATIO_DESC, n_rows)
+        n = c.result_count(0)
+        t = {"row": torch.empty(max(n, 1), dtype=torch.int64, device=dev),
+             "ratio": torch.empty(max(n, 1), dtype=torch.float64, device=dev),
+             "p": torch.empty(max(n, 1), dtype=torch.float64, device=dev),
+             "name_rank": torch.empty(max(n, 1), dtype=torch.int32, device=dev)}
+        c.fetch_device(0, {k: v.data_ptr() for k, v in t.items()})
+        shards.append(t); sizes.append(n); ctxs.append(c)
+    total = sum(sizes)
+    assert total == len(order)
+    dest = [torch.empty(max(n, 1), dtype=torch.int64, device=dev) for n in sizes]
+    c0 = ctxs[0]
+    c0.merge_sorted_device(sizes, [t["ratio"].data_ptr() for t in shards],
+                           [t["name_rank"].data_ptr() for t in shards], [d.data_ptr() for d in dest])
+    merged_row = torch.full((total,), -1, dtype=torch.int64, device=dev)
+    merged_p = torch.zeros(total, dtype=torch.float64, device=dev)
+    for t, d, n in zip(shards, dest, sizes):
+        c0.scatter_rows_device(t["row"].data_ptr(), merged_row.data_ptr(), d.data_ptr(), n, 8)
+        c0.scatter_rows_device(t["p"].data_ptr(), merged_p.data_ptr(), d.data_ptr(), n, 8)
+    torch.cuda.synchronize()
+    assert (merged_row.cpu().numpy() == order).all()
+    assert (merged_p.cpu().numpy() == want["p"][order]).all()
+    # and the host merge gives the same (shard, index) sequence
+    hs = [{k: v[:n].cpu().numpy() for k, v in t.items()} for t, n in zip(shards, sizes)]
+    out_s, out_i = capi.merge_sorted([h["ratio"] for h in hs], [h["name_rank"] for h in hs])
+    host_rows = np.array([hs[s_]["row"][i_] for s_, i_ in zip(out_s, out_i)])
+    assert (host_rows == order).all()
+    for c in ctxs:
+        c.close()
+
+
 def test_pvalue_sort_key(ctx):
     rng = np.random.default_rng(77)
     cells = _random_chars(rng, 300, 90)
