@@ -346,6 +346,7 @@ def main() -> int:
         h2d = R * S + (R + 1) * 8 + (len(G1) + len(G2)) * 4
         d2h = (total_rows if world > 1 else R) * (8 + 4 * 4 + 8 + 8 + 4)   # rank 0 reads the merged rows
         times = []
+        parts = {"upload_pack_ms": 0.0, "run_ms": 0.0, "fetch_merge_ms": 0.0}
         for i in range(1 + args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
@@ -353,7 +354,9 @@ def main() -> int:
             ctx.clear_comparisons()
             ctx.add_rows_chars_raw(chars.data_ptr(), offsets.data_ptr(), R)
             ctx.add_comparison(G1, G2)
+            t1 = time.perf_counter()
             ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, total_rows)
+            t2 = time.perf_counter()
             if world == 1:
                 ctx.fetch_raw(0, ptrs)
             else:
@@ -363,11 +366,16 @@ def main() -> int:
             dt = time.perf_counter() - t0
             if i > 0:
                 times.append(dt)
+                parts["upload_pack_ms"] += 1e3 * (t1 - t0) / args.e2e_steps
+                parts["run_ms"] += 1e3 * (t2 - t1) / args.e2e_steps
+                parts["fetch_merge_ms"] += 1e3 * (t0 + dt - t2) / args.e2e_steps
         e2e_s = torch.tensor([sum(times) / len(times)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e = {"value": total_rows / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(e2e_s.item()),
+               "rank0_breakdown_ms": parts,
+               "h2d_gbs_per_gpu": h2d / (parts["upload_pack_ms"] * 1e-3) / 1e9,
                "path": "feht_add_rows_chars(pinned host chars, 1 B/call) -> feht_run -> "
                        + ("feht_result_fetch" if world == 1 else
                           "feht_result_fetch_device, NCCL gather to rank 0, feht_merge_sorted_device (K5), one D2H"),

@@ -266,28 +266,31 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
         }
         piece_first.push_back(n);
     }
-    // Layout of a staged piece: [offsets (rows+1) x int64, rebased to 0][chars...]
-    std::vector<std::vector<int64_t>> rebased(2);
+    // Layout of a staged piece: [offsets (rows+1) x int64, rebased to 0][chars...].  The copies run on
+    // the copy stream into one of two staging buffers while the pack kernel of the previous piece
+    // runs on the context stream (events order buffer reuse), so the PCIe link never waits for K0.
+    const size_t n_pieces = piece_first.size() - 1;
+    std::vector<std::vector<int64_t>> rebased(n_pieces);   // alive until the final synchronize
     const int64_t first_unit = c->n_units;
-    auto next_piece = [&](int i, const void **src, size_t *bytes) -> bool {
-        if (size_t(i) + 1 >= piece_first.size()) return false;
-        *src = nullptr;
-        *bytes = 0;  // copies are issued by consume (two regions)
-        return true;
-    };
-    auto consume = [&](unsigned char *dev, int i) -> int {
+    for (int b = 0; b < 2; ++b) CU(c, ensure(c->stage[b], kStageBytes));
+    for (size_t i = 0; i < n_pieces; ++i) {
+        const int b = int(i & 1);
+        unsigned char *dev = c->stage[b].p;
         const int64_t r0 = piece_first[i], r1 = piece_first[i + 1];
         const int64_t rows = r1 - r0;
-        std::vector<int64_t> &off = rebased[i & 1];
+        std::vector<int64_t> &off = rebased[i];
         off.resize(size_t(rows) + 1);
         for (int64_t r = 0; r <= rows; ++r) off[size_t(r)] = row_offsets[r0 + r] - row_offsets[r0];
         const size_t off_bytes = (size_t(rows) + 1) * 8;
         const size_t off_pad = (off_bytes + 63) & ~size_t(63);
         const size_t char_bytes = size_t(row_offsets[r1] - row_offsets[r0]);
-        CU(c, cudaMemcpyAsync(dev, off.data(), off_bytes, cudaMemcpyHostToDevice, c->st));
+        if (i >= 2) CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_used[b], 0));
+        CU(c, cudaMemcpyAsync(dev, off.data(), off_bytes, cudaMemcpyHostToDevice, c->copy_stream));
         if (char_bytes)
-            CU(c, cudaMemcpyAsync(dev + off_pad, chars + row_offsets[r0], char_bytes,
-                                  cudaMemcpyHostToDevice, c->st));
+            CU(c, cudaMemcpyAsync(dev + off_pad, chars + row_offsets[r0], char_bytes, cudaMemcpyHostToDevice,
+                                  c->copy_stream));
+        CU(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->st, c->ev_copied[b], 0));
         const int64_t u0 = first_unit + r0;
         if (snp)
             CU(c, launch_pack_snp_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows,
@@ -296,11 +299,10 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
         else
             CU(c, launch_pack_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S,
                                     c->W, c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->st));
-        // `off` is reused two pieces later: the copy above must have consumed it by then
-        CU(c, cudaStreamSynchronize(c->st));
-        return FEHT_OK;
-    };
-    if (int rc = staged_upload(c, next_piece, consume)) return rc;
+        CU(c, cudaEventRecord(c->ev_used[b], c->st));
+    }
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, cudaStreamSynchronize(c->st));
     c->n_units += n;
     c->has_results = false;
     c->rank_is_perm = -1;
