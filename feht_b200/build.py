@@ -36,8 +36,13 @@ def _nvcc() -> str:
     return cand
 
 
+HOST = ROOT / "feht_b200" / "host"
+CLI = ROOT / "feht_b200" / "bin" / "feht-b200"
+
+
 def _sources() -> list[Path]:
-    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")))
+    # kernels + C ABI, and the C++ host mirror (everything except the CLI's main) in one shared library
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + [HOST / "feht_host.cpp"])
 
 
 def _stamp(src: Path, flags: list[str]) -> str:
@@ -71,6 +76,15 @@ def build_cuda(verbose: bool = False, ptxas_info: bool = False) -> Path:
         objs.append(str(obj))
     if rebuilt or not LIB.exists():
         cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB), *objs]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+    # the command line (feht's own options) linked against the library next to it
+    main_src = HOST / "feht_main.cpp"
+    if rebuilt or not CLI.exists() or CLI.stat().st_mtime < main_src.stat().st_mtime:
+        CLI.parent.mkdir(parents=True, exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-I", str(ROOT / "include"), str(main_src), "-o", str(CLI),
+               "-L", str(LIB.parent), "-lfeht_cuda", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath-link," + str(LIB.parent)]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -30,6 +30,8 @@ EXPORTS = [
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device",
+    # include/feht_host.h
+    "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
 
 
@@ -109,6 +111,13 @@ def lib() -> C.CDLL:
     L.feht_result_fetch_device.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.feht_merge_sorted_device.argtypes = [vp, C.c_int, P(i64), P(vp), P(vp), C.c_int, P(vp)]
     L.feht_scatter_rows_device.argtypes = [vp, vp, vp, vp, i64, i32]
+    L.feht_host_run.argtypes = [C.c_char_p, i64, C.c_char_p, i64, C.c_char_p, C.c_char_p, C.c_char, C.c_int,
+                                C.c_int, f64, C.c_int, C.c_int, P(vp), P(i64), C.c_char_p, C.c_int]
+    L.feht_host_plan.argtypes = [C.c_char_p, i64, C.c_char_p, i64, C.c_char_p, C.c_char_p, C.c_char, C.c_int,
+                                 P(vp), P(i64), C.c_char_p, C.c_int]
+    L.feht_host_show_double.argtypes = [f64, C.c_char_p, C.c_int]
+    L.feht_host_free.argtypes = [vp]
+    L.feht_host_free.restype = None
     L.feht_set_row_base.argtypes = [vp, i64]
     L.feht_last_timings.argtypes = [vp, P(f64), C.c_int]
     L.feht_merge_sorted.argtypes = [C.c_int, P(i64), P(vp), P(vp), C.c_int, vp, vp]
@@ -125,6 +134,44 @@ def _ptr(a):
 
 def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class FehtHostError(RuntimeError):
+    """The reference host calls `error`; the C++ host mirror returns the same message."""
+
+
+def _host_call(fn, *args) -> bytes:
+    out, n = C.c_void_p(), C.c_int64()
+    err = C.create_string_buffer(1024)
+    rc = fn(*args, C.byref(out), C.byref(n), err, len(err))
+    if rc != OK:
+        raise FehtHostError(err.value.decode(errors="replace"))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib().feht_host_free(out)
+
+
+def host_run(metadata: bytes, data: bytes, one="all all", two="all all", delimiter=b"\t", mode="binary",
+             correction="bonferroni", ratio_filter=0.0, device=0, engine=ENGINE_AUTO) -> bytes:
+    """app/Main.hs:13-31 through the C++ host mirror + the CUDA hot path: the bytes feht prints."""
+    return _host_call(lib().feht_host_run, metadata, len(metadata), data, len(data), one.encode(), two.encode(),
+                      delimiter, int(mode == "snp"), int(correction == "bonferroni"), float(ratio_filter),
+                      device, engine)
+
+
+def host_plan(metadata: bytes, data: bytes, one="all all", two="all all", delimiter=b"\t", mode="binary") -> bytes:
+    """Parse + plan only (no GPU)."""
+    return _host_call(lib().feht_host_plan, metadata, len(metadata), data, len(data), one.encode(), two.encode(),
+                      delimiter, int(mode == "snp"))
+
+
+def host_show_double(x: float) -> str:
+    buf = C.create_string_buffer(64)
+    n = lib().feht_host_show_double(float(x), buf, len(buf))
+    if n < 0:
+        raise FehtHostError("show buffer too small")
+    return buf.value.decode()
 
 
 def version() -> str:

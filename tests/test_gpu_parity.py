@@ -520,3 +520,51 @@ def test_config2_full_size_properties(ctx):
         assert p_close(got["p"][i:i + 1], want["p"], np.array([True])).all()
     t = ctx.timings()
     assert t["count_launches"] >= 1 and t["total_ms"] > 0
+
+
+# ------------------------------------------------------------- the C++ host mirror, end to end
+@pytest.mark.parametrize("data_name,meta_name,delim,mode", [
+    ("test_binary.txt", "test_metadata.txt", b"\t", "binary"),
+    ("test_snps.txt", "test_metadata.txt", b"\t", "snp"),
+    ("test_snps.csv", "test_metadata.csv", b",", "snp"),
+])
+def test_host_run_prints_what_feht_prints(cuda_lib, fixture_bytes, data_name, meta_name, delim, mode):
+    """app/Main.hs:13-31 through feht_host_run: byte-identical to the oracle front-end's blocks (which
+    reproduce README.md:116-139,170-180,214-222), for every option combination of the CLI."""
+    data, meta = fixture_bytes[data_name], fixture_bytes[meta_name]
+    for one, two in (("all all", "all all"), ("group A", "group B"), ("position sideways", "all"),
+                     ("group A B", "position up")):
+        for correction in ("bonferroni", "none"):
+            for rf in (0.0, 0.5, 0.8, 1.0):
+                blocks, _ = frontend.run_files(meta, data, one=one, two=two, delimiter=delim, mode=mode,
+                                               correction=correction, ratio_filter=rf)
+                want = b"".join(b + b"\n" for b in blocks) + b"Done\n"
+                for engine in (capi.ENGINE_POPC, capi.ENGINE_AUTO):
+                    got = capi.host_run(meta, data, one, two, delim, mode, correction, rf, engine=engine)
+                    assert got == want, (one, two, correction, rf, engine)
+
+
+def test_host_run_readme_rows(cuda_lib, fixture_bytes):
+    """README.md:133: `binary9 2 0 1 4 ... 0.8` in the position sideways-vs-up block."""
+    out = capi.host_run(fixture_bytes["test_metadata.txt"], fixture_bytes["test_binary.txt"],
+                        "position sideways", "position up", ratio_filter=0.8)
+    assert b"Group1 category: position Group1: sideways\nGroup2 category: position Group2: up\n---\n" in out
+    assert b"binary9\t2\t0\t1\t4\t1.0\t0.8\n" in out
+    assert out.endswith(b"-#]\n\nDone\n")
+
+
+def test_cli_binary(cuda_lib, tmp_path):
+    import subprocess
+    from conftest import DATA, ROOT
+    exe = ROOT / "feht_b200" / "bin" / "feht-b200"
+    assert exe.exists(), "build the CLI with python -m feht_b200.build"
+    r = subprocess.run([str(exe), "-i", str(DATA / "test_metadata.txt"), "-d", str(DATA / "test_binary.txt"),
+                        "--one", "group A", "--two", "group B", "-f", "0.6", "-c", "none"],
+                       capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    want = capi.host_run((DATA / "test_metadata.txt").read_bytes(), (DATA / "test_binary.txt").read_bytes(),
+                         "group A", "group B", correction="none", ratio_filter=0.6)
+    assert r.stdout == want
+    assert b"binary4\t0\t5\t3\t1\t4.7619047619047616e-2\t-0.75\n" in r.stdout     # SURVEY.md 8c cross-check
+    bad = subprocess.run([str(exe), "-i", "/nonexistent", "-d", str(DATA / "test_binary.txt")], capture_output=True)
+    assert bad.returncode != 0

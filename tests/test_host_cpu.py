@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_library_exports_every_declared_symbol(cuda_lib):
-    header = (ROOT / "include" / "feht_cuda.h").read_text()
+    header = (ROOT / "include" / "feht_cuda.h").read_text() + (ROOT / "include" / "feht_host.h").read_text()
     declared = set(re.findall(r"\b(feht_[a-z_0-9]+)\s*\(", header))
     declared -= {"feht_ctx"}
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
@@ -66,3 +66,75 @@ def test_merge_sorted_equals_global_order(cuda_lib):
     out_s, out_i = capi.merge_sorted([np.array([0.1, 0.5]), np.array([]), np.array([0.2])],
                                      [np.array([0, 1]), np.array([]), np.array([2])], capi.SORT_PVALUE_ASC)
     assert list(zip(out_s, out_i)) == [(0, 0), (2, 0), (0, 1)]
+
+
+# ------------------------------------------------------------------ C++ host mirror (no GPU needed)
+def _plan_text(meta, data, one, two, delim, mode):
+    from oracle import frontend
+    pd = frontend.parse_data_file(delim, mode, data)
+    table = frontend.get_metadata_from_file(delim, pd, meta)
+    cl = frontend.get_comparison_list(table, frontend.generate_categories(one, two))
+    n_cols = len(data.split(b"\n")[0].replace(b"\r", b"").split(delim)) - 1
+    s = f"columns {n_cols} rows {len(pd.gene_vector_map)}\n".encode()
+    for c in cl:
+        d = c.details if c.details.endswith(b"\n") else c.details + b"\n"
+        s += b"comparison\n" + d
+        s += b"g1 " + b"".join(b"%d " % x for x in sorted(c.g1)) + b"\n"
+        s += b"g2 " + b"".join(b"%d " % x for x in sorted(c.g2)) + b"\n"
+    return s
+
+
+def test_host_show_double_matches_ghc_show(cuda_lib):
+    """GHC `show :: Double` (Comparison.hs:180-181): checked against the oracle front-end's restatement
+    and against literal strings feht prints (README.md:116-139)."""
+    import math
+    import numpy as np
+    from feht_b200 import capi
+    from oracle import frontend
+    lit = {1.0: "1.0", 0.0: "0.0", 0.8: "0.8", -0.8: "-0.8", 0.1: "0.1", 0.05: "5.0e-2", 1e7: "1.0e7",
+           9999999.0: "9999999.0", 12345678.9: "1.23456789e7", 0.047619047619047616: "4.7619047619047616e-2",
+           -0.6666666666666667: "-0.6666666666666667", 1.1131536985421843e-227: "1.1131536985421843e-227",
+           5e-324: "5.0e-324", 1.7976931348623157e308: "1.7976931348623157e308", 100.0: "100.0", 123.456: "123.456"}
+    for x, want in lit.items():
+        assert capi.host_show_double(x) == want, (x, capi.host_show_double(x))
+    assert capi.host_show_double(float("nan")) == "NaN"
+    assert capi.host_show_double(float("inf")) == "Infinity" and capi.host_show_double(-float("inf")) == "-Infinity"
+    assert capi.host_show_double(-0.0) == "-0.0"
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.random(2000), 10.0 ** rng.uniform(-320, 308, 2000), -rng.random(200) * 1e7,
+                         rng.integers(0, 10**9, 500) / 7.0])
+    for x in xs:
+        assert capi.host_show_double(float(x)) == frontend.show_double(float(x)), x
+
+
+@pytest.mark.parametrize("data_name,meta_name,delim,mode", [
+    ("test_binary.txt", "test_metadata.txt", b"\t", "binary"),
+    ("test_snps.txt", "test_metadata.txt", b"\t", "snp"),
+    ("test_snps.csv", "test_metadata.csv", b",", "snp"),
+])
+def test_host_planner_equals_frontend(cuda_lib, fixture_bytes, data_name, meta_name, delim, mode):
+    """N2/N3: parseDataFile + getMetadataFromFile + getComparisonList of the C++ host mirror against the
+    oracle front-end (descriptions byte for byte, column sets) for the reference fixtures."""
+    from feht_b200 import capi
+    data, meta = fixture_bytes[data_name], fixture_bytes[meta_name]
+    for one, two in (("all all", "all all"), ("group A", "group B"), ("group A B", "position up"),
+                     ("position sideways", "all"), ("group C", "group A B")):
+        got = capi.host_plan(meta, data, one, two, delim, mode)
+        assert got == _plan_text(meta, data, one, two, delim, mode), (one, two)
+
+
+def test_host_errors_are_the_reference_messages(cuda_lib, fixture_bytes):
+    from feht_b200 import capi
+    data, meta = fixture_bytes["test_binary.txt"], fixture_bytes["test_metadata.txt"]
+    cases = [((b"", data), "File is empty"),
+             ((meta.split(b"\n")[0] + b"\n", data), "Metadata file missing header information, data, or both"),
+             ((meta + b"nobody\tA\tup\n", data), "name was not found in the data file"),
+             ((meta.replace(b"\tup", b"", 1), data), "MetaCategories not equal to MeatValues"),
+             ((meta, b""), "No names present in data file")]
+    for (m, d), msg in cases:
+        with pytest.raises(capi.FehtHostError) as e:
+            capi.host_plan(m, d)
+        assert msg in str(e.value), (msg, str(e.value))
+    with pytest.raises(capi.FehtHostError) as e:
+        capi.host_plan(meta, data, one="", two="all all")
+    assert "No group one category given" in str(e.value)
