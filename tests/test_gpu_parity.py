@@ -568,3 +568,131 @@ def test_cli_binary(cuda_lib, tmp_path):
     assert b"binary4\t0\t5\t3\t1\t4.7619047619047616e-2\t-0.75\n" in r.stdout     # SURVEY.md 8c cross-check
     bad = subprocess.run([str(exe), "-i", "/nonexistent", "-d", str(DATA / "test_binary.txt")], capture_output=True)
     assert bad.returncode != 0
+
+
+# ------------------------------------------------------------- BASELINE sizes: configs 3, 4, 5
+def _check_sampled_tests_against_oracle(ctx, sp_o, snp, comps, vos_list, rows, n_total, correction, rf):
+    """Regenerate `rows` (marker-row indices) on the CPU from the counter-based generator and compare the
+    GPU's output rows for them with the oracle, comparison by comparison."""
+    for ci, (g1, g2) in comps.items():
+        got = ctx.fetch(ci)
+        pos = {int(r): i for i, r in enumerate(got["row"])}
+        for row in rows:
+            unit = row // 4 if snp else row
+            cells = oracle.synth_fill(sp_o, snp, int(unit), 1)
+            if snp:
+                cells = snp_expand(cells)[row % 4: row % 4 + 1]
+            want = oracle.run_comparison(cells, g1, g2, correction=correction, bonferroni_n=n_total)
+            keep = rf <= abs(want["ratio"][0])
+            assert (row in pos) == bool(keep), (ci, row, want["ratio"][0])
+            if keep:
+                i = pos[row]
+                assert (got["goa"][i], got["gob"][i], got["gta"][i], got["gtb"][i]) == \
+                    (want["goa"][0], want["gob"][0], want["gta"][0], want["gtb"][0]), (ci, row)
+                assert got["ratio"][i] == want["ratio"][0]
+                l = want["goa"][0] + want["gob"][0] + want["gta"][0] + want["gtb"][0]
+                assert p_close(got["p"][i:i + 1], want["p"], np.array([l >= 1000])).all(), (ci, row)
+
+
+def test_config3_snp_full_size(ctx):
+    """Config 3: 500k SNP sites x 10k genomes, one 4-value category -> 10 comparisons x 2M allele rows."""
+    S, SITES = 10_000, 500_000
+    sp_o = make_spec(oracle.SynthSpec, S, law="uniform_half")
+    ctx.set_samples(S)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), True, 0, SITES)
+    vos = (np.arange(S) * 4 // S).astype(np.int32)
+    ctx.add_category(vos, 4)
+    assert ctx.num_rows == 4 * SITES and ctx.num_comparisons == 10
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.0)
+    assert ctx.result_total() == 10 * 4 * SITES
+    groups = [np.flatnonzero(vos == v) for v in range(4)]
+    comps = {0: (groups[0], groups[1]), 5: (groups[2], groups[3]),
+             8: (groups[2], np.flatnonzero(vos != 2))}
+    for ci in comps:
+        got = ctx.fetch(ci)
+        assert (np.sort(got["row"]) == np.arange(4 * SITES)).all()
+        ar = np.abs(got["ratio"])
+        assert (ar[:-1] >= ar[1:]).all()
+        ties = ar[:-1] == ar[1:]
+        assert (got["row"][:-1][ties] < got["row"][1:][ties]).all()
+        # the four allele rows of a site partition its valid calls: per group, sum of '+' = N
+        o = np.argsort(got["row"])
+        n1 = (got["goa"] + got["gob"])[o].reshape(-1, 4)
+        assert (n1 == n1[:, :1]).all()
+        assert (got["goa"][o].reshape(-1, 4).sum(1) == n1[:, 0]).all()
+    rows = np.array([0, 1, 2, 3, 4 * 123456 + 2, 4 * SITES - 1, 777777])
+    _check_sampled_tests_against_oracle(ctx, sp_o, True, comps, None, rows, 4 * SITES, 1, 0.0)
+
+
+def test_config4_category_gemm_full_size(ctx):
+    """Config 4: 2M markers x 20k genomes, one 50-value category (1,225 pairs + 50 one-vs-rest), K2 GEMM
+    engine, ratioFilter 0.5.  Survivors checked against the oracle; a sample of non-survivors as well."""
+    S, R, V = 20_000, 2_000_000, 50
+    sp_o = make_spec(oracle.SynthSpec, S)
+    ctx.set_samples(S)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, 0, R)
+    vos = (np.arange(S) // (S // V)).astype(np.int32)
+    ctx.add_category(vos, V)
+    assert ctx.num_comparisons == V * (V - 1) // 2 + V
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.5)
+    t = ctx.timings()
+    assert t["engine"] == capi.ENGINE_GEMM
+    groups = [np.flatnonzero(vos == v) for v in range(V)]
+    # comparison indices: pair (i,j) -> i*V - i(i+1)/2 + j-i-1 ; one-vs-rest v -> V(V-1)/2 + v
+    pidx = lambda i, j: i * V - i * (i + 1) // 2 + (j - i - 1)
+    comps = {pidx(0, 25): (groups[0], groups[25]), pidx(24, 25): (groups[24], groups[25]),
+             pidx(3, 49): (groups[3], groups[49]), V * (V - 1) // 2 + 7: (groups[7], np.flatnonzero(vos != 7))}
+    total = ctx.result_total()
+    assert 0 < total < 10_000_000
+    for ci in comps:
+        got = ctx.fetch(ci)
+        ar = np.abs(got["ratio"])
+        assert (ar >= 0.5).all() and (ar[:-1] >= ar[1:]).all()
+        rows = np.concatenate([got["row"][:6], got["row"][-3:], np.array([0, 5, R - 1])])
+        _check_sampled_tests_against_oracle(ctx, sp_o, False, {ci: comps[ci]}, None, np.unique(rows), R, 1, 0.5)
+    # both engines give the same survivors (counts are bit-exact either way); K1 on a 200k-row prefix
+    ctx.clear_rows()
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, 0, 200_000)
+    res = {}
+    for eng in (capi.ENGINE_GEMM, capi.ENGINE_POPC):
+        ctx.set_count_engine(eng)
+        ctx.run(capi.CORRECTION_BONFERRONI, 0.5, capi.SORT_ABS_RATIO_DESC, R)
+        res[eng] = [ctx.fetch(ci) for ci in comps]
+    for a, b in zip(res[capi.ENGINE_GEMM], res[capi.ENGINE_POPC]):
+        for k in ("row", "goa", "gob", "gta", "gtb", "ratio", "p"):
+            assert (a[k] == b[k]).all(), k
+
+
+def test_config5_shard_four_categories(ctx):
+    """Config 5, one GPU's shard of the 8-GPU run: 1.25M of the 10M markers x 50k genomes, four categories
+    (2, 5, 10, 20 values -> 281 comparisons), ratioFilter 0.8, Bonferroni n = the global 10M."""
+    S, R, TOTAL = 50_000, 1_250_000, 10_000_000
+    sp_o = make_spec(oracle.SynthSpec, S)
+    ctx.set_samples(S)
+    first = 3 * R                                        # the fourth shard of eight
+    ctx.set_row_base(first)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, first, R)
+    rng = np.random.default_rng(5)
+    cats = [rng.integers(0, v, S).astype(np.int32) for v in (2, 5, 10, 20)]
+    for vos, v in zip(cats, (2, 5, 10, 20)):
+        ctx.add_category(vos, v)
+    assert ctx.num_comparisons == 1 + 15 + 55 + 210
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.8, capi.SORT_ABS_RATIO_DESC, TOTAL)
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM
+    assert ctx.result_total() == 0                       # random categories: no |ratio| >= 0.8
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.015, capi.SORT_ABS_RATIO_DESC, TOTAL)
+    # comparison 0 = the 2-value category; 1 + 15 + 3 = pair (0,3)... of the 10-value one
+    comps = {0: (np.flatnonzero(cats[0] == 0), np.flatnonzero(cats[0] == 1)),
+             1 + 4: (np.flatnonzero(cats[1] == 1), np.flatnonzero(cats[1] == 2)),
+             1 + 10 + 2: (np.flatnonzero(cats[1] == 2), np.flatnonzero(cats[1] != 2))}
+    for ci, (g1, g2) in comps.items():
+        got = ctx.fetch(ci)
+        assert len(got["row"]) > 0 and got["row"].min() >= first and got["row"].max() < first + R
+        for i in list(range(3)) + [len(got["row"]) - 1]:
+            row = int(got["row"][i])
+            cells = oracle.synth_fill(sp_o, False, row, 1)
+            want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=TOTAL)
+            assert (got["goa"][i], got["gob"][i], got["gta"][i], got["gtb"][i]) == \
+                (want["goa"][0], want["gob"][0], want["gta"][0], want["gtb"][0]), (ci, row)
+            assert got["ratio"][i] == want["ratio"][0] and abs(want["ratio"][0]) >= 0.015
+            assert p_close(got["p"][i:i + 1], want["p"], np.array([True])).all()
