@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <queue>
@@ -87,7 +88,7 @@ struct feht_ctx {
     DevBuf<double> r_p, r_ratio, o_p, o_ratio;
     SortWorkspace sw;
     DevBuf<unsigned long long> sw_key_a, sw_key_b;
-    DevBuf<uint32_t> sw_val_a, sw_val_b, sw_control, sw_oa;
+    DevBuf<uint32_t> sw_val_a, sw_val_b, sw_control, sw_oa, sw_coop;
     int rank_is_perm = -1;  // -1 unknown, 0 no, 1 name_rank is a permutation of [0, rows)
 
     bool has_results = false;
@@ -414,7 +415,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->o_goa); release(c->o_gob); release(c->o_gta); release(c->o_gtb);
     release(c->r_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
-    release(c->sw_control); release(c->sw_oa);
+    release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
@@ -626,6 +627,17 @@ extern "C" int feht_set_row_base(feht_ctx *c, int64_t row_base) {
 }
 
 // ====================================================================================== run ==
+namespace {
+// FEHT_SORT=onesweep keeps the tile-per-CTA sort for every size (A/B measurements and tests of that path)
+bool sort_engine_allows_coop() {
+    static const bool allow = [] {
+        const char *e = getenv("FEHT_SORT");
+        return !(e && std::string(e) == "onesweep");
+    }();
+    return allow;
+}
+}  // namespace
+
 extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
     if (!c) return FEHT_E_INVALID;
     if (int rc = use_device(c)) return rc;
@@ -919,10 +931,20 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     tp.r_cnt = c->r_cnt.p; tp.r_ratio = c->r_ratio.p;
     tp.seg_count = c->seg_count.p + n_comps;  // cursors (zeroed above)
     tp.seg_base = c->seg_base.p;
+    bool use_coop = false;
     if (n > 0) {
         CU(c, ensure(c->sw_key_a, nn)); CU(c, ensure(c->sw_key_b, nn));
         CU(c, ensure(c->sw_val_a, nn)); CU(c, ensure(c->sw_val_b, nn));
-        CU(c, ensure(c->sw_control, size_t(16) * 256 + 16 + size_t(16) * sort_status_words(n)));
+        use_coop = sort_engine_allows_coop() && c->num_sms <= coop_sort_max_grid() && n <= coop_sort_capacity(c->num_sms);
+        if (use_coop) {
+            if (!c->sw_coop.p) {
+                CU(c, ensure(c->sw_coop, coop_sort_control_words(c->num_sms)));
+                CU(c, cudaMemsetAsync(c->sw_coop.p, 0, coop_sort_control_words(c->num_sms) * 4, c->st));
+            }
+            c->sw.coop = c->sw_coop.p;
+        } else {
+            CU(c, ensure(c->sw_control, size_t(16) * 256 + 16 + size_t(16) * sort_status_words(n)));
+        }
         CU(c, ensure(c->sw_oa, 8));
         c->sw.key_a = c->sw_key_a.p; c->sw.key_b = c->sw_key_b.p;
         c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
@@ -940,12 +962,20 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
 
     // ---- K4 order
     if (n > 0) {
-        uint32_t *perm = nullptr;
-        CU(c, radix_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
         const ResultSoA out{c->o_row.p, c->o_rank.p, c->o_goa.p, c->o_gob.p, c->o_gta.p, c->o_gtb.p,
                             c->o_p.p, c->o_ratio.p};
-        CU(c, launch_gather_results(perm, n, c->row_base, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p,
-                                    c->r_ratio.p, out, c->st));
+        if (use_coop) {
+            // one wave of keys: every pass in a single cooperative launch, nothing read back by the host
+            CU(c, coop_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->num_sms, c->st, &launches));
+            CU(c, launch_gather_results(c->sw.val_a, c->sw.val_b, coop_sort_selector(c->sw, c->num_sms), n,
+                                        c->row_base, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p, c->r_ratio.p,
+                                        out, c->st));
+        } else {
+            uint32_t *perm = nullptr;
+            CU(c, radix_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
+            CU(c, launch_gather_results(perm, nullptr, nullptr, n, c->row_base, c->r_row.p, c->r_rank.p, c->r_cnt.p,
+                                        c->r_p.p, c->r_ratio.p, out, c->st));
+        }
         ++launches;
     }
     CU(c, cudaEventRecord(c->ev[3], c->st));

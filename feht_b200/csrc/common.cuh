@@ -145,6 +145,8 @@ struct SortWorkspace {
     uint32_t *val_a = nullptr, *val_b = nullptr;            // survivor indices (ping-pong)
     uint32_t *control = nullptr;  // [16][256] histograms, [16] tickets, [passes][tiles][256] status
     uint32_t *or_and = nullptr;   // 8 words
+    uint32_t *coop = nullptr;     // cooperative sort: [num_sms][256] tagged CTA digit counts, [num_sms] flags, selector
+    uint32_t coop_launches = 0;   // tag generator of the cooperative sort (host side)
 };
 size_t sort_status_words(int64_t n);
 // Sorts n survivors by (comp asc, key64 asc, rank asc); rank_presorted = the survivors already sit
@@ -158,9 +160,19 @@ struct ResultSoA {
     int32_t *rank, *goa, *gob, *gta, *gtb;
     double *p, *ratio;
 };
-cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, int64_t row_base, const int32_t *r_row,
-                                  const int32_t *r_rank, const int4 *r_cnt, const double *r_p,
-                                  const double *r_ratio, const ResultSoA &o, cudaStream_t st);
+// Single-wave variant (n <= coop_sort_capacity): every pass inside one cooperative launch, the pass list
+// decided on the device (no host synchronisation); the permutation ends up in ws.val_a or ws.val_b as the
+// device word coop_sort_selector() says (0 / 1).
+int64_t coop_sort_capacity(int num_sms);
+int coop_sort_max_grid();
+size_t coop_sort_control_words(int num_sms);
+cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+                           bool rank_presorted, int num_sms, cudaStream_t st, int *launches);
+const uint32_t *coop_sort_selector(const SortWorkspace &ws, int num_sms);
+// permutation = d_sel && *d_sel ? perm_b : perm_a
+cudaError_t launch_gather_results(const uint32_t *perm_a, const uint32_t *perm_b, const uint32_t *d_sel, int64_t n,
+                                  int64_t row_base, const int32_t *r_row, const int32_t *r_rank, const int4 *r_cnt,
+                                  const double *r_p, const double *r_ratio, const ResultSoA &o, cudaStream_t st);
 // K5: device k-way merge by ranking (dest[i][j] = final position of element j of shard i)
 int merge_max_shards();
 cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *const *d_key,

@@ -8,7 +8,9 @@
 //     key64 = ~bits(abs ratio)   (abs ratio in [0,1] => IEEE bits are monotone; inverted = descending)
 //           =  bits(p)           for FEHT_SORT_PVALUE_ASC
 //
-// Each pass is ONE kernel ("onesweep"): a CTA claims the next 4096-item tile from an atomic ticket,
+// Two engines.  Up to 8192 keys per SM (1.2M on a B200) the whole sort is one cooperative launch
+// (coop_sort_kernel below); beyond that each pass is ONE kernel ("onesweep"):
+// a CTA claims the next 2048-item tile from an atomic ticket,
 // ranks its items stably per digit (warp match-any + per-warp counters in shared memory), publishes
 // its per-digit counts and resolves the counts of all earlier tiles with a decoupled look-back over
 // a status word per (tile, digit), then scatters (key64, index) to the final positions.  The digit
@@ -29,7 +31,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kItems = 8;
-constexpr int kTile = kThreads * kItems;  // 4096
+constexpr int kTile = kThreads * kItems;  // 2048
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagPrefix = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
@@ -188,10 +190,256 @@ __global__ void __launch_bounds__(kThreads) onesweep_pass_kernel(PassArgs A) {
     }
 }
 
+
+// ---- single-wave variant: all passes in ONE cooperative launch.
+// With at most kCoopCap items per SM the whole job is one wave, and the look-back of the tile-per-CTA
+// kernel above degenerates into a serial walk over every earlier tile (nobody has a prefix yet): ncu
+// showed 23-32 us per pass at 1M keys, 12% issue-active, the hottest line the look-back spin.  Here each
+// CTA owns one contiguous chunk (<= 8192 items), ranks it, stages it in shared memory in digit order and
+// writes each digit's run with consecutive threads on consecutive addresses.  The CTAs exchange their
+// per-digit counts through a [grid][256] table of self-validating words (pass tag << 16 | count): a
+// reader spins only on the words it needs, so there is no grid barrier in front of the prefix; the one
+// barrier per pass (a counter) stands between a pass's writes and the next pass's reads.  Which passes
+// run is decided on the device from the OR/AND words K3b left behind, so the host neither synchronises
+// nor copies anything before the launch.  1M keys x 8 passes: 241 us (tile-per-CTA) -> 131 us + gather.
+constexpr int kCoopThreads = 1024;
+constexpr int kCoopWarps = kCoopThreads / 32;
+constexpr int kCoopItems = 8;
+constexpr int kCoopCap = kCoopThreads * kCoopItems;   // items per CTA
+
+struct CoopArgs {
+    unsigned long long *key[2];
+    uint32_t *val[2];
+    int64_t n;
+    int chunk;                  // items per CTA (last CTA may hold fewer)
+    int rounds;                 // ceil(chunk / kCoopThreads) <= kCoopItems
+    const uint32_t *or_and;     // [8]: OR of (rank, key lo, key hi, comp), then AND of the same
+    const uint32_t *r_rank, *r_comp;
+    int rank_presorted;
+    uint32_t *hist;             // [grid][256] per-CTA digit counts of the current pass: tag << 16 | count
+    uint32_t *sel;              // out: which val buffer holds the permutation
+    uint32_t tag_base;          // 32 * launch number: tags of different launches never coincide
+    uint32_t *bar;              // grid barrier counter between passes, zeroed before the launch
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// polling load: volatile asm, or the compiler folds the re-load of a spin loop into the first load and
+// drops the loop (a side-effect-free loop may be assumed to terminate)
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void grid_barrier(uint32_t *bar, unsigned &target) {
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_acquire_u32(bar) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr size_t kCoopDynSmem = size_t(kCoopCap) * (8 + 4 + 1);
+
+__global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid_constant__ CoopArgs A) {
+    // cnt: per-warp digit counters while ranking; afterwards the same 32 KB hold the partial sums of the
+    // cross-CTA prefix (16 slices x {before, total} x 256 digits)
+    __shared__ __align__(16) unsigned int cnt[kCoopWarps][256];
+    __shared__ unsigned int lstart[256];   // CTA-local start of each digit in the staged order
+    __shared__ unsigned int goff[256];     // global position of staged index 0 of each digit
+    __shared__ unsigned int wsum[8];
+    extern __shared__ __align__(16) unsigned char dyn[];
+    unsigned long long *stage_k = reinterpret_cast<unsigned long long *>(dyn);
+    uint32_t *stage_v = reinterpret_cast<uint32_t *>(dyn + size_t(kCoopCap) * 8);
+    unsigned char *stage_d = dyn + size_t(kCoopCap) * 12;
+    unsigned int(*part)[256] = cnt;        // [0..15] before, [16..31] total
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int64_t base = int64_t(cta) * A.chunk;
+    const int count = int(min(int64_t(A.chunk), max(int64_t(0), A.n - base)));
+    const int rounds = A.rounds;
+    const int wbase = wid * 32 * rounds;
+    uint32_t oa[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) oa[j] = A.or_and[j];
+    // candidate digits, least significant first: 4 name-rank bytes, 8 key bytes, 4 comparison bytes;
+    // a digit that is the same in every key needs no pass
+    unsigned todo = 0;
+#pragma unroll
+    for (int cand = 0; cand < 16; ++cand) {
+        const int w = cand < 4 ? 0 : (cand < 8 ? 1 : (cand < 12 ? 2 : 3));
+        if (((((oa[w] ^ oa[4 + w]) >> (8 * (cand & 3))) & 255u) != 0u) && !(cand < 4 && A.rank_presorted))
+            todo |= 1u << cand;
+    }
+    uint32_t tag = A.tag_base;
+    int cur = 0;
+    unsigned target = 0;
+
+    while (todo) {
+        const int cand = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int src = (cand >= 4 && cand < 12) ? 0 : 1;
+        const int shift = src == 0 ? 8 * (cand - 4) : 8 * (cand & 3);
+        const uint32_t *word = cand < 4 ? A.r_rank : A.r_comp;
+        ++tag;
+
+        const unsigned long long *kin = A.key[cur];
+        const uint32_t *vin = A.val[cur];
+        unsigned long long *kout = A.key[cur ^ 1];
+        uint32_t *vout = A.val[cur ^ 1];
+
+        for (int j = tid; j < kCoopWarps * 256; j += kCoopThreads) (&cnt[0][0])[j] = 0;
+        unsigned long long k[kCoopItems];
+        uint32_t v[kCoopItems];
+        uint32_t dr[kCoopItems];   // digit | rank inside the warp's items << 9
+#pragma unroll
+        for (int it = 0; it < kCoopItems; ++it) {
+            const int li = wbase + it * 32 + lane;
+            const bool in = it < rounds && li < count;
+            // .cg: the ping-pong buffers are rewritten by other SMs every pass
+            k[it] = in ? __ldcg(kin + base + li) : 0ull;
+            v[it] = in ? __ldcg(vin + base + li) : 0u;
+        }
+        __syncthreads();
+        // stable rank of every item among the warp's items with the same digit (issuing all the MATCH ops
+        // first was tried: it spills under the 64-register cap and came out 4% slower)
+#pragma unroll
+        for (int it = 0; it < kCoopItems; ++it) {
+            if (it < rounds) {
+                const bool in = wbase + it * 32 + lane < count;
+                const uint32_t d = in ? digit_of(src, shift, k[it], v[it], word) : 256u;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                const unsigned lower = peers & ((1u << lane) - 1u);
+                uint32_t b = 0;
+                if (d < 256u) b = cnt[wid][d];
+                __syncwarp();
+                if (d < 256u && lower == 0) cnt[wid][d] = b + __popc(peers);
+                __syncwarp();
+                dr[it] = d | ((b + __popc(lower)) << 9);
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned run = 0;
+#pragma unroll 8
+            for (int ww = 0; ww < kCoopWarps; ++ww) {
+                const unsigned c = cnt[ww][tid];
+                cnt[ww][tid] = run;
+                run += c;
+            }
+            A.hist[size_t(cta) * 256 + tid] = (tag << 16) | run;   // published: the tag makes the word self-validating
+            unsigned inc = run;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            unsigned wb = 0;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww)
+                if (ww < wid) wb += wsum[ww];
+            lstart[tid] = wb + inc - run;
+        }
+        __syncthreads();
+        // stage the chunk in digit order (stable): needs nothing from the other CTAs
+#pragma unroll
+        for (int it = 0; it < kCoopItems; ++it) {
+            if (it < rounds) {
+                const uint32_t d = dr[it] & 511u;
+                if (d < 256u) {
+                    const uint32_t li = lstart[d] + cnt[wid][d] + (dr[it] >> 9);
+                    stage_k[li] = k[it];
+                    stage_v[li] = v[it];
+                    stage_d[li] = (unsigned char)d;
+                }
+            }
+        }
+        __syncthreads();
+        {
+            // counts of every digit in the CTAs before me and in all CTAs: thread = 4 digits x one of 16
+            // slices of the CTA list, 128-bit loads, all of a thread's loads in flight together.  No grid
+            // barrier: a word is valid once it carries this pass's tag, so a thread only waits for the
+            // words it needs (one L2 round trip after the slowest CTA published).
+            const int q = tid & 63, grp = tid >> 6;
+            uint4 before = make_uint4(0, 0, 0, 0), total = make_uint4(0, 0, 0, 0);
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(A.hist);
+            constexpr int kSlice = 10;   // 16 x 10 >= any grid this kernel is launched with
+            uint4 h[kSlice];
+#pragma unroll
+            for (int j = 0; j < kSlice; ++j) {
+                const int c = grp + 16 * j;
+                h[j] = c < G ? __ldcg(h4 + size_t(c) * 64 + q) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < kSlice; ++j) {
+                const int c = grp + 16 * j;
+                if (c < G) {
+                    while ((h[j].x >> 16) != tag || (h[j].y >> 16) != tag || (h[j].z >> 16) != tag ||
+                           (h[j].w >> 16) != tag)
+                        h[j] = ld_relaxed_v4(h4 + size_t(c) * 64 + q);
+                    const uint4 m = make_uint4(h[j].x & 0xffffu, h[j].y & 0xffffu, h[j].z & 0xffffu, h[j].w & 0xffffu);
+                    total.x += m.x; total.y += m.y; total.z += m.z; total.w += m.w;
+                    if (c < cta) { before.x += m.x; before.y += m.y; before.z += m.z; before.w += m.w; }
+                }
+            }
+            *reinterpret_cast<uint4 *>(&part[grp][4 * q]) = before;
+            *reinterpret_cast<uint4 *>(&part[16 + grp][4 * q]) = total;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned before = 0, total = 0;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                before += part[g][tid];
+                total += part[16 + g][tid];
+            }
+            unsigned inc = total;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            unsigned wb = 0;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww)
+                if (ww < wid) wb += wsum[ww];
+            goff[tid] = wb + inc - total + before - lstart[tid];
+        }
+        __syncthreads();
+        // consecutive threads write consecutive addresses inside each digit's run
+        for (int li = tid; li < count; li += kCoopThreads) {
+            const uint32_t pos = goff[stage_d[li]] + uint32_t(li);
+            kout[pos] = stage_k[li];
+            vout[pos] = stage_v[li];
+        }
+        cur ^= 1;
+        // the next pass reads what every CTA just wrote.  (One flag per CTA with every CTA polling all
+        // flags was measured slower than the single counter: 0.176 vs 0.156 ms per 1M-key sort.)
+        if (todo) grid_barrier(A.bar, target);
+    }
+    if (cta == 0 && tid == 0) *A.sel = uint32_t(cur);
+}
+
 __global__ void __launch_bounds__(256)
-gather_kernel(const uint32_t *__restrict__ perm, int64_t n, int64_t row_base, const int32_t *__restrict__ r_row,
+gather_kernel(const uint32_t *__restrict__ perm_a, const uint32_t *__restrict__ perm_b,
+              const uint32_t *__restrict__ sel, int64_t n, int64_t row_base, const int32_t *__restrict__ r_row,
               const int32_t *__restrict__ r_rank, const int4 *__restrict__ r_cnt,
               const double *__restrict__ r_p, const double *__restrict__ r_ratio, ResultSoA o) {
+    // the cooperative sort decides on the device how many passes run, hence where the permutation ends up
+    const uint32_t *__restrict__ perm = (sel && *sel) ? perm_b : perm_a;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += int64_t(gridDim.x) * blockDim.x) {
         const uint32_t s = perm[i];
@@ -335,11 +583,56 @@ cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank,
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather_results(const uint32_t *perm, int64_t n, int64_t row_base, const int32_t *r_row,
-                                  const int32_t *r_rank, const int4 *r_cnt, const double *r_p,
-                                  const double *r_ratio, const ResultSoA &o, cudaStream_t st) {
+int64_t coop_sort_capacity(int num_sms) { return int64_t(num_sms) * kCoopCap; }
+int coop_sort_max_grid() { return 160; }   // kSlice * 16 in the kernel
+size_t coop_sort_control_words(int num_sms) { return size_t(num_sms) * 256 + 8; }
+
+cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+                           bool rank_presorted, int num_sms, cudaStream_t st, int *launches) {
+    // control block: [grid][256] tagged counts, the buffer selector, the barrier counter
+    uint32_t *sel = ws.coop + size_t(num_sms) * 256;
+    cudaError_t e = cudaMemsetAsync(sel, 0, 2 * sizeof(uint32_t), st);
+    if (e != cudaSuccess || n <= 1) return e;
+    CoopArgs a{};
+    a.key[0] = ws.key_a; a.key[1] = ws.key_b;
+    a.val[0] = ws.val_a; a.val[1] = ws.val_b;
+    a.n = n;
+    // whole warps per CTA, as few CTAs idle as possible
+    int64_t chunk = (n + num_sms - 1) / num_sms;
+    chunk = (chunk + kCoopThreads - 1) / kCoopThreads * kCoopThreads;
+    a.chunk = int(chunk);
+    a.rounds = int(chunk / kCoopThreads);
+    a.or_and = ws.or_and;
+    a.r_rank = reinterpret_cast<const uint32_t *>(r_rank);
+    a.r_comp = reinterpret_cast<const uint32_t *>(r_comp);
+    a.rank_presorted = rank_presorted ? 1 : 0;
+    a.hist = ws.coop;
+    a.sel = sel;
+    a.bar = sel + 1;
+    // the control block is zeroed when it is allocated; a launch uses tags base+1 .. base+16 (never 0, no
+    // overlap with the launches before it; the sequence repeats after 2047 launches, by when every slot in
+    // use has been rewritten many times)
+    ws.coop_launches = ws.coop_launches % 2047u + 1u;
+    a.tag_base = ws.coop_launches * 32u;
+    const int grid = int((n + chunk - 1) / chunk);
+    static const cudaError_t attr = cudaFuncSetAttribute(coop_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         int(kCoopDynSmem));
+    if (attr != cudaSuccess) return attr;
+    void *args[] = {&a};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(coop_sort_kernel), dim3(grid), dim3(kCoopThreads),
+                                    args, kCoopDynSmem, st);
+    if (launches) ++*launches;
+    return e;
+}
+
+const uint32_t *coop_sort_selector(const SortWorkspace &ws, int num_sms) { return ws.coop + size_t(num_sms) * 256; }
+
+cudaError_t launch_gather_results(const uint32_t *perm_a, const uint32_t *perm_b, const uint32_t *d_sel, int64_t n,
+                                  int64_t row_base, const int32_t *r_row, const int32_t *r_rank, const int4 *r_cnt,
+                                  const double *r_p, const double *r_ratio, const ResultSoA &o, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(perm, n, row_base, r_row, r_rank, r_cnt, r_p, r_ratio, o);
+    gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(perm_a, perm_b, d_sel, n, row_base, r_row, r_rank, r_cnt, r_p,
+                                                      r_ratio, o);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,9 @@ def run(cfg, rows, engine, steps, ratio_filter=None):
             S, snp, rf = 50_000, False, 0.8
             rng = np.random.default_rng(5)
             cats = [[rng.integers(0, v, S).astype(np.int32), v] for v in (2, 5, 10, 20)]
+        elif cfg == "c2":    # 1M x 5k, one comparison 2500 vs 2500 (the bench.py workload)
+            S, snp, rf = 5_000, False, 0.0
+            cats = []
         elif cfg == "c2b":   # 1M x 5k, groups of 300 / 400 genomes: hypergeometric branch (l ~ 693)
             S, snp, rf = 5_000, False, 0.0
             cats = []
@@ -42,6 +45,8 @@ def run(cfg, rows, engine, steps, ratio_filter=None):
         ctx.generate_synthetic(sp, snp, 0, rows)
         if cfg == "c2b":
             ctx.add_comparison(np.arange(0, 300), np.arange(300, 700))
+        if cfg == "c2":
+            ctx.add_comparison(np.arange(0, 2500), np.arange(2500, 5000))
         for vos, nv in cats:
             ctx.add_category(vos, nv)
         ctx.set_count_engine(eng)
