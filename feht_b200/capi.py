@@ -29,7 +29,7 @@ EXPORTS = [
     "feht_set_count_engine", "feht_run", "feht_result_count", "feht_result_total",
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
-    "feht_scatter_rows_device",
+    "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
     L.feht_comparison_info.argtypes = [vp, i64, P(i32), P(i32), P(i32), P(i32)]
     L.feht_set_count_engine.argtypes = [vp, C.c_int]
     L.feht_run.argtypes = [vp, C.c_int, f64, C.c_int, i64]
+    L.feht_run_async.argtypes = [vp, C.c_int, f64, C.c_int, i64]
+    L.feht_timings_accumulated.argtypes = [vp, P(f64), C.c_int, C.c_int]
     L.feht_result_count.argtypes = [vp, i64]
     L.feht_result_count.restype = i64
     L.feht_result_total.argtypes = [vp]
@@ -345,6 +347,11 @@ class Context:
             bonferroni_n=0):
         self._check(self._L.feht_run(self._h, correction, float(ratio_filter), sort_key, bonferroni_n))
 
+    def run_async(self, correction=CORRECTION_BONFERRONI, ratio_filter=0.0, sort_key=SORT_ABS_RATIO_DESC,
+                  bonferroni_n=0):
+        """Enqueue the run on the context's stream; result / timing accessors synchronise."""
+        self._check(self._L.feht_run_async(self._h, correction, float(ratio_filter), sort_key, bonferroni_n))
+
     def result_count(self, c: int) -> int:
         return int(self._check(self._L.feht_result_count(self._h, c)))
 
@@ -392,6 +399,12 @@ class Context:
         self._check(self._L.feht_last_timings(self._h, buf, 8))
         keys = ["count_ms", "test_ms", "order_ms", "total_ms", "launches", "count_launches", "count_bytes",
                 "engine"]
+        return dict(zip(keys, list(buf)))
+
+    def timings_accumulated(self, reset: bool = False) -> dict:
+        buf = (C.c_double * 7)()
+        self._check(self._L.feht_timings_accumulated(self._h, buf, 7, 1 if reset else 0))
+        keys = ["runs", "count_ms", "test_ms", "order_ms", "total_ms", "launches", "count_launches"]
         return dict(zip(keys, list(buf)))
 
     def eval_tables(self, goa, gob, gta, gtb):

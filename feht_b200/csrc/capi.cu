@@ -48,7 +48,12 @@ struct feht_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t own_stream = nullptr, st = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // stage events of a run, two sets used alternately: feht_run_async re-records a set only after the run
+    // before last has been timed, so consecutive runs can be enqueued without a host synchronisation
+    cudaEvent_t evr[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    struct PendingRun { bool active = false; double launches = 0, count_launches = 0, count_bytes = 0; } pend[2];
+    int ev_slot = 0;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // runs, count/test/order/total ms, launches, count launches
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     std::string err;
 
@@ -390,7 +395,8 @@ extern "C" int feht_create(feht_ctx **out, int device) {
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     c->st = c->own_stream;
     for (int i = 0; i < 4; ++i)
-        if ((e = cudaEventCreate(&c->ev[i])) != cudaSuccess) return bail("event", e);
+        for (int k = 0; k < 2; ++k)
+            if ((e = cudaEventCreate(&c->evr[k][i])) != cudaSuccess) return bail("event", e);
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
         if ((e = cudaEventCreateWithFlags(&c->ev_used[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
@@ -417,7 +423,8 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
     if (c->d_choose) cudaFree(c->d_choose);
-    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < 4; ++i) if (c->evr[k][i]) cudaEventDestroy(c->evr[k][i]);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_used[i]) cudaEventDestroy(c->ev_used[i]);
@@ -638,10 +645,39 @@ bool sort_engine_allows_coop() {
 }
 }  // namespace
 
-extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
+namespace {
+// stage times of the run recorded in event set `slot` (waits for that run to finish)
+int settle(feht_ctx *c, int slot) {
+    feht_ctx::PendingRun &pr = c->pend[slot];
+    if (!pr.active) return FEHT_OK;
+    cudaEvent_t *ev = c->evr[slot];
+    CU(c, cudaEventSynchronize(ev[3]));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, ev[0], ev[1])); c->tm.count_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms, ev[1], ev[2])); c->tm.test_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms, ev[2], ev[3])); c->tm.order_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms, ev[0], ev[3])); c->tm.total_ms = ms;
+    c->tm.launches = pr.launches;
+    c->tm.count_launches = pr.count_launches;
+    c->tm.count_bytes = pr.count_bytes;
+    c->acc[0] += 1; c->acc[1] += c->tm.count_ms; c->acc[2] += c->tm.test_ms; c->acc[3] += c->tm.order_ms;
+    c->acc[4] += c->tm.total_ms; c->acc[5] += pr.launches; c->acc[6] += pr.count_launches;
+    pr.active = false;
+    return FEHT_OK;
+}
+// older run first, so that c->tm ends up describing the last one
+int settle_all(feht_ctx *c) {
+    if (int rc = settle(c, c->ev_slot ^ 1)) return rc;
+    return settle(c, c->ev_slot);
+}
+
+int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n, bool async) {
     if (!c) return FEHT_E_INVALID;
     if (int rc = use_device(c)) return rc;
     c->has_results = false;
+    c->ev_slot ^= 1;
+    if (int rc = settle(c, c->ev_slot)) return rc;   // the run before last: finished long ago
+    cudaEvent_t *const ev = c->evr[c->ev_slot];
     if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
     if (correction != FEHT_CORRECTION_NONE && correction != FEHT_CORRECTION_BONFERRONI)
         return fail(c, FEHT_E_INVALID, "unknown correction %d", correction);
@@ -655,8 +691,12 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     if (bonferroni_n <= 0) bonferroni_n = R;
     c->seg_off.assign(size_t(n_comps) + 1, 0);
     c->n_surv = 0;
-    c->tm = Timings();
-    if (n_comps == 0 || R == 0) { c->has_results = true; return FEHT_OK; }
+    if (n_comps == 0 || R == 0) {
+        if (int rc = settle_all(c)) return rc;
+        c->tm = Timings();
+        c->has_results = true;
+        return FEHT_OK;
+    }
 
     // V.! bounds (Comparison.hs:123): every referenced column must exist in every row
     const int64_t row_len = std::min(c->min_row_len, c->S);
@@ -857,7 +897,7 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
     }
     c->last_engine = use_gemm ? FEHT_ENGINE_GEMM : FEHT_ENGINE_POPC;
 
-    CU(c, cudaEventRecord(c->ev[0], c->st));
+    CU(c, cudaEventRecord(ev[0], c->st));
     const int n_popc_slots = use_gemm ? n_explicit : n_slots;
     if (c->snp == 1)
         CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
@@ -870,7 +910,7 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
                                 c->gemm_passes.p, c->gemm_n_passes, c->counts.p, c->num_sms, c->st,
                                 &count_launches));
     launches += count_launches;
-    CU(c, cudaEventRecord(c->ev[1], c->st));
+    CU(c, cudaEventRecord(ev[1], c->st));
 
     // ---- K3 test + correct + filter
     TestParams tp{};
@@ -958,7 +998,7 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
                              c->r_comp.p, c->st));
         ++launches;
     }
-    CU(c, cudaEventRecord(c->ev[2], c->st));
+    CU(c, cudaEventRecord(ev[2], c->st));
 
     // ---- K4 order
     if (n > 0) {
@@ -978,19 +1018,28 @@ extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int so
         }
         ++launches;
     }
-    CU(c, cudaEventRecord(c->ev[3], c->st));
-    CU(c, cudaStreamSynchronize(c->st));
-    float ms = 0;
-    CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->tm.count_ms = ms;
-    CU(c, cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->tm.test_ms = ms;
-    CU(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->tm.order_ms = ms;
-    CU(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[3])); c->tm.total_ms = ms;
-    c->tm.launches = launches;
-    c->tm.count_launches = count_launches;
-    const int n_planes = c->snp == 1 ? 3 : 2;
-    c->tm.count_bytes = double(c->n_units) * double((c->S + 63) / 64) * 8.0 * n_planes;
+    CU(c, cudaEventRecord(ev[3], c->st));
+    {
+        feht_ctx::PendingRun &pr = c->pend[c->ev_slot];
+        pr.active = true;
+        pr.launches = launches;
+        pr.count_launches = count_launches;
+        const int n_planes = c->snp == 1 ? 3 : 2;
+        pr.count_bytes = double(c->n_units) * double((c->S + 63) / 64) * 8.0 * n_planes;
+    }
+    if (!async)
+        if (int rc = settle_all(c)) return rc;
     c->has_results = true;
     return FEHT_OK;
+}
+}  // namespace
+
+extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
+    return run_impl(c, correction, ratio_filter, sort_key, bonferroni_n, false);
+}
+
+extern "C" int feht_run_async(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
+    return run_impl(c, correction, ratio_filter, sort_key, bonferroni_n, true);
 }
 
 extern "C" int64_t feht_result_count(const feht_ctx *c, int64_t comparison) {
@@ -1063,11 +1112,24 @@ extern "C" int feht_scatter_rows_device(feht_ctx *c, const void *d_src, void *d_
     return FEHT_OK;
 }
 
-extern "C" int feht_last_timings(const feht_ctx *c, double *out, int n) {
-    if (!c || !out) return FEHT_E_INVALID;
+extern "C" int feht_last_timings(const feht_ctx *cc, double *out, int n) {
+    if (!cc || !out) return FEHT_E_INVALID;
+    feht_ctx *c = const_cast<feht_ctx *>(cc);
+    if (int rc = use_device(c)) return rc;
+    if (int rc = settle_all(c)) return rc;
     const double v[8] = {c->tm.count_ms, c->tm.test_ms, c->tm.order_ms, c->tm.total_ms,
                          c->tm.launches, c->tm.count_launches, c->tm.count_bytes, double(c->last_engine)};
     for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    return FEHT_OK;
+}
+
+extern "C" int feht_timings_accumulated(feht_ctx *c, double *out, int n, int reset) {
+    if (!c || !out) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    if (int rc = settle_all(c)) return rc;
+    for (int i = 0; i < n && i < 7; ++i) out[i] = c->acc[i];
+    if (reset)
+        for (double &a : c->acc) a = 0;
     return FEHT_OK;
 }
 

@@ -165,6 +165,13 @@ int feht_set_count_engine(feht_ctx *ctx, int engine);
  */
 int feht_run(feht_ctx *ctx, int correction, double ratio_filter, int sort_key,
              int64_t bonferroni_n);
+/* The same work, enqueued on the context's stream without waiting for it: the call returns as soon as the
+ * host has nothing left to do (immediately for ratio_filter <= 0, where the output size is known up front;
+ * a filtered run still waits for the survivor counts).  feht_result_* / feht_last_timings synchronise.  A
+ * host that pipelines several data sets (or the benchmark's back-to-back steps) uses this; the Haskell
+ * shim calls the blocking feht_run. */
+int feht_run_async(feht_ctx *ctx, int correction, double ratio_filter, int sort_key,
+                   int64_t bonferroni_n);
 
 /* Surviving rows of comparison c, in final order. */
 int64_t feht_result_count(const feht_ctx *ctx, int64_t comparison);
@@ -189,6 +196,9 @@ int feht_set_row_base(feht_ctx *ctx, int64_t row_base);
  * out[5] count-kernel launches, out[6] algorithmic bytes read by the count stage,
  * out[7] engine that counted the categories (FEHT_ENGINE_POPC or FEHT_ENGINE_GEMM). */
 int feht_last_timings(const feht_ctx *ctx, double *out, int n);
+/* Sums over every run since the last reset (waits for the enqueued runs): out[0] runs, out[1] count ms,
+ * out[2] test ms, out[3] order ms, out[4] total ms, out[5] kernel launches, out[6] count-kernel launches. */
+int feht_timings_accumulated(feht_ctx *ctx, double *out, int n, int reset);
 
 /*
  * Host k-way merge of sorted shards of one comparison: shard i has n[i] rows with

@@ -16,6 +16,7 @@ from oracle import frontend
 from helpers import copy_spec, make_spec, p_close, pack_rows, pack_snp, snp_expand
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = __import__("pathlib").Path(__file__).resolve().parent.parent
 
 
 def _random_chars(rng, n_rows, n_samples, p_missing=0.05, ragged=False):
@@ -696,3 +697,76 @@ def test_config5_shard_four_categories(ctx):
                 (want["goa"][0], want["gob"][0], want["gta"][0], want["gtb"][0]), (ci, row)
             assert got["ratio"][i] == want["ratio"][0] and abs(want["ratio"][0]) >= 0.015
             assert p_close(got["p"][i:i + 1], want["p"], np.array([True])).all()
+
+
+# ------------------------------------------------------------------------------------ async run / sort engines
+def test_run_async_back_to_back_equals_blocking_run(ctx):
+    """feht_run_async enqueues without waiting; three runs back to back (the third re-uses the event set of
+    the first) must leave the results of a blocking run, and the accumulated stage times must count them."""
+    rng = np.random.default_rng(2024)
+    cells = _random_chars(rng, 5000, 400)
+    g1, g2 = np.arange(0, 150), np.arange(150, 400)
+    ctx.set_samples(400)
+    ctx.add_rows_chars(cells)
+    ctx.add_comparison(g1, g2)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.0)
+    want = ctx.fetch(0)
+    ctx.timings_accumulated(reset=True)
+    for _ in range(3):
+        ctx.run_async(capi.CORRECTION_BONFERRONI, 0.0)
+    got = ctx.fetch(0)
+    for k in want:
+        a, b = want[k], got[k]
+        assert ((a == b) | ((a != a) & (b != b))).all(), k
+    acc = ctx.timings_accumulated()
+    assert int(acc["runs"]) == 3 and acc["count_ms"] > 0 and acc["total_ms"] >= acc["count_ms"]
+    assert int(acc["launches"]) == 3 * int(ctx.timings()["launches"])
+    # a filtered run through the async entry point (it has to wait for the survivor counts itself)
+    ctx.run(capi.CORRECTION_NONE, 0.05)
+    want = ctx.fetch(0)
+    ctx.run_async(capi.CORRECTION_NONE, 0.05)
+    got = ctx.fetch(0)
+    assert len(want["row"]) > 0 and (want["row"] == got["row"]).all() and (want["p"] == got["p"]).all()
+
+
+def test_sort_engines_agree(cuda_lib):
+    """K4 has two engines: one cooperative launch (up to 8192 survivors per SM) and one kernel per pass
+    (tile per CTA, look-back).  FEHT_SORT=onesweep forces the second at any size (read once per process,
+    hence the subprocesses); both must give the oracle's order on many comparisons, filtered output (name-rank
+    passes) and the p-value key."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import oracle, hashlib
+        from feht_b200 import capi
+        rng = np.random.default_rng(31)
+        S, R = 240, 30000
+        f = rng.beta(0.4, 0.4, size=(R, 1))
+        cells = np.where(rng.random((R, S)) < f, ord('1'), ord('0')).astype(np.uint8)
+        cells[rng.random((R, S)) < 0.03] = ord('-')
+        vos = rng.integers(0, 6, size=S).astype(np.int32)
+        rank = rng.permutation(R).astype(np.int32)
+        h = hashlib.sha256()
+        with capi.Context(0) as ctx:
+            ctx.set_samples(S); ctx.add_rows_chars(cells, name_rank=rank); ctx.add_category(vos, 6)
+            for rf, key in ((0.0, capi.SORT_ABS_RATIO_DESC), (0.25, capi.SORT_ABS_RATIO_DESC), (0.0, capi.SORT_PVALUE_ASC)):
+                ctx.run(capi.CORRECTION_BONFERRONI, rf, key)
+                for ci in range(ctx.num_comparisons):
+                    got = ctx.fetch(ci)
+                    for k in ("row", "goa", "gob", "gta", "gtb", "p", "ratio"):
+                        h.update(np.ascontiguousarray(got[k]).tobytes())
+                    r = np.abs(got["ratio"])
+                    if key == capi.SORT_ABS_RATIO_DESC:
+                        assert (r[:-1] >= r[1:]).all()
+                        tie = r[:-1] == r[1:]
+                        assert (rank[got["row"][:-1]][tie] < rank[got["row"][1:]][tie]).all()
+        print(h.hexdigest())
+    """) % (str(ROOT_DIR), str(ROOT_DIR / "tests"))
+    digests = {}
+    for eng in ("coop", "onesweep"):
+        env = dict(os.environ, FEHT_SORT=eng)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[eng] = r.stdout.strip().split()[-1]
+    assert digests["coop"] == digests["onesweep"]
