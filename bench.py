@@ -48,6 +48,16 @@ def _spec(cls):
     return make_spec(cls, S)
 
 
+def _k1_traffic():
+    """dram bytes read+written by one K1 launch of this workload, from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "k1_traffic.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if d.get("rows") == ROWS_PER_GPU and d.get("genomes") == S:
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    return None
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -383,6 +393,35 @@ def main() -> int:
                           "feht_result_fetch_device, NCCL gather to rank 0, feht_merge_sorted_device (K5), one D2H"),
                "timer": "host perf_counter between barrier+synchronize (covers H2D, kernels, D2H)"}
         del chars
+        # second figure: the host already holds the PACKED planes (what the C++ loader of feht_b200/host
+        # produces from the TSV, and the only form configs 2-5 fit in host memory in): feht_add_rows_packed
+        if world == 1:
+            Wd = ctx.row_stride_words
+            pv = torch.empty((R, Wd), dtype=torch.int64, pin_memory=True)
+            pd = torch.empty((R, Wd), dtype=torch.int64, pin_memory=True)
+            for r0 in range(0, R, 200_000):
+                n = min(200_000, R - r0)
+                pv[r0:r0 + n].copy_(torch.from_numpy(ctx.read_plane(0, r0, n).view(np.int64)))
+                pd[r0:r0 + n].copy_(torch.from_numpy(ctx.read_plane(1, r0, n).view(np.int64)))
+            ptimes = []
+            for i in range(1 + args.e2e_steps):
+                barrier()
+                t0 = time.perf_counter()
+                ctx.clear_rows()
+                ctx.clear_comparisons()
+                ctx.add_rows_packed_raw(pv.data_ptr(), pd.data_ptr(), R, Wd)
+                ctx.add_comparison(G1, G2)
+                ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, total_rows)
+                ctx.fetch_raw(0, ptrs)
+                barrier()
+                if i > 0:
+                    ptimes.append(time.perf_counter() - t0)
+            e2e["packed_host_input"] = {
+                "value": total_rows / (sum(ptimes) / len(ptimes)), "unit": UNIT,
+                "ms_per_step": 1e3 * sum(ptimes) / len(ptimes), "h2d_bytes_per_step": 2 * R * Wd * 8,
+                "d2h_bytes_per_step": d2h,
+                "path": "feht_add_rows_packed(pinned host bit-planes, 2 bits/call) -> feht_run -> feht_result_fetch"}
+            del pv, pd
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N=1)
     cpu = None
@@ -411,7 +450,11 @@ def main() -> int:
                        "parallelism": f"rows sharded over {world} GPU(s), no data-path collective",
                        "stage_ms_per_step": {k: stage[k] / args.steps for k in ("count_ms", "test_ms", "order_ms")}},
             "roofline": {"bound": "hbm", "kernel": "count_popc_kernel (K1)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": _k1_traffic() if R == ROWS_PER_GPU else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                           "(profiles/k1_traffic.json, profiles/README.md r1b)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": count_bytes, "avg_launch_ms": count_ms},
             "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(stage["launches"]),
