@@ -292,6 +292,12 @@ def main() -> int:
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_samples(S)
+    # host cores that transcode part of a chars upload (e2e only): this rank's share of the box
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, local_world) - 1)   # one core drives the DMA path
+    if os.environ.get("FEHT_BENCH_HOST_THREADS"):
+        host_threads = int(os.environ["FEHT_BENCH_HOST_THREADS"])
+    ctx.set_host_threads(host_threads)
     ctx.set_row_base(rank * R)
     ctx.reserve_rows(R)
     ctx.generate_synthetic(_spec(capi.SynthSpec), False, rank * R, R)
@@ -367,6 +373,7 @@ def main() -> int:
             ctx.add_rows_chars_raw(chars.data_ptr(), offsets.data_ptr(), R)
             ctx.add_comparison(G1, G2)
             t1 = time.perf_counter()
+            ctx.last_upload_host_rows_chars = ctx.last_upload_host_rows
             ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, total_rows)
             t2 = time.perf_counter()
             if world == 1:
@@ -384,11 +391,18 @@ def main() -> int:
         e2e_s = torch.tensor([sum(times) / len(times)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        host_rows = ctx.last_upload_host_rows_chars
+        # bytes that crossed the link: raw chars for the DMA + K0 share, two packed planes for the host share
+        h2d = (R - host_rows) * S + host_rows * ctx.row_stride_words * 16 + (R + 1) * 8 + (len(G1) + len(G2)) * 4
         e2e = {"value": total_rows / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "host_input_bytes_per_step": R * S,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(e2e_s.item()),
                "rank0_breakdown_ms": parts,
-               "h2d_gbs_per_gpu": h2d / (parts["upload_pack_ms"] * 1e-3) / 1e9,
-               "path": "feht_add_rows_chars(pinned host chars, 1 B/call) -> feht_run -> "
+               "host_transcoder": {"threads": host_threads, "rows_packed_on_host": ctx.last_upload_host_rows_chars,
+                                   "note": "feht_add_rows_chars splits the upload: DMA + GPU pack kernel for one end "
+                                           "of the row range, AVX2 host threads packing to 2 bits/call for the other"},
+               "input_gbs_per_gpu": R * S / (parts["upload_pack_ms"] * 1e-3) / 1e9,
+               "path": "feht_add_rows_chars(pinned host chars, 1 B/call; DMA+K0 and host transcoder threads) -> feht_run -> "
                        + ("feht_result_fetch" if world == 1 else
                           "feht_result_fetch_device, NCCL gather to rank 0, feht_merge_sorted_device (K5), one D2H"),
                "timer": "host perf_counter between barrier+synchronize (covers H2D, kernels, D2H)"}

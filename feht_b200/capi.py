@@ -30,6 +30,7 @@ EXPORTS = [
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
+    "feht_set_host_threads", "feht_last_upload_host_rows",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -103,6 +104,9 @@ def lib() -> C.CDLL:
     L.feht_comparison_info.argtypes = [vp, i64, P(i32), P(i32), P(i32), P(i32)]
     L.feht_set_count_engine.argtypes = [vp, C.c_int]
     L.feht_run.argtypes = [vp, C.c_int, f64, C.c_int, i64]
+    L.feht_set_host_threads.argtypes = [vp, C.c_int]
+    L.feht_last_upload_host_rows.argtypes = [vp]
+    L.feht_last_upload_host_rows.restype = i64
     L.feht_run_async.argtypes = [vp, C.c_int, f64, C.c_int, i64]
     L.feht_timings_accumulated.argtypes = [vp, P(f64), C.c_int, C.c_int]
     L.feht_result_count.argtypes = [vp, i64]
@@ -240,6 +244,14 @@ class Context:
     # ---- data
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._L.feht_set_stream(self._h, cuda_stream_ptr))
+
+    def set_host_threads(self, n: int):
+        """Host threads that transcode part of a chars upload (0 = DMA + GPU pack only, < 0 = default)."""
+        self._check(self._L.feht_set_host_threads(self._h, n))
+
+    @property
+    def last_upload_host_rows(self) -> int:
+        return int(self._L.feht_last_upload_host_rows(self._h))
 
     def set_samples(self, n: int):
         self._check(self._L.feht_set_samples(self._h, n))

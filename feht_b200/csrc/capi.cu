@@ -11,8 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <limits>
+#include <mutex>
 #include <queue>
+#include <thread>
 
 #include "common.cuh"
 
@@ -54,7 +57,15 @@ struct feht_ctx {
     struct PendingRun { bool active = false; double launches = 0, count_launches = 0, count_bytes = 0; } pend[2];
     int ev_slot = 0;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // runs, count/test/order/total ms, launches, count launches
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[4] = {nullptr, nullptr, nullptr, nullptr}, ev_used[4] = {nullptr, nullptr, nullptr, nullptr};
+    // host transcoder (host_pack.cpp): worker threads pack pieces of a chars upload while the DMA engine moves
+    // the others raw; each worker owns two pinned output buffers (events order their reuse)
+    int host_threads = -1;                 // -1: FEHT_HOST_PACK_THREADS or all cores; 0: off
+    cudaStream_t pack_stream = nullptr;    // H2D of the host-packed pieces
+    uint64_t *pack_pinned = nullptr;       // [workers][2][kHostPackBufWords]
+    int pack_workers_alloc = 0;
+    std::vector<cudaEvent_t> pack_ev;      // [workers][2]
+    int64_t last_upload_host_rows = 0;     // rows of the last chars upload the host cores packed
     std::string err;
 
     int64_t S = 0, W = 0;
@@ -205,6 +216,13 @@ int check_mode(feht_ctx *c, int snp) {
 }
 
 constexpr size_t kStageBytes = size_t(96) << 20;
+// chars upload (add_chars_common): piece = at most 8 MB of chars; the DMA path moves up to 3 pieces per
+// staging slot (4 slots in one 96 MB buffer); a host worker packs one piece into a 4 MB pinned buffer
+constexpr size_t kPieceBytes = size_t(8) << 20;
+constexpr int kDmaPiecesMax = 3, kDmaSlots = 4;
+constexpr int kPackBufsMax = 2;
+constexpr size_t kHostPackBufWords = size_t(4) << 17;   // 4 MB of 64-bit words
+constexpr size_t kHostPackMinBytes = size_t(64) << 20;  // smaller uploads are not worth waking the cores for
 // AUTO engine: categories go to the GEMM from this many pair-slots on (measured crossover)
 constexpr int kGemmAutoMinSlots = 8;
 
@@ -252,7 +270,14 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
     const int mult = snp ? 4 : 1;
     if (int rc = append_rank(c, name_rank, n * mult, c->n_units * mult)) return rc;
 
-    // pieces = runs of whole rows whose chars + offsets fit a staging buffer
+    // Pieces = runs of whole rows with at most kPieceBytes of chars + offsets and kHostPackBufWords of packed
+    // output.  Two producers fill the SAME bit-planes from opposite ends of the piece list:
+    //  * the DMA path (this thread): up to kDmaPieces consecutive pieces are copied raw on the copy stream into
+    //    one of four staging slots and packed by K0 on the context stream (events order slot reuse);
+    //  * the host transcoder (worker threads, host_pack.cpp): a worker packs a piece with AVX2 into one of its
+    //    two pinned buffers and uploads the planes at 2 bits per call.
+    // The PCIe link carries 1 B/call for the first kind and 0.25 B/call for the second, so the upload runs at
+    // 53 GB/s + 3/4 of whatever the cores pack instead of 53 GB/s (measured 110 GB/s on 16 cores alone).
     std::vector<int64_t> piece_first;
     {
         int64_t r = 0;
@@ -262,53 +287,143 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
             int64_t q = r;
             while (q < n) {
                 const size_t add = size_t(row_offsets[q + 1] - row_offsets[q]) + 8;
-                if (add + 64 > kStageBytes)
+                if (add + 64 > kPieceBytes)
                     return fail(c, FEHT_E_INVALID, "a single row exceeds the staging buffer");
-                if (bytes + add + 64 > kStageBytes) break;
+                if (bytes + add + 64 > kPieceBytes) break;
+                if (size_t(q + 1 - r) * size_t(c->W) * size_t(n_planes) > kHostPackBufWords) break;
                 bytes += add;
                 ++q;
             }
+            if (q == r) return fail(c, FEHT_E_INVALID, "a single row exceeds the packing buffer");
             r = q;
         }
         piece_first.push_back(n);
     }
-    // Layout of a staged piece: [offsets (rows+1) x int64, rebased to 0][chars...].  The copies run on
-    // the copy stream into one of two staging buffers while the pack kernel of the previous piece
-    // runs on the context stream (events order buffer reuse), so the PCIe link never waits for K0.
-    const size_t n_pieces = piece_first.size() - 1;
-    std::vector<std::vector<int64_t>> rebased(n_pieces);   // alive until the final synchronize
+    const int64_t n_pieces = int64_t(piece_first.size()) - 1;
     const int64_t first_unit = c->n_units;
-    for (int b = 0; b < 2; ++b) CU(c, ensure(c->stage[b], kStageBytes));
-    for (size_t i = 0; i < n_pieces; ++i) {
-        const int b = int(i & 1);
-        unsigned char *dev = c->stage[b].p;
-        const int64_t r0 = piece_first[i], r1 = piece_first[i + 1];
+    const int64_t total_chars = row_offsets[n] - row_offsets[0];
+
+    // ---- host transcoder workers
+    int workers = 0;
+    if (host_pack_available() && total_chars >= int64_t(kHostPackMinBytes) && n_pieces >= 8) {
+        workers = c->host_threads;
+        if (workers < 0) {
+            const char *e = getenv("FEHT_HOST_PACK_THREADS");
+            workers = e ? atoi(e) : int(std::thread::hardware_concurrency());
+        }
+        workers = std::max(0, std::min(workers, 64));
+        if (int64_t(workers) > n_pieces / 2) workers = int(n_pieces / 2);
+    }
+    if (workers > c->pack_workers_alloc) {
+        if (c->pack_pinned) { cudaFreeHost(c->pack_pinned); c->pack_pinned = nullptr; }
+        CU(c, cudaHostAlloc(reinterpret_cast<void **>(&c->pack_pinned), size_t(workers) * kPackBufsMax * kHostPackBufWords * 8,
+                            cudaHostAllocDefault));
+        while (int(c->pack_ev.size()) < kPackBufsMax * workers) {
+            cudaEvent_t ev = nullptr;
+            CU(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->pack_ev.push_back(ev);
+        }
+        c->pack_workers_alloc = workers;
+    }
+    constexpr int kDmaPieces = kDmaPiecesMax, kPackBufs = kPackBufsMax;   // (1..3 pieces, 2..4 buffers: no measurable difference)
+    std::mutex mu;
+    int64_t lo = 0, hi = n_pieces - 1;
+    auto claim_back = [&]() -> int64_t {
+        std::lock_guard<std::mutex> g(mu);
+        return lo <= hi ? hi-- : -1;
+    };
+    auto claim_front = [&](int64_t *count) -> int64_t {   // up to kDmaPieces consecutive pieces
+        std::lock_guard<std::mutex> g(mu);
+        if (lo > hi) return -1;
+        const int64_t first = lo;
+        *count = std::min<int64_t>(kDmaPieces, hi - lo + 1);
+        lo += *count;
+        return first;
+    };
+    std::atomic<int> worker_err{0};
+    std::atomic<int64_t> host_rows{0};
+    std::vector<std::thread> pool;
+    pool.reserve(size_t(workers));
+    for (int t = 0; t < workers; ++t) {
+        pool.emplace_back([&, t] {
+            if (cudaSetDevice(c->device) != cudaSuccess) { worker_err = 1; return; }
+            bool used[kPackBufsMax] = {false, false};
+            int k = 0;
+            for (;;) {
+                const int64_t i = claim_back();
+                if (i < 0) break;
+                uint64_t *buf = c->pack_pinned + (size_t(t) * kPackBufsMax + size_t(k)) * kHostPackBufWords;
+                cudaEvent_t ev = c->pack_ev[size_t(t) * kPackBufsMax + size_t(k)];
+                if (used[k] && cudaEventSynchronize(ev) != cudaSuccess) { worker_err = 1; return; }
+                const int64_t r0 = piece_first[size_t(i)], r1 = piece_first[size_t(i) + 1];
+                const size_t words = size_t(r1 - r0) * size_t(c->W);
+                const int64_t u0 = first_unit + r0;
+                if (snp)
+                    host_pack_snp(chars, row_offsets, r0, r1, c->S, c->W, buf, buf + words, buf + 2 * words);
+                else
+                    host_pack_binary(chars, row_offsets, r0, r1, c->S, c->W, buf, buf + words);
+                cudaError_t e = cudaSuccess;
+                for (int pl = 0; pl < n_planes && e == cudaSuccess; ++pl)
+                    e = cudaMemcpyAsync(c->plane[pl] + u0 * c->W, buf + size_t(pl) * words, words * 8,
+                                        cudaMemcpyHostToDevice, c->pack_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ev, c->pack_stream);
+                if (e != cudaSuccess) { worker_err = 1; return; }
+                used[k] = true;
+                k = (k + 1) % kPackBufs;
+                host_rows += r1 - r0;
+            }
+        });
+    }
+
+    // ---- DMA path.  Layout of a staged slot: [offsets (rows+1) x int64, rebased to 0][chars...].
+    auto join_all = [&] { for (std::thread &th : pool) th.join(); };
+    std::vector<std::vector<int64_t>> rebased;   // alive until the final synchronize
+    rebased.reserve(size_t(n_pieces / kDmaPieces + 2));
+    cudaError_t derr = ensure(c->stage[0], kStageBytes);
+    for (int64_t k = 0; derr == cudaSuccess; ++k) {
+        const int b = int(k % kDmaSlots);
+        // host-side wait (not a stream wait): the DMA path claims work only when it can start on it, so the
+        // workers get whatever it cannot take
+        if (k >= kDmaSlots && (derr = cudaEventSynchronize(c->ev_used[b])) != cudaSuccess) break;
+        int64_t cnt = 0;
+        const int64_t i = claim_front(&cnt);
+        if (i < 0) break;
+        unsigned char *dev = c->stage[0].p + size_t(b) * (kStageBytes / kDmaSlots);
+        const int64_t r0 = piece_first[size_t(i)], r1 = piece_first[size_t(i + cnt)];
         const int64_t rows = r1 - r0;
-        std::vector<int64_t> &off = rebased[i];
-        off.resize(size_t(rows) + 1);
+        rebased.emplace_back(size_t(rows) + 1);
+        std::vector<int64_t> &off = rebased.back();
         for (int64_t r = 0; r <= rows; ++r) off[size_t(r)] = row_offsets[r0 + r] - row_offsets[r0];
         const size_t off_bytes = (size_t(rows) + 1) * 8;
         const size_t off_pad = (off_bytes + 63) & ~size_t(63);
         const size_t char_bytes = size_t(row_offsets[r1] - row_offsets[r0]);
-        if (i >= 2) CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_used[b], 0));
-        CU(c, cudaMemcpyAsync(dev, off.data(), off_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-        if (char_bytes)
-            CU(c, cudaMemcpyAsync(dev + off_pad, chars + row_offsets[r0], char_bytes, cudaMemcpyHostToDevice,
-                                  c->copy_stream));
-        CU(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
-        CU(c, cudaStreamWaitEvent(c->st, c->ev_copied[b], 0));
+        if ((derr = cudaMemcpyAsync(dev, off.data(), off_bytes, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) break;
+        if (char_bytes && (derr = cudaMemcpyAsync(dev + off_pad, chars + row_offsets[r0], char_bytes,
+                                                  cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) break;
+        if ((derr = cudaEventRecord(c->ev_copied[b], c->copy_stream)) != cudaSuccess) break;
+        if ((derr = cudaStreamWaitEvent(c->st, c->ev_copied[b], 0)) != cudaSuccess) break;
         const int64_t u0 = first_unit + r0;
         if (snp)
-            CU(c, launch_pack_snp_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows,
-                                        c->S, c->W, c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W,
-                                        c->plane[2] + u0 * c->W, c->st));
+            derr = launch_pack_snp_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S, c->W,
+                                         c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->plane[2] + u0 * c->W, c->st);
         else
-            CU(c, launch_pack_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S,
-                                    c->W, c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->st));
-        CU(c, cudaEventRecord(c->ev_used[b], c->st));
+            derr = launch_pack_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S, c->W,
+                                     c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->st);
+        if (derr != cudaSuccess) break;
+        derr = cudaEventRecord(c->ev_used[b], c->st);
     }
+    if (derr != cudaSuccess) {   // let the workers drain the list before reporting
+        { std::lock_guard<std::mutex> g(mu); lo = hi + 1; }
+        join_all();
+        return fail(c, FEHT_E_CUDA, "chars upload: %s", cudaGetErrorString(derr));
+    }
+    join_all();
+    if (worker_err.load()) return fail(c, FEHT_E_CUDA, "chars upload: a host packing worker failed: %s",
+                                       cudaGetErrorString(cudaGetLastError()));
+    CU(c, cudaStreamSynchronize(c->pack_stream));
     CU(c, cudaStreamSynchronize(c->copy_stream));
     CU(c, cudaStreamSynchronize(c->st));
+    c->last_upload_host_rows = host_rows.load();
     c->n_units += n;
     c->has_results = false;
     c->rank_is_perm = -1;
@@ -397,7 +512,8 @@ extern "C" int feht_create(feht_ctx **out, int device) {
     for (int i = 0; i < 4; ++i)
         for (int k = 0; k < 2; ++k)
             if ((e = cudaEventCreate(&c->evr[k][i])) != cudaSuccess) return bail("event", e);
-    for (int i = 0; i < 2; ++i) {
+    if ((e = cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    for (int i = 0; i < 4; ++i) {
         if ((e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
         if ((e = cudaEventCreateWithFlags(&c->ev_used[i], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     }
@@ -425,16 +541,27 @@ extern "C" void feht_destroy(feht_ctx *c) {
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
         for (int i = 0; i < 4; ++i) if (c->evr[k][i]) cudaEventDestroy(c->evr[k][i]);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_used[i]) cudaEventDestroy(c->ev_used[i]);
     }
+    for (cudaEvent_t ev : c->pack_ev) cudaEventDestroy(ev);
+    if (c->pack_pinned) cudaFreeHost(c->pack_pinned);
+    if (c->pack_stream) cudaStreamDestroy(c->pack_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
 extern "C" const char *feht_last_error(const feht_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int feht_set_host_threads(feht_ctx *c, int n_threads) {
+    if (!c) return FEHT_E_INVALID;
+    c->host_threads = n_threads < 0 ? -1 : n_threads;
+    return FEHT_OK;
+}
+
+extern "C" int64_t feht_last_upload_host_rows(const feht_ctx *c) { return c ? c->last_upload_host_rows : FEHT_E_INVALID; }
 
 extern "C" int feht_set_stream(feht_ctx *c, void *cuda_stream) {
     if (!c) return FEHT_E_INVALID;

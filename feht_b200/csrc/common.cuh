@@ -75,6 +75,14 @@ cudaError_t launch_repack_rows(const uint64_t *d_src, int64_t src_stride, uint64
                                int64_t W, int64_t S, int64_t n_rows, const uint64_t *d_and_with,
                                cudaStream_t st);
 
+// host_pack.cpp: the same planes produced on the host cores (AVX2), rows [r0, r1) of the caller's buffer into
+// [r1-r0][W] words per plane
+bool host_pack_available();
+void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                      uint64_t *value, uint64_t *valid);
+void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                   uint64_t *hi, uint64_t *valid, uint64_t *lo);
+
 // count_popc.cu  (K1)
 struct PopcPlan {
     int logL;      // lanes per row = 1 << logL

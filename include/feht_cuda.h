@@ -82,6 +82,16 @@ int feht_clear_rows(feht_ctx *ctx);
  */
 int feht_add_rows_chars(feht_ctx *ctx, const uint8_t *chars, const int64_t *row_offsets,
                         int64_t n_rows, const int32_t *name_rank);
+/*
+ * Uploads of 64 MB and more are split between two producers of the same bit-planes: the DMA engine moves
+ * pieces raw (1 B/call) for the GPU pack kernel, and n_threads host threads transcode pieces from the other end
+ * of the row range (AVX2) and upload them packed (2 bits/call), because the PCIe link, not the GPU, bounds this
+ * call.  n_threads: 0 = DMA only, < 0 = default (env FEHT_HOST_PACK_THREADS, else every core).  Only the wire
+ * format is produced on the host; there is no CPU path for counting / testing / ordering.
+ */
+int feht_set_host_threads(feht_ctx *ctx, int n_threads);
+/* rows of the last chars upload that the host threads transcoded (diagnostics / tests) */
+int64_t feht_last_upload_host_rows(const feht_ctx *ctx);
 
 /*
  * Append rows already packed: bit s of word (s/64) of a row = sample s; value bit set iff the

@@ -770,3 +770,28 @@ def test_sort_engines_agree(cuda_lib):
         assert r.returncode == 0, r.stderr[-2000:]
         digests[eng] = r.stdout.strip().split()[-1]
     assert digests["coop"] == digests["onesweep"]
+
+
+def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
+    """A chars upload of 64 MB and more is split between the DMA + K0 path and host threads that pack pieces
+    with AVX2 (host_pack.cpp).  Both must produce the same bit-planes: ragged rows, rows longer than S, stray
+    characters, binary and SNP."""
+    rng = np.random.default_rng(99)
+    S, R = 2100, 36000
+    lens = rng.integers(S - 70, S + 40, size=R)
+    lens[:100] = rng.integers(0, 64, size=100)                      # very short rows too
+    alphabet = np.frombuffer(b"01-1 0NX", dtype=np.uint8)
+    rows = [alphabet[rng.integers(0, len(alphabet), size=int(n))] for n in lens]
+    snp_alphabet = np.frombuffer(b"ACGTacgt-N01x", dtype=np.uint8)
+    snp_rows = [snp_alphabet[rng.integers(0, len(snp_alphabet), size=int(n))] for n in lens]
+    for snp, data in ((False, rows), (True, snp_rows)):
+        planes = {}
+        for threads in (0, 5):
+            with capi.Context(0) as c:
+                c.set_samples(S)
+                c.set_host_threads(threads)
+                (c.add_snp_chars if snp else c.add_rows_chars)(data)
+                assert (c.last_upload_host_rows > 0) == (threads > 0), (snp, threads, c.last_upload_host_rows)
+                planes[threads] = [c.read_plane(p, 0, R) for p in range(3 if snp else 2)]
+        for a, b in zip(planes[0], planes[5]):
+            assert (a == b).all(), snp
