@@ -97,7 +97,7 @@ struct feht_ctx {
     DevBuf<GroupComp> gcomps;
     DevBuf<SlotDef> sdefs;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
-    DevBuf<long long> seg_base;
+    int64_t survivor_hint = 0;             // survivors of the last filtered run (sizes the next run's arrays)
     DevBuf<int32_t> r_comp, r_row, r_rank, o_rank, o_goa, o_gob, o_gta, o_gtb;
     DevBuf<int64_t> o_row;
     DevBuf<int4> r_cnt;
@@ -532,7 +532,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     for (int i = 0; i < 3; ++i) if (c->plane[i]) cudaFree(c->plane[i]);
     release(c->rank); release(c->stage[0]); release(c->stage[1]);
     release(c->gemm_b); release(c->gemm_passes);
-    release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->sdefs); release(c->seg_count); release(c->seg_base);
+    release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->sdefs); release(c->seg_count);
     release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
     release(c->o_goa); release(c->o_gob); release(c->o_gta); release(c->o_gtb);
     release(c->r_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
@@ -959,7 +959,6 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     CU(c, ensure(c->sdefs, sdefs.size()));
     CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
     CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
-    CU(c, ensure(c->seg_base, size_t(n_comps)));
     CU(c, cudaMemcpyAsync(c->masks.p, hmask.data(), hmask.size() * 8, cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->groups.p, groups.data(), groups.size() * sizeof(ScreenGroup), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->fracs.p, fracs.data(), fracs.size() * sizeof(FracDef), cudaMemcpyHostToDevice, c->st));
@@ -1071,33 +1070,53 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         tp.dense_by_rank = c->rank_is_perm;
     }
     const bool rank_presorted = tp.dense && (c->have_rank != 1 || tp.dense_by_rank);
-    std::vector<long long> base(static_cast<size_t>(n_comps), 0);
+    auto ensure_survivors = [&](size_t nn) -> cudaError_t {
+        cudaError_t e;
+        if ((e = ensure(c->r_comp, nn)) != cudaSuccess || (e = ensure(c->r_row, nn)) != cudaSuccess ||
+            (e = ensure(c->r_rank, nn)) != cudaSuccess || (e = ensure(c->r_cnt, nn)) != cudaSuccess ||
+            (e = ensure(c->r_p, nn)) != cudaSuccess || (e = ensure(c->r_ratio, nn)) != cudaSuccess)
+            return e;
+        tp.r_comp = c->r_comp.p; tp.r_row = c->r_row.p; tp.r_rank = c->r_rank.p;
+        tp.r_cnt = c->r_cnt.p; tp.r_ratio = c->r_ratio.p;
+        return cudaSuccess;
+    };
     if (tp.dense) {
         for (int i = 0; i <= n_comps; ++i) c->seg_off[size_t(i)] = int64_t(i) * R;
+        if (c->seg_off[size_t(n_comps)] >= (int64_t(1) << 30))
+            return fail(c, FEHT_E_INVALID, "2^30 or more surviving rows in one run");
+        CU(c, ensure_survivors(size_t(c->seg_off[size_t(n_comps)])));
     } else {
-        tp.seg_count = c->seg_count.p;
-        CU(c, launch_test_count(tp, c->st));
-        ++launches;
-        std::vector<unsigned long long> cnt(static_cast<size_t>(n_comps));
-        CU(c, cudaMemcpyAsync(cnt.data(), c->seg_count.p, size_t(n_comps) * 8, cudaMemcpyDeviceToHost, c->st));
-        CU(c, cudaStreamSynchronize(c->st));
+        // K3a, filtered: one screen pass writes the survivors through a global cursor into arrays sized from the
+        // last run (first run: 1/1024 of the tests, at least 1M slots); only if they did not fit is the pass
+        // repeated with the exact size.  The host needs the counts anyway (result offsets, grid sizes).
+        const double n_tests = double(R) * double(n_comps);
+        int64_t cap = std::max<int64_t>(int64_t(1) << 20, std::min<int64_t>(int64_t(n_tests / 1024.0), int64_t(1) << 24));
+        cap = std::max(cap, c->survivor_hint + c->survivor_hint / 4);
+        std::vector<unsigned long long> cnt(static_cast<size_t>(n_comps) + 1);
+        for (int attempt = 0;; ++attempt) {
+            CU(c, ensure_survivors(size_t(cap)));
+            tp.seg_count = c->seg_count.p;
+            tp.cursor = c->seg_count.p + n_comps;
+            tp.capacity = cap;
+            CU(c, launch_test_emit(tp, c->st));
+            ++launches;
+            CU(c, cudaMemcpyAsync(cnt.data(), c->seg_count.p, (size_t(n_comps) + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+            CU(c, cudaStreamSynchronize(c->st));
+            const unsigned long long total = cnt[size_t(n_comps)];
+            if (total >= (1ull << 30)) return fail(c, FEHT_E_INVALID, "2^30 or more surviving rows in one run");
+            if (int64_t(total) <= cap || attempt == 1) break;
+            cap = int64_t(total);
+            CU(c, cudaMemsetAsync(c->seg_count.p, 0, (size_t(n_comps) + 1) * 8, c->st));
+        }
         for (int i = 0; i < n_comps; ++i) c->seg_off[size_t(i) + 1] = c->seg_off[size_t(i)] + int64_t(cnt[size_t(i)]);
-        for (int i = 0; i < n_comps; ++i) base[size_t(i)] = c->seg_off[size_t(i)];
-        CU(c, cudaMemcpyAsync(c->seg_base.p, base.data(), size_t(n_comps) * 8, cudaMemcpyHostToDevice, c->st));
+        c->survivor_hint = c->seg_off[size_t(n_comps)];
     }
     const int64_t n = c->seg_off[size_t(n_comps)];
-    if (n >= (int64_t(1) << 30)) return fail(c, FEHT_E_INVALID, "2^30 or more surviving rows in one run");
     c->n_surv = n;
     const size_t nn = size_t(n);
-    CU(c, ensure(c->r_comp, nn)); CU(c, ensure(c->r_row, nn)); CU(c, ensure(c->r_rank, nn));
-    CU(c, ensure(c->r_cnt, nn)); CU(c, ensure(c->r_p, nn)); CU(c, ensure(c->r_ratio, nn));
     CU(c, ensure(c->o_row, nn)); CU(c, ensure(c->o_rank, nn));
     CU(c, ensure(c->o_goa, nn)); CU(c, ensure(c->o_gob, nn)); CU(c, ensure(c->o_gta, nn)); CU(c, ensure(c->o_gtb, nn));
     CU(c, ensure(c->o_p, nn)); CU(c, ensure(c->o_ratio, nn));
-    tp.r_comp = c->r_comp.p; tp.r_row = c->r_row.p; tp.r_rank = c->r_rank.p;
-    tp.r_cnt = c->r_cnt.p; tp.r_ratio = c->r_ratio.p;
-    tp.seg_count = c->seg_count.p + n_comps;  // cursors (zeroed above)
-    tp.seg_base = c->seg_base.p;
     bool use_coop = false;
     if (n > 0) {
         CU(c, ensure(c->sw_key_a, nn)); CU(c, ensure(c->sw_key_b, nn));
@@ -1117,8 +1136,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
         c->sw.control = c->sw_control.p;
         c->sw.or_and = c->sw_oa.p;
-        CU(c, launch_test_emit(tp, c->st));
-        ++launches;
+        if (tp.dense) {
+            CU(c, launch_test_emit(tp, c->st));
+            ++launches;
+        }
         // K3b: p-values of the survivors (+ Bonferroni) and the sort keys
         CU(c, launch_pvalues(c->r_cnt.p, c->r_ratio.p, n, c->d_choose, correction, double(bonferroni_n),
                              c->r_p.p, sort_key, c->sw.key_a, c->sw.val_a, c->sw.or_and, c->r_rank.p,

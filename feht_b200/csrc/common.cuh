@@ -129,15 +129,15 @@ struct TestParams {
     int32_t *r_comp, *r_row, *r_rank;
     int4 *r_cnt;
     double *r_ratio;
-    unsigned long long *seg_count;   // [n_comps] (count mode) / cursors (emit mode)
-    const long long *seg_base;       // [n_comps] exclusive offsets (emit mode, filtered)
+    unsigned long long *seg_count;   // filtered output: [n_comps] survivors per comparison (zeroed by the caller)
+    unsigned long long *cursor;      // filtered output: next free survivor slot (zeroed by the caller)
+    long long capacity;              // filtered output: slots the survivor arrays hold
     int dense;                       // 1: every test survives, index = comp*n_rows + row
     int dense_by_rank;               // dense and name_rank is a permutation: index = comp*n_rows + rank
 };
 // counts how many distinct in-range values rank[0..n) holds (== n iff it is a permutation of [0,n))
 cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t *flags_words,
                                         unsigned long long *out_count, cudaStream_t st);
-cudaError_t launch_test_count(const TestParams &p, cudaStream_t st);
 cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
 // K3b over n compacted survivors: p (+ Bonferroni) and, when d_key != null, the sort keys + OR/AND words
 cudaError_t launch_pvalues(const int4 *d_tables, const double *d_ratio, int64_t n, const double *d_choose,

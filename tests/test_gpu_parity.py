@@ -795,3 +795,36 @@ def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
                 planes[threads] = [c.read_plane(p, 0, R) for p in range(3 if snp else 2)]
         for a, b in zip(planes[0], planes[5]):
             assert (a == b).all(), snp
+
+
+def test_filtered_output_single_pass_and_capacity_overflow(ctx):
+    """Filtered runs write the survivors in ONE screen pass through a global cursor into arrays sized from a
+    guess (1M slots the first time); more survivors than slots makes the library repeat the pass with the exact
+    size.  2.1M tests with a ratio filter that nearly all pass (overflow on the first run), then a stricter
+    filter in the same context (arrays now larger than needed); both against the oracle."""
+    rng = np.random.default_rng(4242)
+    S, R = 70, 100000
+    cells = _random_chars(rng, R, S, p_missing=0.02)
+    vos = rng.integers(0, 6, size=S).astype(np.int32)
+    groups = [np.flatnonzero(vos == v) for v in range(6)]
+    comps = [(groups[a], groups[b]) for a, b in itertools.combinations(range(6), 2)]
+    comps += [(groups[v], np.flatnonzero(vos != v)) for v in range(6)]
+    ctx.set_samples(S)
+    ctx.add_rows_chars(cells)
+    ctx.add_category(vos, 6)
+    assert ctx.num_comparisons == len(comps) == 21
+    for rf in (1e-9, 0.4):
+        ctx.run(capi.CORRECTION_BONFERRONI, rf)
+        total = ctx.result_total()
+        assert (total > (1 << 20)) == (rf < 0.1), (rf, total)
+        for ci in (0, 7, 14, 15, 20):
+            g1, g2 = comps[ci]
+            want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=R, n_threads=8)
+            order = oracle.filter_and_order(want["ratio"], None, rf)
+            got = ctx.fetch(ci)
+            assert len(got["row"]) == len(order) == ctx.result_count(ci), (rf, ci)
+            assert (got["row"] == order).all(), (rf, ci)
+            assert (got["ratio"] == want["ratio"][order]).all()
+            for k in ("goa", "gob", "gta", "gtb"):
+                assert (got[k] == want[k][order]).all(), (rf, ci, k)
+            assert p_close(got["p"], want["p"][order], np.zeros(len(order), bool)).all()
