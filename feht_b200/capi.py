@@ -17,6 +17,7 @@ OK = 0
 CORRECTION_NONE, CORRECTION_BONFERRONI = 0, 1
 SORT_ABS_RATIO_DESC, SORT_PVALUE_ASC = 0, 1
 ENGINE_AUTO, ENGINE_POPC, ENGINE_GEMM = 0, 1, 2
+FET_TWO_TAIL, FET_ONE_TAIL = 0, 1
 E_INVALID, E_CUDA, E_BOUNDS, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5
 
 # every symbol include/feht_cuda.h declares (tests check the library exports all of them)
@@ -30,7 +31,7 @@ EXPORTS = [
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
-    "feht_set_host_threads", "feht_last_upload_host_rows",
+    "feht_set_host_threads", "feht_last_upload_host_rows", "feht_set_fet_mode",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -105,6 +106,7 @@ def lib() -> C.CDLL:
     L.feht_set_count_engine.argtypes = [vp, C.c_int]
     L.feht_run.argtypes = [vp, C.c_int, f64, C.c_int, i64]
     L.feht_set_host_threads.argtypes = [vp, C.c_int]
+    L.feht_set_fet_mode.argtypes = [vp, C.c_int]
     L.feht_last_upload_host_rows.argtypes = [vp]
     L.feht_last_upload_host_rows.restype = i64
     L.feht_run_async.argtypes = [vp, C.c_int, f64, C.c_int, i64]
@@ -244,6 +246,10 @@ class Context:
     # ---- data
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._L.feht_set_stream(self._h, cuda_stream_ptr))
+
+    def set_fet_mode(self, mode: int):
+        """FET_TWO_TAIL (default) or FET_ONE_TAIL (FET.hs:82,101-107)."""
+        self._check(self._L.feht_set_fet_mode(self._h, mode))
 
     def set_host_threads(self, n: int):
         """Host threads that transcode part of a chars upload (0 = DMA + GPU pack only, < 0 = default)."""

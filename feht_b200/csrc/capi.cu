@@ -80,6 +80,7 @@ struct feht_ctx {
     std::vector<Comp> comps;
     std::vector<Cat> cats;
     int engine = FEHT_ENGINE_AUTO;
+    int fet_mode = FEHT_FET_TWO_TAIL;
 
     double *d_choose = nullptr;
     DevBuf<unsigned char> stage[2];
@@ -554,6 +555,14 @@ extern "C" void feht_destroy(feht_ctx *c) {
 }
 
 extern "C" const char *feht_last_error(const feht_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int feht_set_fet_mode(feht_ctx *c, int mode) {
+    if (!c) return FEHT_E_INVALID;
+    if (mode != FEHT_FET_TWO_TAIL && mode != FEHT_FET_ONE_TAIL) return fail(c, FEHT_E_INVALID, "unknown FET mode %d", mode);
+    c->fet_mode = mode;
+    c->has_results = false;
+    return FEHT_OK;
+}
 
 extern "C" int feht_set_host_threads(feht_ctx *c, int n_threads) {
     if (!c) return FEHT_E_INVALID;
@@ -1141,7 +1150,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
             ++launches;
         }
         // K3b: p-values of the survivors (+ Bonferroni) and the sort keys
-        CU(c, launch_pvalues(c->r_cnt.p, c->r_ratio.p, n, c->d_choose, correction, double(bonferroni_n),
+        CU(c, launch_pvalues(c->r_cnt.p, c->r_ratio.p, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode,
                              c->r_p.p, sort_key, c->sw.key_a, c->sw.val_a, c->sw.or_and, c->r_rank.p,
                              c->r_comp.p, c->st));
         ++launches;
@@ -1339,7 +1348,7 @@ extern "C" int feht_eval_tables(feht_ctx *c, const int32_t *goa, const int32_t *
     DevBuf<int4> dt; DevBuf<double> dp, dr;
     CU(c, ensure(dt, size_t(n))); CU(c, ensure(dp, size_t(n))); CU(c, ensure(dr, size_t(n)));
     CU(c, cudaMemcpyAsync(dt.p, h.data(), size_t(n) * 16, cudaMemcpyHostToDevice, c->st));
-    CU(c, launch_eval_tables(dt.p, n, c->d_choose, dp.p, dr.p, c->st));
+    CU(c, launch_eval_tables(dt.p, n, c->d_choose, c->fet_mode, dp.p, dr.p, c->st));
     if (p_out) CU(c, cudaMemcpyAsync(p_out, dp.p, size_t(n) * 8, cudaMemcpyDeviceToHost, c->st));
     if (ratio_out) CU(c, cudaMemcpyAsync(ratio_out, dr.p, size_t(n) * 8, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));

@@ -141,10 +141,10 @@ cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t
 cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
 // K3b over n compacted survivors: p (+ Bonferroni) and, when d_key != null, the sort keys + OR/AND words
 cudaError_t launch_pvalues(const int4 *d_tables, const double *d_ratio, int64_t n, const double *d_choose,
-                           int correction, double bonferroni_n, double *d_p, int sort_key,
+                           int correction, double bonferroni_n, int one_tail, double *d_p, int sort_key,
                            unsigned long long *d_key, uint32_t *d_val, uint32_t *d_or_and,
                            const int32_t *r_rank, const int32_t *r_comp, cudaStream_t st);
-cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose,
+cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose, int one_tail,
                                double *d_p, double *d_ratio, cudaStream_t st);
 
 // sort.cu  (K4)

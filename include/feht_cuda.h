@@ -48,6 +48,8 @@ enum { FEHT_CORRECTION_NONE = 0, FEHT_CORRECTION_BONFERRONI = 1 };
 /* Ordering of each comparison's rows.  The reference orders by abs(ratio) descending
  * (Comparison.hs:155,160-162); ties are broken by name_rank ascending. */
 enum { FEHT_SORT_ABS_RATIO_DESC = 0, FEHT_SORT_PVALUE_ASC = 1 };
+/* FETMode (FET.hs:82); the reference's hot path always asks for TwoTail (Comparison.hs:51) */
+enum { FEHT_FET_TWO_TAIL = 0, FEHT_FET_ONE_TAIL = 1 };
 
 /* ---------------------------------------------------------------- context ---- */
 /* Replaces: nothing (the reference is a pure function); owns the device state. */
@@ -182,6 +184,11 @@ int feht_run(feht_ctx *ctx, int correction, double ratio_filter, int sort_key,
  * shim calls the blocking feht_run. */
 int feht_run_async(feht_ctx *ctx, int correction, double ratio_filter, int sort_key,
                    int64_t bonferroni_n);
+
+/* FETMode of the p-values feht_run and feht_eval_tables compute (FET.hs:101-111): TwoTail (default, what
+ * Comparison.hs:51 asks for) or OneTail = chi-square p / 2 for table totals >= 1000, else
+ * `cumulative (hypergeometric m l k) goa`. */
+int feht_set_fet_mode(feht_ctx *ctx, int mode);
 
 /* Surviving rows of comparison c, in final order. */
 int64_t feht_result_count(const feht_ctx *ctx, int64_t comparison);

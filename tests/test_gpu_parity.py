@@ -144,6 +144,36 @@ def test_fetspec_known_answers_on_device(ctx, golden):
     assert p[0] == want[0] and p[1] == want[1]          # hypergeometric KATs: bit-exact
 
 
+def test_one_tail_mode_known_answers_and_random_tables(ctx, golden):
+    """FETMode OneTail (FET.hs:82,101,105-107): the four OneTail known answers of FETSpec.hs on the device, then
+    random tables on both branches against the oracle (hypergeometric cumulative: bit-exact)."""
+    ctx.set_fet_mode(capi.FET_ONE_TAIL)
+    one = [g for g in golden["fetspec"] if g[4] == "one"]
+    assert len(one) == 4
+    a, b, c, d = (np.array([g[i] for g in one], dtype=np.int32) for i in range(4))
+    p, _ = ctx.eval_tables(a, b, c, d)
+    want = np.array([g[5] for g in one])
+    assert p_close(p, want, (a + b + c + d) >= 1000).all(), (p, want)
+    assert p[0] == want[0] and p[1] == want[1]          # `cumulative d goa`: bit-exact
+    rng = np.random.default_rng(17)
+    tabs = [t for t in itertools.product(range(0, 6), repeat=4)]
+    for _ in range(1200):
+        l = int(rng.integers(20, 1000)) if rng.random() < 0.7 else int(rng.integers(1000, 30000))
+        k = int(rng.integers(1, l))
+        m = int(rng.integers(0, l + 1))
+        lo, hi = max(0, m + k - l), min(m, k)
+        goa = int(rng.integers(lo, hi + 1))
+        tabs.append((goa, k - goa, m - goa, l - k - m + goa))
+    a, b, c, d = (np.array(x, dtype=np.int32) for x in zip(*tabs))
+    p, _ = ctx.eval_tables(a, b, c, d)
+    want = np.array([oracle.fet(*t, mode=oracle.ONE_TAIL) for t in tabs])
+    ok = p_close(p, want, (a + b + c + d) >= 1000)
+    assert ok.all(), (np.array(tabs)[~ok][:5], p[~ok][:5], want[~ok][:5])
+    ctx.set_fet_mode(capi.FET_TWO_TAIL)
+    p2, _ = ctx.eval_tables(a[:50], b[:50], c[:50], d[:50])
+    assert (p2 == np.array([oracle.fet(*t) for t in tabs[:50]])).all()
+
+
 def test_chi_square_branch_sweep(ctx):
     rng = np.random.default_rng(9)
     tabs = []
