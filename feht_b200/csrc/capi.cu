@@ -1130,12 +1130,9 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     if (n > 0) {
         CU(c, ensure(c->sw_key_a, nn)); CU(c, ensure(c->sw_key_b, nn));
         CU(c, ensure(c->sw_val_a, nn)); CU(c, ensure(c->sw_val_b, nn));
-        use_coop = sort_engine_allows_coop() && c->num_sms <= coop_sort_max_grid() && n <= coop_sort_capacity(c->num_sms);
+        use_coop = sort_engine_allows_coop() && c->num_sms <= coop_sort_max_grid();
         if (use_coop) {
-            if (!c->sw_coop.p) {
-                CU(c, ensure(c->sw_coop, coop_sort_control_words(c->num_sms)));
-                CU(c, cudaMemsetAsync(c->sw_coop.p, 0, coop_sort_control_words(c->num_sms) * 4, c->st));
-            }
+            if (!c->sw_coop.p) CU(c, ensure(c->sw_coop, coop_sort_control_words(c->num_sms)));
             c->sw.coop = c->sw_coop.p;
         } else {
             CU(c, ensure(c->sw_control, size_t(16) * 256 + 16 + size_t(16) * sort_status_words(n)));

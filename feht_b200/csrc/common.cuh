@@ -155,6 +155,7 @@ struct SortWorkspace {
     uint32_t *or_and = nullptr;   // 8 words
     uint32_t *coop = nullptr;     // cooperative sort: [num_sms][256] tagged CTA digit counts, [num_sms] flags, selector
     uint32_t coop_launches = 0;   // tag generator of the cooperative sort (host side)
+    int coop_clean_rows = 0;      // rows of the count table known to hold only tags of recent launches
 };
 size_t sort_status_words(int64_t n);
 // Sorts n survivors by (comp asc, key64 asc, rank asc); rank_presorted = the survivors already sit
@@ -168,9 +169,9 @@ struct ResultSoA {
     int32_t *rank, *goa, *gob, *gta, *gtb;
     double *p, *ratio;
 };
-// Single-wave variant (n <= coop_sort_capacity): every pass inside one cooperative launch, the pass list
-// decided on the device (no host synchronisation); the permutation ends up in ws.val_a or ws.val_b as the
-// device word coop_sort_selector() says (0 / 1).
+// Cooperative engine: every pass inside one launch, the pass list decided on the device (no host
+// synchronisation); one chunk per CTA up to coop_sort_capacity, several beyond.  The permutation ends up in
+// ws.val_a or ws.val_b as the device word coop_sort_selector() says (0 / 1).
 int64_t coop_sort_capacity(int num_sms);
 int coop_sort_max_grid();
 size_t coop_sort_control_words(int num_sms);

@@ -211,8 +211,9 @@ struct CoopArgs {
     unsigned long long *key[2];
     uint32_t *val[2];
     int64_t n;
-    int chunk;                  // items per CTA (last CTA may hold fewer)
+    int chunk;                  // items per chunk
     int rounds;                 // ceil(chunk / kCoopThreads) <= kCoopItems
+    int chunks;                 // chunks per CTA (multi-chunk variant; the single-chunk variant has one)
     const uint32_t *or_and;     // [8]: OR of (rank, key lo, key hi, comp), then AND of the same
     const uint32_t *r_rank, *r_comp;
     int rank_presorted;
@@ -249,14 +250,37 @@ __device__ __forceinline__ void grid_barrier(uint32_t *bar, unsigned &target) {
     __syncthreads();
 }
 
+// lanes of the warp holding the same 9-bit digit: nine ballots instead of MATCH.ANY
+__device__ __forceinline__ unsigned peers_of(uint32_t d) {
+#ifdef FEHT_SORT_MATCH_ANY
+    return __match_any_sync(0xffffffffu, d);
+#else
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+#endif
+}
+
 constexpr size_t kCoopDynSmem = size_t(kCoopCap) * (8 + 4 + 1);
 
+// MULTI = false: one chunk per CTA (n <= grid * 8192), counts exchanged as tagged words, no barrier before the
+// prefix.  MULTI = true: each CTA owns a contiguous range of `chunks` full chunks; a pass first counts the digits
+// of the whole range (keys read once more), exchanges plain counts behind a grid barrier, then ranks, stages and
+// writes chunk after chunk with a running per-digit offset -- three sweeps of the data per pass instead of the
+// two of a look-back design, but every write is a run of one digit's items (32 per chunk on average = 256 B).
+template <bool MULTI>
 __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid_constant__ CoopArgs A) {
     // cnt: per-warp digit counters while ranking; afterwards the same 32 KB hold the partial sums of the
     // cross-CTA prefix (16 slices x {before, total} x 256 digits)
     __shared__ __align__(16) unsigned int cnt[kCoopWarps][256];
-    __shared__ unsigned int lstart[256];   // CTA-local start of each digit in the staged order
+    __shared__ unsigned int lstart[256];   // chunk-local start of each digit in the staged order
     __shared__ unsigned int goff[256];     // global position of staged index 0 of each digit
+    __shared__ unsigned int run_off[256];  // global position of this CTA's next item of each digit
     __shared__ unsigned int wsum[8];
     extern __shared__ __align__(16) unsigned char dyn[];
     unsigned long long *stage_k = reinterpret_cast<unsigned long long *>(dyn);
@@ -266,8 +290,8 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int cta = blockIdx.x, G = gridDim.x;
-    const int64_t base = int64_t(cta) * A.chunk;
-    const int count = int(min(int64_t(A.chunk), max(int64_t(0), A.n - base)));
+    const int n_chunks = MULTI ? A.chunks : 1;
+    const int64_t cta_base = int64_t(cta) * A.chunk * n_chunks;
     const int rounds = A.rounds;
     const int wbase = wid * 32 * rounds;
     uint32_t oa[8];
@@ -299,131 +323,166 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
         unsigned long long *kout = A.key[cur ^ 1];
         uint32_t *vout = A.val[cur ^ 1];
 
-        for (int j = tid; j < kCoopWarps * 256; j += kCoopThreads) (&cnt[0][0])[j] = 0;
-        unsigned long long k[kCoopItems];
-        uint32_t v[kCoopItems];
-        uint32_t dr[kCoopItems];   // digit | rank inside the warp's items << 9
-#pragma unroll
-        for (int it = 0; it < kCoopItems; ++it) {
-            const int li = wbase + it * 32 + lane;
-            const bool in = it < rounds && li < count;
-            // .cg: the ping-pong buffers are rewritten by other SMs every pass
-            k[it] = in ? __ldcg(kin + base + li) : 0ull;
-            v[it] = in ? __ldcg(vin + base + li) : 0u;
-        }
-        __syncthreads();
-        // stable rank of every item among the warp's items with the same digit (issuing all the MATCH ops
-        // first was tried: it spills under the 64-register cap and came out 4% slower)
-#pragma unroll
-        for (int it = 0; it < kCoopItems; ++it) {
-            if (it < rounds) {
-                const bool in = wbase + it * 32 + lane < count;
-                const uint32_t d = in ? digit_of(src, shift, k[it], v[it], word) : 256u;
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                const unsigned lower = peers & ((1u << lane) - 1u);
-                uint32_t b = 0;
-                if (d < 256u) b = cnt[wid][d];
-                __syncwarp();
-                if (d < 256u && lower == 0) cnt[wid][d] = b + __popc(peers);
-                __syncwarp();
-                dr[it] = d | ((b + __popc(lower)) << 9);
+        if (MULTI) {
+            // sweep 1: digit counts of the CTA's whole range
+            for (int j = tid; j < kCoopWarps * 256; j += kCoopThreads) (&cnt[0][0])[j] = 0;
+            __syncthreads();
+            const int64_t lo = cta_base, hi = min(A.n, cta_base + int64_t(A.chunk) * n_chunks);
+            for (int64_t i = lo + tid; i < hi; i += kCoopThreads) {
+                const uint32_t d = src == 0 ? uint32_t(__ldcg(kin + i) >> shift) & 255u
+                                            : (__ldg(word + __ldcg(vin + i)) >> shift) & 255u;
+                atomicAdd(&cnt[wid][d], 1u);
             }
-        }
-        __syncthreads();
-        if (tid < 256) {
-            unsigned run = 0;
+            __syncthreads();
+            if (tid < 256) {
+                unsigned run = 0;
 #pragma unroll 8
-            for (int ww = 0; ww < kCoopWarps; ++ww) {
-                const unsigned c = cnt[ww][tid];
-                cnt[ww][tid] = run;
-                run += c;
+                for (int ww = 0; ww < kCoopWarps; ++ww) run += cnt[ww][tid];
+                A.hist[size_t(cta) * 256 + tid] = run;
             }
-            A.hist[size_t(cta) * 256 + tid] = (tag << 16) | run;   // published: the tag makes the word self-validating
-            unsigned inc = run;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) wsum[wid] = inc;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            unsigned wb = 0;
-#pragma unroll
-            for (int ww = 0; ww < 8; ++ww)
-                if (ww < wid) wb += wsum[ww];
-            lstart[tid] = wb + inc - run;
+            grid_barrier(A.bar, target);
         }
-        __syncthreads();
-        // stage the chunk in digit order (stable): needs nothing from the other CTAs
+
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int64_t base = cta_base + int64_t(ch) * A.chunk;
+            const int count = int(min(int64_t(A.chunk), max(int64_t(0), A.n - base)));
+            if (MULTI) __syncthreads();   // the previous chunk's stage and cnt are consumed
+            for (int j = tid; j < kCoopWarps * 256; j += kCoopThreads) (&cnt[0][0])[j] = 0;
+            unsigned long long k[kCoopItems];
+            uint32_t v[kCoopItems];
+            uint32_t dr[kCoopItems];   // digit | rank inside the warp's items << 9
 #pragma unroll
-        for (int it = 0; it < kCoopItems; ++it) {
-            if (it < rounds) {
-                const uint32_t d = dr[it] & 511u;
-                if (d < 256u) {
-                    const uint32_t li = lstart[d] + cnt[wid][d] + (dr[it] >> 9);
-                    stage_k[li] = k[it];
-                    stage_v[li] = v[it];
-                    stage_d[li] = (unsigned char)d;
+            for (int it = 0; it < kCoopItems; ++it) {
+                const int li = wbase + it * 32 + lane;
+                const bool in = it < rounds && li < count;
+                // .cg: the ping-pong buffers are rewritten by other SMs every pass
+                k[it] = in ? __ldcg(kin + base + li) : 0ull;
+                v[it] = in ? __ldcg(vin + base + li) : 0u;
+            }
+            __syncthreads();
+            // stable rank of every item among the warp's items with the same digit (issuing all the MATCH ops
+            // first was tried: it spills under the 64-register cap and came out 4% slower)
+#pragma unroll
+            for (int it = 0; it < kCoopItems; ++it) {
+                if (it < rounds) {
+                    const bool in = wbase + it * 32 + lane < count;
+                    const uint32_t d = in ? digit_of(src, shift, k[it], v[it], word) : 256u;
+                    const unsigned peers = peers_of(d);
+                    const unsigned lower = peers & ((1u << lane) - 1u);
+                    uint32_t b = 0;
+                    if (d < 256u) b = cnt[wid][d];
+                    __syncwarp();
+                    if (d < 256u && lower == 0) cnt[wid][d] = b + __popc(peers);
+                    __syncwarp();
+                    dr[it] = d | ((b + __popc(lower)) << 9);
                 }
             }
-        }
-        __syncthreads();
-        {
-            // counts of every digit in the CTAs before me and in all CTAs: thread = 4 digits x one of 16
-            // slices of the CTA list, 128-bit loads, all of a thread's loads in flight together.  No grid
-            // barrier: a word is valid once it carries this pass's tag, so a thread only waits for the
-            // words it needs (one L2 round trip after the slowest CTA published).
-            const int q = tid & 63, grp = tid >> 6;
-            uint4 before = make_uint4(0, 0, 0, 0), total = make_uint4(0, 0, 0, 0);
-            const uint4 *h4 = reinterpret_cast<const uint4 *>(A.hist);
-            constexpr int kSlice = 10;   // 16 x 10 >= any grid this kernel is launched with
-            uint4 h[kSlice];
+            __syncthreads();
+            unsigned my_run = 0;   // threads 0..255: items of digit tid in this chunk
+            if (tid < 256) {
+                unsigned run = 0;
+#pragma unroll 8
+                for (int ww = 0; ww < kCoopWarps; ++ww) {
+                    const unsigned c = cnt[ww][tid];
+                    cnt[ww][tid] = run;
+                    run += c;
+                }
+                my_run = run;
+                if (!MULTI) A.hist[size_t(cta) * 256 + tid] = (tag << 16) | run;   // the tag makes the word self-validating
+                unsigned inc = run;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) wsum[wid] = inc;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                unsigned wb = 0;
 #pragma unroll
-            for (int j = 0; j < kSlice; ++j) {
-                const int c = grp + 16 * j;
-                h[j] = c < G ? __ldcg(h4 + size_t(c) * 64 + q) : make_uint4(0, 0, 0, 0);
+                for (int ww = 0; ww < 8; ++ww)
+                    if (ww < wid) wb += wsum[ww];
+                lstart[tid] = wb + inc - run;
             }
+            __syncthreads();
+            // stage the chunk in digit order (stable): needs nothing from the other CTAs
 #pragma unroll
-            for (int j = 0; j < kSlice; ++j) {
-                const int c = grp + 16 * j;
-                if (c < G) {
-                    while ((h[j].x >> 16) != tag || (h[j].y >> 16) != tag || (h[j].z >> 16) != tag ||
-                           (h[j].w >> 16) != tag)
-                        h[j] = ld_relaxed_v4(h4 + size_t(c) * 64 + q);
-                    const uint4 m = make_uint4(h[j].x & 0xffffu, h[j].y & 0xffffu, h[j].z & 0xffffu, h[j].w & 0xffffu);
-                    total.x += m.x; total.y += m.y; total.z += m.z; total.w += m.w;
-                    if (c < cta) { before.x += m.x; before.y += m.y; before.z += m.z; before.w += m.w; }
+            for (int it = 0; it < kCoopItems; ++it) {
+                if (it < rounds) {
+                    const uint32_t d = dr[it] & 511u;
+                    if (d < 256u) {
+                        const uint32_t li = lstart[d] + cnt[wid][d] + (dr[it] >> 9);
+                        stage_k[li] = k[it];
+                        stage_v[li] = v[it];
+                        stage_d[li] = (unsigned char)d;
+                    }
                 }
             }
-            *reinterpret_cast<uint4 *>(&part[grp][4 * q]) = before;
-            *reinterpret_cast<uint4 *>(&part[16 + grp][4 * q]) = total;
-        }
-        __syncthreads();
-        if (tid < 256) {
-            unsigned before = 0, total = 0;
+            __syncthreads();
+            if (ch == 0) {
+                // counts of every digit in the CTAs before me and in all CTAs: thread = 4 digits x one of 16
+                // slices of the CTA list, 128-bit loads, all of a thread's loads in flight together.  Single
+                // chunk: no grid barrier, a word is valid once it carries this pass's tag, so a thread only
+                // waits for the words it needs (one L2 round trip after the slowest CTA published).
+                const int q = tid & 63, grp = tid >> 6;
+                uint4 before = make_uint4(0, 0, 0, 0), total = make_uint4(0, 0, 0, 0);
+                const uint4 *h4 = reinterpret_cast<const uint4 *>(A.hist);
+                constexpr int kSlice = 10;   // 16 x 10 >= any grid this kernel is launched with
+                uint4 h[kSlice];
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
-                before += part[g][tid];
-                total += part[16 + g][tid];
-            }
-            unsigned inc = total;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) wsum[wid] = inc;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            unsigned wb = 0;
+                for (int j = 0; j < kSlice; ++j) {
+                    const int c = grp + 16 * j;
+                    h[j] = c < G ? __ldcg(h4 + size_t(c) * 64 + q) : make_uint4(0, 0, 0, 0);
+                }
 #pragma unroll
-            for (int ww = 0; ww < 8; ++ww)
-                if (ww < wid) wb += wsum[ww];
-            goff[tid] = wb + inc - total + before - lstart[tid];
-        }
-        __syncthreads();
-        // consecutive threads write consecutive addresses inside each digit's run
-        for (int li = tid; li < count; li += kCoopThreads) {
-            const uint32_t pos = goff[stage_d[li]] + uint32_t(li);
-            kout[pos] = stage_k[li];
-            vout[pos] = stage_v[li];
+                for (int j = 0; j < kSlice; ++j) {
+                    const int c = grp + 16 * j;
+                    if (c < G) {
+                        uint4 m = h[j];
+                        if (!MULTI) {
+                            while ((h[j].x >> 16) != tag || (h[j].y >> 16) != tag || (h[j].z >> 16) != tag ||
+                                   (h[j].w >> 16) != tag)
+                                h[j] = ld_relaxed_v4(h4 + size_t(c) * 64 + q);
+                            m = make_uint4(h[j].x & 0xffffu, h[j].y & 0xffffu, h[j].z & 0xffffu, h[j].w & 0xffffu);
+                        }
+                        total.x += m.x; total.y += m.y; total.z += m.z; total.w += m.w;
+                        if (c < cta) { before.x += m.x; before.y += m.y; before.z += m.z; before.w += m.w; }
+                    }
+                }
+                *reinterpret_cast<uint4 *>(&part[grp][4 * q]) = before;
+                *reinterpret_cast<uint4 *>(&part[16 + grp][4 * q]) = total;
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned before1 = 0, total1 = 0;
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) {
+                        before1 += part[g][tid];
+                        total1 += part[16 + g][tid];
+                    }
+                    unsigned inc = total1;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    if (lane == 31) wsum[wid] = inc;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    unsigned wb = 0;
+#pragma unroll
+                    for (int ww = 0; ww < 8; ++ww)
+                        if (ww < wid) wb += wsum[ww];
+                    run_off[tid] = wb + inc - total1 + before1;
+                }
+            }
+            if (tid < 256) {
+                // (threads 0..255 own run_off[tid]: no other thread touches it)
+                goff[tid] = run_off[tid] - lstart[tid];
+                run_off[tid] += my_run;
+            }
+            __syncthreads();
+            // consecutive threads write consecutive addresses inside each digit's run
+            for (int li = tid; li < count; li += kCoopThreads) {
+                const uint32_t pos = goff[stage_d[li]] + uint32_t(li);
+                kout[pos] = stage_k[li];
+                vout[pos] = stage_v[li];
+            }
         }
         cur ^= 1;
         // the next pass reads what every CTA just wrote.  (One flag per CTA with every CTA polling all
@@ -589,7 +648,7 @@ size_t coop_sort_control_words(int num_sms) { return size_t(num_sms) * 256 + 8; 
 
 cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
                            bool rank_presorted, int num_sms, cudaStream_t st, int *launches) {
-    // control block: [grid][256] tagged counts, the buffer selector, the barrier counter
+    // control block: [grid][256] digit counts, the buffer selector, the barrier counter
     uint32_t *sel = ws.coop + size_t(num_sms) * 256;
     cudaError_t e = cudaMemsetAsync(sel, 0, 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess || n <= 1) return e;
@@ -597,11 +656,23 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, 
     a.key[0] = ws.key_a; a.key[1] = ws.key_b;
     a.val[0] = ws.val_a; a.val[1] = ws.val_b;
     a.n = n;
-    // whole warps per CTA, as few CTAs idle as possible
-    int64_t chunk = (n + num_sms - 1) / num_sms;
-    chunk = (chunk + kCoopThreads - 1) / kCoopThreads * kCoopThreads;
-    a.chunk = int(chunk);
-    a.rounds = int(chunk / kCoopThreads);
+    const bool multi = n > coop_sort_capacity(num_sms);
+    int grid;
+    if (!multi) {
+        // whole warps per CTA, as few CTAs idle as possible
+        int64_t chunk = (n + num_sms - 1) / num_sms;
+        chunk = (chunk + kCoopThreads - 1) / kCoopThreads * kCoopThreads;
+        a.chunk = int(chunk);
+        a.rounds = int(chunk / kCoopThreads);
+        a.chunks = 1;
+        grid = int((n + chunk - 1) / chunk);
+    } else {
+        a.chunk = kCoopCap;
+        a.rounds = kCoopItems;
+        const int64_t total_chunks = (n + kCoopCap - 1) / kCoopCap;
+        a.chunks = int((total_chunks + num_sms - 1) / num_sms);
+        grid = int((total_chunks + a.chunks - 1) / a.chunks);
+    }
     a.or_and = ws.or_and;
     a.r_rank = reinterpret_cast<const uint32_t *>(r_rank);
     a.r_comp = reinterpret_cast<const uint32_t *>(r_comp);
@@ -609,18 +680,30 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, 
     a.hist = ws.coop;
     a.sel = sel;
     a.bar = sel + 1;
-    // the control block is zeroed when it is allocated; a launch uses tags base+1 .. base+16 (never 0, no
-    // overlap with the launches before it; the sequence repeats after 2047 launches, by when every slot in
-    // use has been rewritten many times)
+    // Tags (single-chunk variant).  The control block is zeroed when it is allocated; a launch uses tags
+    // base+1 .. base+16, never 0 and never those of the launches around it.  The sequence repeats after 2047
+    // launches, so rows of the table that no launch in between has rewritten (a larger grid than any recent one,
+    // or multi-chunk launches, which store plain counts) are cleared first.
     ws.coop_launches = ws.coop_launches % 2047u + 1u;
     a.tag_base = ws.coop_launches * 32u;
-    const int grid = int((n + chunk - 1) / chunk);
-    static const cudaError_t attr = cudaFuncSetAttribute(coop_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         int(kCoopDynSmem));
+    if (multi) {
+        ws.coop_clean_rows = 0;
+    } else if (grid > ws.coop_clean_rows || ws.coop_launches == 1u) {
+        e = cudaMemsetAsync(ws.coop, 0, size_t(num_sms) * 256 * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        ws.coop_clean_rows = num_sms;
+    }
+    static const cudaError_t attr = [] {
+        cudaError_t r = cudaFuncSetAttribute(coop_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(kCoopDynSmem));
+        if (r != cudaSuccess) return r;
+        return cudaFuncSetAttribute(coop_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCoopDynSmem));
+    }();
     if (attr != cudaSuccess) return attr;
     void *args[] = {&a};
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(coop_sort_kernel), dim3(grid), dim3(kCoopThreads),
-                                    args, kCoopDynSmem, st);
+    const void *fn = multi ? reinterpret_cast<const void *>(coop_sort_kernel<true>)
+                           : reinterpret_cast<const void *>(coop_sort_kernel<false>);
+    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopThreads), args, kCoopDynSmem, st);
     if (launches) ++*launches;
     return e;
 }
