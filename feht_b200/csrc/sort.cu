@@ -667,11 +667,14 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, 
         a.chunks = 1;
         grid = int((n + chunk - 1) / chunk);
     } else {
-        a.chunk = kCoopCap;
-        a.rounds = kCoopItems;
-        const int64_t total_chunks = (n + kCoopCap - 1) / kCoopCap;
-        a.chunks = int((total_chunks + num_sms - 1) / num_sms);
-        grid = int((total_chunks + a.chunks - 1) / a.chunks);
+        // as many chunks per CTA as full-size chunks would need, then the chunk shrunk so that every SM gets work
+        // (1.24M keys: 2 chunks of 5120 on 121 CTAs, not 2 x 8192 on 76)
+        a.chunks = int((n + coop_sort_capacity(num_sms) - 1) / coop_sort_capacity(num_sms));
+        int64_t chunk = (n + int64_t(num_sms) * a.chunks - 1) / (int64_t(num_sms) * a.chunks);
+        chunk = (chunk + kCoopThreads - 1) / kCoopThreads * kCoopThreads;
+        a.chunk = int(chunk);
+        a.rounds = int(chunk / kCoopThreads);
+        grid = int((n + chunk * a.chunks - 1) / (chunk * a.chunks));
     }
     a.or_and = ws.or_and;
     a.r_rank = reinterpret_cast<const uint32_t *>(r_rank);
