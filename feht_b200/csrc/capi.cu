@@ -53,8 +53,8 @@ struct feht_ctx {
     cudaStream_t own_stream = nullptr, st = nullptr, copy_stream = nullptr;
     // stage events of a run, two sets used alternately: feht_run_async re-records a set only after the run
     // before last has been timed, so consecutive runs can be enqueued without a host synchronisation
-    cudaEvent_t evr[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-    struct PendingRun { bool active = false; double launches = 0, count_launches = 0, count_bytes = 0; } pend[2];
+    cudaEvent_t evr[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
+    struct PendingRun { bool active = false, fused = false; double launches = 0, count_launches = 0, count_bytes = 0; } pend[2];
     int ev_slot = 0;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // runs, count/test/order/total ms, launches, count launches
     cudaEvent_t ev_copied[4] = {nullptr, nullptr, nullptr, nullptr}, ev_used[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -99,10 +99,10 @@ struct feht_ctx {
     DevBuf<SlotDef> sdefs;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
     int64_t survivor_hint = 0;             // survivors of the last filtered run (sizes the next run's arrays)
-    DevBuf<int32_t> r_comp, r_row, r_rank, o_rank, o_goa, o_gob, o_gta, o_gtb;
+    DevBuf<int32_t> r_comp, o_rank, o_goa, o_gob, o_gta, o_gtb;
+    DevBuf<SurvivorRec> r_rec;
     DevBuf<int64_t> o_row;
-    DevBuf<int4> r_cnt;
-    DevBuf<double> r_p, r_ratio, o_p, o_ratio;
+    DevBuf<double> r_p, o_p, o_ratio;
     SortWorkspace sw;
     DevBuf<unsigned long long> sw_key_a, sw_key_b;
     DevBuf<uint32_t> sw_val_a, sw_val_b, sw_control, sw_oa, sw_coop;
@@ -510,7 +510,7 @@ extern "C" int feht_create(feht_ctx **out, int device) {
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     c->st = c->own_stream;
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         for (int k = 0; k < 2; ++k)
             if ((e = cudaEventCreate(&c->evr[k][i])) != cudaSuccess) return bail("event", e);
     if ((e = cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
@@ -534,14 +534,14 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->rank); release(c->stage[0]); release(c->stage[1]);
     release(c->gemm_b); release(c->gemm_passes);
     release(c->masks); release(c->counts); release(c->groups); release(c->fracs); release(c->gcomps); release(c->sdefs); release(c->seg_count);
-    release(c->r_comp); release(c->r_row); release(c->r_rank); release(c->o_row); release(c->o_rank);
+    release(c->r_comp); release(c->r_rec); release(c->o_row); release(c->o_rank);
     release(c->o_goa); release(c->o_gob); release(c->o_gta); release(c->o_gtb);
-    release(c->r_cnt); release(c->r_p); release(c->r_ratio); release(c->o_p); release(c->o_ratio);
+    release(c->r_p); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
-        for (int i = 0; i < 4; ++i) if (c->evr[k][i]) cudaEventDestroy(c->evr[k][i]);
+        for (int i = 0; i < 5; ++i) if (c->evr[k][i]) cudaEventDestroy(c->evr[k][i]);
     for (int i = 0; i < 4; ++i) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_used[i]) cudaEventDestroy(c->ev_used[i]);
@@ -787,12 +787,17 @@ int settle(feht_ctx *c, int slot) {
     feht_ctx::PendingRun &pr = c->pend[slot];
     if (!pr.active) return FEHT_OK;
     cudaEvent_t *ev = c->evr[slot];
-    CU(c, cudaEventSynchronize(ev[3]));
-    float ms = 0;
+    CU(c, cudaEventSynchronize(ev[4]));
+    // ev: 0 | count | 1 | screen | 2 | A | 3 | B | 4 with (A, B) = (p-values, order + gather) for the p-value
+    // order and (order, p-values fused with the gather) for the reference's |ratio| order
+    float ms = 0, ms_screen = 0, ms_a = 0, ms_b = 0;
     CU(c, cudaEventElapsedTime(&ms, ev[0], ev[1])); c->tm.count_ms = ms;
-    CU(c, cudaEventElapsedTime(&ms, ev[1], ev[2])); c->tm.test_ms = ms;
-    CU(c, cudaEventElapsedTime(&ms, ev[2], ev[3])); c->tm.order_ms = ms;
-    CU(c, cudaEventElapsedTime(&ms, ev[0], ev[3])); c->tm.total_ms = ms;
+    CU(c, cudaEventElapsedTime(&ms_screen, ev[1], ev[2]));
+    CU(c, cudaEventElapsedTime(&ms_a, ev[2], ev[3]));
+    CU(c, cudaEventElapsedTime(&ms_b, ev[3], ev[4]));
+    c->tm.test_ms = ms_screen + (pr.fused ? ms_b : ms_a);
+    c->tm.order_ms = pr.fused ? ms_a : ms_b;
+    CU(c, cudaEventElapsedTime(&ms, ev[0], ev[4])); c->tm.total_ms = ms;
     c->tm.launches = pr.launches;
     c->tm.count_launches = pr.count_launches;
     c->tm.count_bytes = pr.count_bytes;
@@ -1079,15 +1084,25 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         tp.dense_by_rank = c->rank_is_perm;
     }
     const bool rank_presorted = tp.dense && (c->have_rank != 1 || tp.dense_by_rank);
+    // the reference's |ratio| order: K3a builds the sort keys, K4 sorts, K3b computes p row by row of the final
+    // order and writes every output column (no separate gather); p-value order: K3b first, then K4 + gather
+    const bool fused = sort_key == FEHT_SORT_ABS_RATIO_DESC;
+    CU(c, ensure(c->sw_oa, 8));
+    c->sw.or_and = c->sw_oa.p;
     auto ensure_survivors = [&](size_t nn) -> cudaError_t {
         cudaError_t e;
-        if ((e = ensure(c->r_comp, nn)) != cudaSuccess || (e = ensure(c->r_row, nn)) != cudaSuccess ||
-            (e = ensure(c->r_rank, nn)) != cudaSuccess || (e = ensure(c->r_cnt, nn)) != cudaSuccess ||
-            (e = ensure(c->r_p, nn)) != cudaSuccess || (e = ensure(c->r_ratio, nn)) != cudaSuccess)
+        if ((e = ensure(c->r_comp, nn)) != cudaSuccess || (e = ensure(c->r_rec, nn)) != cudaSuccess ||
+            (e = ensure(c->sw_key_a, nn)) != cudaSuccess || (e = ensure(c->sw_key_b, nn)) != cudaSuccess ||
+            (e = ensure(c->sw_val_a, nn)) != cudaSuccess || (e = ensure(c->sw_val_b, nn)) != cudaSuccess)
             return e;
-        tp.r_comp = c->r_comp.p; tp.r_row = c->r_row.p; tp.r_rank = c->r_rank.p;
-        tp.r_cnt = c->r_cnt.p; tp.r_ratio = c->r_ratio.p;
-        return cudaSuccess;
+        if (!fused && (e = ensure(c->r_p, nn)) != cudaSuccess) return e;
+        tp.r_comp = c->r_comp.p; tp.rec = c->r_rec.p;
+        c->sw.key_a = c->sw_key_a.p; c->sw.key_b = c->sw_key_b.p;
+        c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
+        tp.key = fused ? c->sw.key_a : nullptr;
+        tp.val = c->sw.val_a;
+        tp.or_and = c->sw.or_and;
+        return fused ? launch_init_or_and(c->sw.or_and, c->st) : cudaSuccess;
     };
     if (tp.dense) {
         for (int i = 0; i <= n_comps; ++i) c->seg_off[size_t(i)] = int64_t(i) * R;
@@ -1127,9 +1142,8 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     CU(c, ensure(c->o_goa, nn)); CU(c, ensure(c->o_gob, nn)); CU(c, ensure(c->o_gta, nn)); CU(c, ensure(c->o_gtb, nn));
     CU(c, ensure(c->o_p, nn)); CU(c, ensure(c->o_ratio, nn));
     bool use_coop = false;
+    const ResultSoA out{c->o_row.p, c->o_rank.p, c->o_goa.p, c->o_gob.p, c->o_gta.p, c->o_gtb.p, c->o_p.p, c->o_ratio.p};
     if (n > 0) {
-        CU(c, ensure(c->sw_key_a, nn)); CU(c, ensure(c->sw_key_b, nn));
-        CU(c, ensure(c->sw_val_a, nn)); CU(c, ensure(c->sw_val_b, nn));
         use_coop = sort_engine_allows_coop() && c->num_sms <= coop_sort_max_grid();
         if (use_coop) {
             if (!c->sw_coop.p) CU(c, ensure(c->sw_coop, coop_sort_control_words(c->num_sms)));
@@ -1137,45 +1151,61 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         } else {
             CU(c, ensure(c->sw_control, size_t(16) * 256 + 16 + size_t(16) * sort_status_words(n)));
         }
-        CU(c, ensure(c->sw_oa, 8));
-        c->sw.key_a = c->sw_key_a.p; c->sw.key_b = c->sw_key_b.p;
-        c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
         c->sw.control = c->sw_control.p;
-        c->sw.or_and = c->sw_oa.p;
         if (tp.dense) {
             CU(c, launch_test_emit(tp, c->st));
             ++launches;
         }
-        // K3b: p-values of the survivors (+ Bonferroni) and the sort keys
-        CU(c, launch_pvalues(c->r_cnt.p, c->r_ratio.p, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode,
-                             c->r_p.p, sort_key, c->sw.key_a, c->sw.val_a, c->sw.or_and, c->r_rank.p,
-                             c->r_comp.p, c->st));
-        ++launches;
     }
     CU(c, cudaEventRecord(ev[2], c->st));
-
-    // ---- K4 order
-    if (n > 0) {
-        const ResultSoA out{c->o_row.p, c->o_rank.p, c->o_goa.p, c->o_gob.p, c->o_gta.p, c->o_gtb.p,
-                            c->o_p.p, c->o_ratio.p};
+    uint32_t *perm = nullptr;
+    auto order = [&]() -> int {
         if (use_coop) {
-            // one wave of keys: every pass in a single cooperative launch, nothing read back by the host
-            CU(c, coop_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->num_sms, c->st, &launches));
-            CU(c, launch_gather_results(c->sw.val_a, c->sw.val_b, coop_sort_selector(c->sw, c->num_sms), n,
-                                        c->row_base, c->r_row.p, c->r_rank.p, c->r_cnt.p, c->r_p.p, c->r_ratio.p,
-                                        out, c->st));
+            // every pass in a single cooperative launch, nothing read back by the host
+            CU(c, coop_sort_perm(c->sw, n, c->r_rec.p, c->r_comp.p, rank_presorted, c->num_sms, c->st, &launches));
         } else {
-            uint32_t *perm = nullptr;
-            CU(c, radix_sort_perm(c->sw, n, c->r_rank.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
-            CU(c, launch_gather_results(perm, nullptr, nullptr, n, c->row_base, c->r_row.p, c->r_rank.p, c->r_cnt.p,
-                                        c->r_p.p, c->r_ratio.p, out, c->st));
+            CU(c, radix_sort_perm(c->sw, n, c->r_rec.p, c->r_comp.p, rank_presorted, c->st, &perm, &launches));
         }
+        return FEHT_OK;
+    };
+    PvalueIo io{};
+    io.rec = c->r_rec.p;
+    io.r_comp = c->r_comp.p;
+    if (n > 0 && fused) {
+        if (int rc = order()) return rc;
+        CU(c, cudaEventRecord(ev[3], c->st));
+        // K3b fused with the gather: p (+ Bonferroni) of the survivors in their final order, all columns written
+        io.perm_a = use_coop ? c->sw.val_a : perm;
+        io.perm_b = use_coop ? c->sw.val_b : nullptr;
+        io.d_sel = use_coop ? coop_sort_selector(c->sw, c->num_sms) : nullptr;
+        io.out = out;
+        io.row_base = c->row_base;
+        CU(c, launch_pvalues(io, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode, c->st));
         ++launches;
+    } else if (n > 0) {
+        // p-value order: K3b computes p and the keys, then K4 and the gather
+        io.d_p = c->r_p.p;
+        io.d_key = c->sw.key_a;
+        io.d_val = c->sw.val_a;
+        io.d_or_and = c->sw.or_and;
+        CU(c, launch_pvalues(io, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode, c->st));
+        ++launches;
+        CU(c, cudaEventRecord(ev[3], c->st));
+        if (int rc = order()) return rc;
+        if (use_coop)
+            CU(c, launch_gather_results(c->sw.val_a, c->sw.val_b, coop_sort_selector(c->sw, c->num_sms), n, c->row_base,
+                                        c->r_rec.p, c->r_p.p, out, c->st));
+        else
+            CU(c, launch_gather_results(perm, nullptr, nullptr, n, c->row_base, c->r_rec.p, c->r_p.p, out, c->st));
+        ++launches;
+    } else {
+        CU(c, cudaEventRecord(ev[3], c->st));
     }
-    CU(c, cudaEventRecord(ev[3], c->st));
+    CU(c, cudaEventRecord(ev[4], c->st));
     {
         feht_ctx::PendingRun &pr = c->pend[c->ev_slot];
         pr.active = true;
+        pr.fused = fused;
         pr.launches = launches;
         pr.count_launches = count_launches;
         const int n_planes = c->snp == 1 ? 3 : 2;
@@ -1342,13 +1372,13 @@ extern "C" int feht_eval_tables(feht_ctx *c, const int32_t *goa, const int32_t *
             return fail(c, FEHT_E_INVALID, "negative count (the device path only sees popcounts)");
         h[size_t(i)] = make_int4(goa[i], gob[i], gta[i], gtb[i]);
     }
-    DevBuf<int4> dt; DevBuf<double> dp, dr;
-    CU(c, ensure(dt, size_t(n))); CU(c, ensure(dp, size_t(n))); CU(c, ensure(dr, size_t(n)));
+    DevBuf<int4> dt; DevBuf<double> dp, dr; DevBuf<SurvivorRec> drec;
+    CU(c, ensure(dt, size_t(n))); CU(c, ensure(dp, size_t(n))); CU(c, ensure(dr, size_t(n))); CU(c, ensure(drec, size_t(n)));
     CU(c, cudaMemcpyAsync(dt.p, h.data(), size_t(n) * 16, cudaMemcpyHostToDevice, c->st));
-    CU(c, launch_eval_tables(dt.p, n, c->d_choose, c->fet_mode, dp.p, dr.p, c->st));
+    CU(c, launch_eval_tables(dt.p, n, c->d_choose, c->fet_mode, dp.p, dr.p, drec.p, c->st));
     if (p_out) CU(c, cudaMemcpyAsync(p_out, dp.p, size_t(n) * 8, cudaMemcpyDeviceToHost, c->st));
     if (ratio_out) CU(c, cudaMemcpyAsync(ratio_out, dr.p, size_t(n) * 8, cudaMemcpyDeviceToHost, c->st));
     CU(c, cudaStreamSynchronize(c->st));
-    release(dt); release(dp); release(dr);
+    release(dt); release(dp); release(dr); release(drec);
     return FEHT_OK;
 }

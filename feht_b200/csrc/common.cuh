@@ -113,6 +113,19 @@ cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, 
                               int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
 
 // fet.cu  (K3)
+// What the final gather needs about a surviving test: exactly one 32-byte sector.
+struct __align__(16) SurvivorRec {
+    int4 cnt;        // (goa, gob, gta, gtb)
+    double ratio;
+    int32_t row;     // marker row inside this context
+    int32_t rank;    // name rank (tie-break of the order)
+};
+// ordered results, final types (what feht_result_fetch copies out)
+struct ResultSoA {
+    int64_t *row;
+    int32_t *rank, *goa, *gob, *gta, *gtb;
+    double *p, *ratio;
+};
 struct TestParams {
     const int4 *counts;       // [n_slots][n_rows]
     const ScreenGroup *groups;
@@ -125,10 +138,13 @@ struct TestParams {
     int n_comps;
     double ratio_filter;
     const int32_t *name_rank; // may be null
-    // survivors (SoA)
-    int32_t *r_comp, *r_row, *r_rank;
-    int4 *r_cnt;
-    double *r_ratio;
+    // survivors: one 32-byte record each + the comparison index (a sort digit source)
+    SurvivorRec *rec;
+    int32_t *r_comp;
+    // sort keys by |ratio|, built here when the order is the reference's (null: K3b builds p-value keys)
+    unsigned long long *key;
+    uint32_t *val;
+    uint32_t *or_and;
     unsigned long long *seg_count;   // filtered output: [n_comps] survivors per comparison (zeroed by the caller)
     unsigned long long *cursor;      // filtered output: next free survivor slot (zeroed by the caller)
     long long capacity;              // filtered output: slots the survivor arrays hold
@@ -139,13 +155,27 @@ struct TestParams {
 cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t *flags_words,
                                         unsigned long long *out_count, cudaStream_t st);
 cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
-// K3b over n compacted survivors: p (+ Bonferroni) and, when d_key != null, the sort keys + OR/AND words
-cudaError_t launch_pvalues(const int4 *d_tables, const double *d_ratio, int64_t n, const double *d_choose,
-                           int correction, double bonferroni_n, int one_tail, double *d_p, int sort_key,
-                           unsigned long long *d_key, uint32_t *d_val, uint32_t *d_or_and,
-                           const int32_t *r_rank, const int32_t *r_comp, cudaStream_t st);
+// OR/AND accumulators of the sort-key words (rank, key lo, key hi, comparison): {0,0,0,0,~0,~0,~0,~0}
+cudaError_t launch_init_or_and(uint32_t *d_or_and, cudaStream_t st);
+// K3b over n survivors: p (+ Bonferroni).
+//  * plain (perm_a == null): test i reads rec[i], writes d_p[i]; with d_key != null it also builds the p-value
+//    sort keys + OR/AND words (FEHT_SORT_PVALUE_ASC);
+//  * fused with the final gather (perm_a != null, the reference's |ratio| order): test i is the survivor
+//    perm[i] (perm = *d_sel ? perm_b : perm_a), and every output column of row i is written, p included.
+struct PvalueIo {
+    const SurvivorRec *rec;
+    const int32_t *r_comp;
+    double *d_p;
+    unsigned long long *d_key;
+    uint32_t *d_val, *d_or_and;
+    const uint32_t *perm_a, *perm_b, *d_sel;
+    ResultSoA out;
+    int64_t row_base;
+};
+cudaError_t launch_pvalues(const PvalueIo &io, int64_t n, const double *d_choose, int correction,
+                           double bonferroni_n, int one_tail, cudaStream_t st);
 cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose, int one_tail,
-                               double *d_p, double *d_ratio, cudaStream_t st);
+                               double *d_p, double *d_ratio, SurvivorRec *d_rec, cudaStream_t st);
 
 // sort.cu  (K4)
 struct SortWorkspace {
@@ -161,27 +191,21 @@ size_t sort_status_words(int64_t n);
 // Sorts n survivors by (comp asc, key64 asc, rank asc); rank_presorted = the survivors already sit
 // in name-rank order inside every comparison (the stable sort then needs no rank passes).
 // Returns the permutation (device pointer inside ws) and adds the number of kernel launches.
-cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec, const int32_t *r_comp,
                             bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches);
-// ordered results, final types (what feht_result_fetch copies out)
-struct ResultSoA {
-    int64_t *row;
-    int32_t *rank, *goa, *gob, *gta, *gtb;
-    double *p, *ratio;
-};
 // Cooperative engine: every pass inside one launch, the pass list decided on the device (no host
 // synchronisation); one chunk per CTA up to coop_sort_capacity, several beyond.  The permutation ends up in
 // ws.val_a or ws.val_b as the device word coop_sort_selector() says (0 / 1).
 int64_t coop_sort_capacity(int num_sms);
 int coop_sort_max_grid();
 size_t coop_sort_control_words(int num_sms);
-cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec, const int32_t *r_comp,
                            bool rank_presorted, int num_sms, cudaStream_t st, int *launches);
 const uint32_t *coop_sort_selector(const SortWorkspace &ws, int num_sms);
 // permutation = d_sel && *d_sel ? perm_b : perm_a
 cudaError_t launch_gather_results(const uint32_t *perm_a, const uint32_t *perm_b, const uint32_t *d_sel, int64_t n,
-                                  int64_t row_base, const int32_t *r_row, const int32_t *r_rank, const int4 *r_cnt,
-                                  const double *r_p, const double *r_ratio, const ResultSoA &o, cudaStream_t st);
+                                  int64_t row_base, const SurvivorRec *rec, const double *r_p, const ResultSoA &o,
+                                  cudaStream_t st);
 // K5: device k-way merge by ranking (dest[i][j] = final position of element j of shard i)
 int merge_max_shards();
 cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *const *d_key,

@@ -28,6 +28,7 @@
 namespace feht {
 namespace {
 
+constexpr int kRankStride = int(sizeof(SurvivorRec) / 4);   // words between the name ranks of two survivors
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kItems = 8;
@@ -37,22 +38,23 @@ constexpr uint32_t kFlagPrefix = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
 
 // digit of item for a pass: src 0 = byte of the carried 64-bit key, src 1 = byte of word[val]
+// (the name rank lives in the 32-byte survivor record: word stride 8; the comparison index has its own array)
 __device__ __forceinline__ uint32_t digit_of(int src, int shift, unsigned long long k, uint32_t v,
-                                             const uint32_t *__restrict__ word) {
-    return src == 0 ? uint32_t(k >> shift) & 255u : (__ldg(word + v) >> shift) & 255u;
+                                             const uint32_t *__restrict__ word, int stride) {
+    return src == 0 ? uint32_t(k >> shift) & 255u : (__ldg(word + size_t(v) * stride) >> shift) & 255u;
 }
 
 // global histogram of the first pass
 __global__ void __launch_bounds__(256)
 first_hist_kernel(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val,
-                  int64_t n, int src, int shift, const uint32_t *__restrict__ word,
+                  int64_t n, int src, int shift, const uint32_t *__restrict__ word, int stride,
                   uint32_t *__restrict__ hist) {
     __shared__ unsigned int h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += int64_t(gridDim.x) * blockDim.x)
-        atomicAdd(&h[digit_of(src, shift, key[i], val[i], word)], 1u);
+        atomicAdd(&h[digit_of(src, shift, key[i], val[i], word, stride)], 1u);
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(hist + threadIdx.x, h[threadIdx.x]);
 }
@@ -65,6 +67,7 @@ struct PassArgs {
     int64_t n;
     int src, shift;              // this pass's digit
     const uint32_t *word;        // gather source when src == 1
+    int stride, nstride;         // its word stride (this pass / next pass)
     const uint32_t *hist;        // [256] global digit counts of this pass
     uint32_t *ticket;            // tile ticket of this pass
     volatile uint32_t *status;   // [n_tiles][256]
@@ -102,8 +105,8 @@ __global__ void __launch_bounds__(kThreads) onesweep_pass_kernel(PassArgs A) {
 #pragma unroll
     for (int it = 0; it < kItems; ++it) {
         const bool in = warp_base + it * 32 + lane < A.n;
-        dig[it] = in ? digit_of(A.src, A.shift, k[it], v[it], A.word) : 256u;
-        if (A.has_next && in) atomicAdd(&nh[digit_of(A.nsrc, A.nshift, k[it], v[it], A.nword)], 1u);
+        dig[it] = in ? digit_of(A.src, A.shift, k[it], v[it], A.word, A.stride) : 256u;
+        if (A.has_next && in) atomicAdd(&nh[digit_of(A.nsrc, A.nshift, k[it], v[it], A.nword, A.nstride)], 1u);
     }
     // stable rank inside the warp's 32*kItems items, per digit
 #pragma unroll
@@ -215,7 +218,7 @@ struct CoopArgs {
     int rounds;                 // ceil(chunk / kCoopThreads) <= kCoopItems
     int chunks;                 // chunks per CTA (multi-chunk variant; the single-chunk variant has one)
     const uint32_t *or_and;     // [8]: OR of (rank, key lo, key hi, comp), then AND of the same
-    const uint32_t *r_rank, *r_comp;
+    const uint32_t *r_rank, *r_comp;   // digit sources: &rec[0].rank (word stride 8), comparison index (stride 1)
     int rank_presorted;
     uint32_t *hist;             // [grid][256] per-CTA digit counts of the current pass: tag << 16 | count
     uint32_t *sel;              // out: which val buffer holds the permutation
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
         const int src = (cand >= 4 && cand < 12) ? 0 : 1;
         const int shift = src == 0 ? 8 * (cand - 4) : 8 * (cand & 3);
         const uint32_t *word = cand < 4 ? A.r_rank : A.r_comp;
+        const int wstride = cand < 4 ? kRankStride : 1;
         ++tag;
 
         const unsigned long long *kin = A.key[cur];
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
             const int64_t lo = cta_base, hi = min(A.n, cta_base + int64_t(A.chunk) * n_chunks);
             for (int64_t i = lo + tid; i < hi; i += kCoopThreads) {
                 const uint32_t d = src == 0 ? uint32_t(__ldcg(kin + i) >> shift) & 255u
-                                            : (__ldg(word + __ldcg(vin + i)) >> shift) & 255u;
+                                            : (__ldg(word + size_t(__ldcg(vin + i)) * wstride) >> shift) & 255u;
                 atomicAdd(&cnt[wid][d], 1u);
             }
             __syncthreads();
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
             for (int it = 0; it < kCoopItems; ++it) {
                 if (it < rounds) {
                     const bool in = wbase + it * 32 + lane < count;
-                    const uint32_t d = in ? digit_of(src, shift, k[it], v[it], word) : 256u;
+                    const uint32_t d = in ? digit_of(src, shift, k[it], v[it], word, wstride) : 256u;
                     const unsigned peers = peers_of(d);
                     const unsigned lower = peers & ((1u << lane) - 1u);
                     uint32_t b = 0;
@@ -494,20 +498,20 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
 
 __global__ void __launch_bounds__(256)
 gather_kernel(const uint32_t *__restrict__ perm_a, const uint32_t *__restrict__ perm_b,
-              const uint32_t *__restrict__ sel, int64_t n, int64_t row_base, const int32_t *__restrict__ r_row,
-              const int32_t *__restrict__ r_rank, const int4 *__restrict__ r_cnt,
-              const double *__restrict__ r_p, const double *__restrict__ r_ratio, ResultSoA o) {
-    // the cooperative sort decides on the device how many passes run, hence where the permutation ends up
+              const uint32_t *__restrict__ sel, int64_t n, int64_t row_base, const SurvivorRec *__restrict__ rec,
+              const double *__restrict__ r_p, ResultSoA o) {
+    // (p-value order only: with the reference's |ratio| order K3b writes the final rows itself)
     const uint32_t *__restrict__ perm = (sel && *sel) ? perm_b : perm_a;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += int64_t(gridDim.x) * blockDim.x) {
         const uint32_t s = perm[i];
-        const int4 t = r_cnt[s];
-        o.row[i] = row_base + r_row[s];
-        o.rank[i] = r_rank[s];
+        const int4 *rp = reinterpret_cast<const int4 *>(rec + s);
+        const int4 t = __ldg(rp), u = __ldg(rp + 1);
+        o.row[i] = row_base + u.z;
+        o.rank[i] = u.w;
         o.goa[i] = t.x; o.gob[i] = t.y; o.gta[i] = t.z; o.gtb[i] = t.w;
         o.p[i] = r_p[s];
-        o.ratio[i] = r_ratio[s];
+        o.ratio[i] = __hiloint2double(u.y, u.x);
     }
 }
 
@@ -584,8 +588,9 @@ inline int blocks_for(int64_t n, int per) {
 
 size_t sort_status_words(int64_t n) { return size_t((n + kTile - 1) / kTile) * 256; }
 
-cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec, const int32_t *r_comp,
                             bool rank_presorted, cudaStream_t st, uint32_t **perm_out, int *launches) {
+    const uint32_t *r_rank = reinterpret_cast<const uint32_t *>(&rec->rank);
     *perm_out = ws.val_a;
     if (n <= 1) return cudaSuccess;
     uint32_t oa[8];
@@ -594,17 +599,17 @@ cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank,
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
 
-    struct Pass { int src, shift; const uint32_t *word; };
+    struct Pass { int src, shift; const uint32_t *word; int stride; };
     Pass passes[16];
     int np = 0;
     auto varying = [&](int w, int b) { return (((oa[w] ^ oa[4 + w]) >> (8 * b)) & 255u) != 0; };
     if (!rank_presorted)
         for (int b = 0; b < 4; ++b)
-            if (varying(0, b)) passes[np++] = Pass{1, 8 * b, reinterpret_cast<const uint32_t *>(r_rank)};
+            if (varying(0, b)) passes[np++] = Pass{1, 8 * b, r_rank, kRankStride};
     for (int b = 0; b < 8; ++b)
-        if (varying(1 + b / 4, b % 4)) passes[np++] = Pass{0, 8 * b, nullptr};
+        if (varying(1 + b / 4, b % 4)) passes[np++] = Pass{0, 8 * b, nullptr, 1};
     for (int b = 0; b < 4; ++b)
-        if (varying(3, b)) passes[np++] = Pass{1, 8 * b, reinterpret_cast<const uint32_t *>(r_comp)};
+        if (varying(3, b)) passes[np++] = Pass{1, 8 * b, reinterpret_cast<const uint32_t *>(r_comp), 1};
     if (np == 0) return cudaSuccess;
 
     const int n_tiles = int((n + kTile - 1) / kTile);
@@ -617,20 +622,21 @@ cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank,
     uint32_t *status = ws.control + 16 * 256 + 16;
 
     first_hist_kernel<<<blocks_for(n, 2048), 256, 0, st>>>(ws.key_a, ws.val_a, n, passes[0].src,
-                                                           passes[0].shift, passes[0].word, hist);
+                                                           passes[0].shift, passes[0].word, passes[0].stride, hist);
     if (launches) ++*launches;
     unsigned long long *kin = ws.key_a, *kout = ws.key_b;
     uint32_t *vin = ws.val_a, *vout = ws.val_b;
     for (int p = 0; p < np; ++p) {
         PassArgs a{};
         a.kin = kin; a.vin = vin; a.kout = kout; a.vout = vout; a.n = n;
-        a.src = passes[p].src; a.shift = passes[p].shift; a.word = passes[p].word;
+        a.src = passes[p].src; a.shift = passes[p].shift; a.word = passes[p].word; a.stride = passes[p].stride;
         a.hist = hist + p * 256;
         a.ticket = ticket + p;
         a.status = status + size_t(p) * status_words;
         a.has_next = p + 1 < np;
         if (a.has_next) {
             a.nsrc = passes[p + 1].src; a.nshift = passes[p + 1].shift; a.nword = passes[p + 1].word;
+            a.nstride = passes[p + 1].stride;
             a.nhist = hist + (p + 1) * 256;
         }
         onesweep_pass_kernel<<<n_tiles, kThreads, 0, st>>>(a);
@@ -646,7 +652,7 @@ int64_t coop_sort_capacity(int num_sms) { return int64_t(num_sms) * kCoopCap; }
 int coop_sort_max_grid() { return 160; }   // kSlice * 16 in the kernel
 size_t coop_sort_control_words(int num_sms) { return size_t(num_sms) * 256 + 8; }
 
-cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, const int32_t *r_comp,
+cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec, const int32_t *r_comp,
                            bool rank_presorted, int num_sms, cudaStream_t st, int *launches) {
     // control block: [grid][256] digit counts, the buffer selector, the barrier counter
     uint32_t *sel = ws.coop + size_t(num_sms) * 256;
@@ -677,7 +683,7 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, 
         grid = int((n + chunk * a.chunks - 1) / (chunk * a.chunks));
     }
     a.or_and = ws.or_and;
-    a.r_rank = reinterpret_cast<const uint32_t *>(r_rank);
+    a.r_rank = reinterpret_cast<const uint32_t *>(&rec->rank);
     a.r_comp = reinterpret_cast<const uint32_t *>(r_comp);
     a.rank_presorted = rank_presorted ? 1 : 0;
     a.hist = ws.coop;
@@ -714,11 +720,10 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const int32_t *r_rank, 
 const uint32_t *coop_sort_selector(const SortWorkspace &ws, int num_sms) { return ws.coop + size_t(num_sms) * 256; }
 
 cudaError_t launch_gather_results(const uint32_t *perm_a, const uint32_t *perm_b, const uint32_t *d_sel, int64_t n,
-                                  int64_t row_base, const int32_t *r_row, const int32_t *r_rank, const int4 *r_cnt,
-                                  const double *r_p, const double *r_ratio, const ResultSoA &o, cudaStream_t st) {
+                                  int64_t row_base, const SurvivorRec *rec, const double *r_p, const ResultSoA &o,
+                                  cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(perm_a, perm_b, d_sel, n, row_base, r_row, r_rank, r_cnt, r_p,
-                                                      r_ratio, o);
+    gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(perm_a, perm_b, d_sel, n, row_base, rec, r_p, o);
     return cudaGetLastError();
 }
 
