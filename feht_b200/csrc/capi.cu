@@ -856,8 +856,12 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     for (size_t k = 0; k < c->cats.size(); ++k) {
         cat_slot0[k] = n_slots;
         n_slots += (c->cats[k].n_values + 1) / 2;
-        if (c->cats[k].n_values > 2) cat_tot[k] = n_slots++;
     }
+    // "whole category" slots (one-vs-rest = total - value) go last: the popcount engine does not scan them, it
+    // adds up the category's value slots (the values partition the category's genomes)
+    const int n_scanned = n_slots;
+    for (size_t k = 0; k < c->cats.size(); ++k)
+        if (c->cats[k].n_values > 2) cat_tot[k] = n_slots++;
     if (size_t(n_slots) * 2 * plan.w4pad * 16 > (size_t(1) << 31))
         return fail(c, FEHT_E_INVALID, "mask storage too large");
     std::vector<uint64_t> hmask(size_t(n_slots) * 2 * mrow, 0);
@@ -1038,17 +1042,24 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     c->last_engine = use_gemm ? FEHT_ENGINE_GEMM : FEHT_ENGINE_POPC;
 
     CU(c, cudaEventRecord(ev[0], c->st));
-    const int n_popc_slots = use_gemm ? n_explicit : n_slots;
+    const int n_popc_slots = use_gemm ? n_explicit : n_scanned;
     if (c->snp == 1)
         CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
                                     c->masks.p, n_popc_slots, c->counts.p, c->num_sms, c->st, &count_launches));
     else
         CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_popc_slots,
                                 c->counts.p, c->num_sms, c->st, &count_launches));
-    if (use_gemm)
+    if (use_gemm) {
         CU(c, launch_count_gemm(c->plane[0], c->plane[1], c->n_units, c->W, c->S, c->gemm_b.p,
                                 c->gemm_passes.p, c->gemm_n_passes, c->counts.p, c->num_sms, c->st,
                                 &count_launches));
+    } else {
+        for (size_t k = 0; k < c->cats.size(); ++k)
+            if (cat_tot[k] >= 0) {
+                CU(c, launch_sum_slots(c->counts.p, R, cat_slot0[k], (c->cats[k].n_values + 1) / 2, cat_tot[k], c->st));
+                ++count_launches;
+            }
+    }
     launches += count_launches;
     CU(c, cudaEventRecord(ev[1], c->st));
 

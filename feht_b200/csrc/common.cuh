@@ -100,6 +100,9 @@ cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
                                   const PopcPlan &plan, const uint4 *d_masks, int n_slots,
                                   int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
 
+// counts[tot_slot][row] = (sum of P, sum of N, 0, 0) over both halves of pair-slots [slot0, slot0 + n)
+cudaError_t launch_sum_slots(int4 *d_counts, int64_t n_rows, int slot0, int n, int tot_slot, cudaStream_t st);
+
 // count_gemm.cu  (K2)
 int gemm_stage_count(int64_t S);
 size_t gemm_pass_desc_bytes();

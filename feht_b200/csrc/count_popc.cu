@@ -286,6 +286,21 @@ count_popc_snp_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ va
     }
 }
 
+// "whole category" record = sum of the category's value records: the values partition the category's genomes
+// (Table.hs:111-115,243-247), so the total mask never has to be scanned
+__global__ void __launch_bounds__(256)
+sum_slots_kernel(int4 *__restrict__ counts, int64_t n_rows, int slot0, int n, int tot_slot) {
+    for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += int64_t(gridDim.x) * blockDim.x) {
+        int p = 0, q = 0;
+        for (int s = 0; s < n; ++s) {
+            const int4 a = counts[size_t(slot0 + s) * size_t(n_rows) + size_t(r)];
+            p += a.x + a.z;
+            q += a.y + a.w;
+        }
+        counts[size_t(tot_slot) * size_t(n_rows) + size_t(r)] = make_int4(p, q, 0, 0);
+    }
+}
+
 // Launch one instantiation as a persistent grid: exactly (resident CTAs per SM) x (SMs) CTAs, each
 // looping over row groups, so there is no partial last wave (the first version launched 6 CTAs/SM
 // against an occupancy of 4 and lost a quarter of the time in a half-empty second wave).
@@ -415,6 +430,14 @@ cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
                                   int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
     return launch_any<true>(d_hi, d_valid, d_lo, n_sites, W, plan, d_masks, n_slots, d_counts,
                             num_sms, st, launches);
+}
+
+cudaError_t launch_sum_slots(int4 *d_counts, int64_t n_rows, int slot0, int n, int tot_slot, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    int64_t b = (n_rows + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    sum_slots_kernel<<<int(b), 256, 0, st>>>(d_counts, n_rows, slot0, n, tot_slot);
+    return cudaGetLastError();
 }
 
 }  // namespace feht
