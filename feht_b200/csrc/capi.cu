@@ -217,10 +217,13 @@ int check_mode(feht_ctx *c, int snp) {
 }
 
 constexpr size_t kStageBytes = size_t(96) << 20;
-// chars upload (add_chars_common): piece = at most 8 MB of chars; the DMA path moves up to 3 pieces per
-// staging slot (4 slots in one 96 MB buffer); a host worker packs one piece into a 4 MB pinned buffer
+// chars upload (add_chars_common): piece = about 8 MB of chars (one row if a row is longer); the DMA path moves up to
+// 3 consecutive pieces that fit a 24 MB staging slot (4 slots in one 96 MB buffer); a host worker packs one piece
+// into a pinned buffer of at most 4 MB.  (2 MB pieces, meant to keep the packed buffers in the last-level cache until
+// the DMA engine has read them, were slower: 52 vs 48 ms -- the workers then take 97% of the rows and the link idles.)
 constexpr size_t kPieceBytes = size_t(8) << 20;
 constexpr int kDmaPiecesMax = 3, kDmaSlots = 4;
+constexpr size_t kDmaSlotBytes = kStageBytes / kDmaSlots;
 constexpr int kPackBufsMax = 2;
 constexpr size_t kHostPackBufWords = size_t(4) << 17;   // 4 MB of 64-bit words
 constexpr size_t kHostPackMinBytes = size_t(64) << 20;  // smaller uploads are not worth waking the cores for
@@ -288,9 +291,9 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
             int64_t q = r;
             while (q < n) {
                 const size_t add = size_t(row_offsets[q + 1] - row_offsets[q]) + 8;
-                if (add + 64 > kPieceBytes)
+                if (add + 128 > kDmaSlotBytes)
                     return fail(c, FEHT_E_INVALID, "a single row exceeds the staging buffer");
-                if (bytes + add + 64 > kPieceBytes) break;
+                if (q > r && bytes + add > kPieceBytes) break;
                 if (size_t(q + 1 - r) * size_t(c->W) * size_t(n_planes) > kHostPackBufWords) break;
                 bytes += add;
                 ++q;
@@ -326,19 +329,26 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
         }
         c->pack_workers_alloc = workers;
     }
-    constexpr int kDmaPieces = kDmaPiecesMax, kPackBufs = kPackBufsMax;   // (1..3 pieces, 2..4 buffers: no measurable difference)
+    constexpr int kPackBufs = kPackBufsMax;
     std::mutex mu;
     int64_t lo = 0, hi = n_pieces - 1;
     auto claim_back = [&]() -> int64_t {
         std::lock_guard<std::mutex> g(mu);
         return lo <= hi ? hi-- : -1;
     };
-    auto claim_front = [&](int64_t *count) -> int64_t {   // up to kDmaPieces consecutive pieces
+    auto claim_front = [&](int64_t *count) -> int64_t {   // consecutive pieces that fit one staging slot
         std::lock_guard<std::mutex> g(mu);
         if (lo > hi) return -1;
         const int64_t first = lo;
-        *count = std::min<int64_t>(kDmaPieces, hi - lo + 1);
-        lo += *count;
+        int64_t cnt = 0;
+        while (lo <= hi && cnt < kDmaPiecesMax) {
+            const size_t bytes = size_t(row_offsets[piece_first[size_t(lo) + 1]] - row_offsets[piece_first[size_t(first)]]) +
+                                 size_t(piece_first[size_t(lo) + 1] - piece_first[size_t(first)] + 1) * 8 + 128;
+            if (cnt > 0 && bytes > kDmaSlotBytes) break;
+            ++lo;
+            ++cnt;
+        }
+        *count = cnt;
         return first;
     };
     std::atomic<int> worker_err{0};
@@ -379,7 +389,7 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
     // ---- DMA path.  Layout of a staged slot: [offsets (rows+1) x int64, rebased to 0][chars...].
     auto join_all = [&] { for (std::thread &th : pool) th.join(); };
     std::vector<std::vector<int64_t>> rebased;   // alive until the final synchronize
-    rebased.reserve(size_t(n_pieces / kDmaPieces + 2));
+    rebased.reserve(size_t(n_pieces) + 2);
     cudaError_t derr = ensure(c->stage[0], kStageBytes);
     for (int64_t k = 0; derr == cudaSuccess; ++k) {
         const int b = int(k % kDmaSlots);
@@ -389,7 +399,7 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
         int64_t cnt = 0;
         const int64_t i = claim_front(&cnt);
         if (i < 0) break;
-        unsigned char *dev = c->stage[0].p + size_t(b) * (kStageBytes / kDmaSlots);
+        unsigned char *dev = c->stage[0].p + size_t(b) * kDmaSlotBytes;
         const int64_t r0 = piece_first[size_t(i)], r1 = piece_first[size_t(i + cnt)];
         const int64_t rows = r1 - r0;
         rebased.emplace_back(size_t(rows) + 1);
