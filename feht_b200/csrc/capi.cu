@@ -91,6 +91,8 @@ struct feht_ctx {
     DevBuf<unsigned char> gemm_passes;
     int gemm_n_passes = 0;
     bool gemm_ready = false;         // gemm_b / gemm_passes match the current categories
+    bool plan_ready = false;         // masks / groups / fracs / gcomps / sdefs on the device match the comparisons
+    int plan_groups = 0, plan_max_frac = 0, plan_max_comp = 0, plan_max_slot = 0;
     int last_engine = 0;             // engine the last run counted categories with
     DevBuf<int4> counts;
     DevBuf<ScreenGroup> groups;
@@ -597,6 +599,7 @@ extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
     CU(c, cudaStreamSynchronize(c->st));
     for (int i = 0; i < 3; ++i) { if (c->plane[i]) cudaFree(c->plane[i]); c->plane[i] = nullptr; }
     c->gemm_ready = false;
+    c->plan_ready = false;
     c->S = n_samples;
     c->W = ((n_samples + 63) / 64 + 1) & ~int64_t(1);  // even number of 64-bit words: 16-byte rows
     c->snp = -1;
@@ -710,7 +713,8 @@ extern "C" int64_t feht_add_comparison(feht_ctx *c, const int32_t *g1, int64_t n
     for (int32_t v : cp.g1) { if (v < 0) return fail(c, FEHT_E_BOUNDS, "negative column index"); cp.max_col = std::max<int64_t>(cp.max_col, v); }
     for (int32_t v : cp.g2) { if (v < 0) return fail(c, FEHT_E_BOUNDS, "negative column index"); cp.max_col = std::max<int64_t>(cp.max_col, v); }
     c->comps.push_back(std::move(cp));
-    c->gemm_ready = false;  // explicit slots come first: the categories' slot base moves
+    c->gemm_ready = false;
+    c->plan_ready = false;  // explicit slots come first: the categories' slot base moves
     c->has_results = false;
     return int64_t(c->comps.size()) - 1;
 }
@@ -730,6 +734,7 @@ extern "C" int64_t feht_add_category(feht_ctx *c, const int32_t *value_of_sample
     const int ci = int(c->cats.size());
     c->cats.push_back(std::move(cat));
     c->gemm_ready = false;
+    c->plan_ready = false;
     const int64_t first = int64_t(c->comps.size());
     for (int i = 0; i < n_values; ++i)
         for (int j = i + 1; j < n_values; ++j) {
@@ -750,6 +755,7 @@ extern "C" int feht_clear_comparisons(feht_ctx *c) {
     c->comps.clear();
     c->cats.clear();
     c->gemm_ready = false;
+    c->plan_ready = false;
     c->has_results = false;
     return FEHT_OK;
 }
@@ -874,6 +880,9 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         if (c->cats[k].n_values > 2) cat_tot[k] = n_slots++;
     if (size_t(n_slots) * 2 * plan.w4pad * 16 > (size_t(1) << 31))
         return fail(c, FEHT_E_INVALID, "mask storage too large");
+    // The masks and the screen plan only change with the comparisons (and S): a context that runs the same
+    // comparisons again re-uses what is on the device (five small uploads less in front of every run).
+    if (!c->plan_ready) {
     std::vector<uint64_t> hmask(size_t(n_slots) * 2 * mrow, 0);
     auto mask_row = [&](int slot, int which) { return hmask.data() + (size_t(slot) * 2 + which) * mrow; };
     std::vector<ScreenGroup> groups;
@@ -985,13 +994,18 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     CU(c, ensure(c->fracs, fracs.size()));
     CU(c, ensure(c->gcomps, gcomps.size()));
     CU(c, ensure(c->sdefs, sdefs.size()));
-    CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
-    CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
     CU(c, cudaMemcpyAsync(c->masks.p, hmask.data(), hmask.size() * 8, cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->groups.p, groups.data(), groups.size() * sizeof(ScreenGroup), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->fracs.p, fracs.data(), fracs.size() * sizeof(FracDef), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->gcomps.p, gcomps.data(), gcomps.size() * sizeof(GroupComp), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->sdefs.p, sdefs.data(), sdefs.size() * sizeof(SlotDef), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaStreamSynchronize(c->st));   // the host vectors die here (once per set of comparisons)
+    c->plan_groups = int(groups.size());
+    c->plan_max_frac = max_frac; c->plan_max_comp = max_comp; c->plan_max_slot = max_slot;
+    c->plan_ready = true;
+    }
+    CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
+    CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
     CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
 
     int launches = 0, count_launches = 0;
@@ -1080,10 +1094,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     tp.fracs = c->fracs.p;
     tp.gcomps = c->gcomps.p;
     tp.slots = c->sdefs.p;
-    tp.max_slot = max_slot;
-    tp.n_groups = int(groups.size());
-    tp.max_frac = max_frac;
-    tp.max_comp = max_comp;
+    tp.max_slot = c->plan_max_slot;
+    tp.n_groups = c->plan_groups;
+    tp.max_frac = c->plan_max_frac;
+    tp.max_comp = c->plan_max_comp;
     tp.n_rows = R;
     tp.n_comps = n_comps;
     tp.ratio_filter = ratio_filter;
