@@ -1006,7 +1006,8 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     }
     CU(c, ensure(c->counts, size_t(n_slots) * size_t(R)));
     CU(c, ensure(c->seg_count, size_t(n_comps) * 2));
-    CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
+    if (ratio_filter > 0.0)   // survivor counters + cursor of the filtered screen (dense runs have neither)
+        CU(c, cudaMemsetAsync(c->seg_count.p, 0, size_t(n_comps) * 2 * 8, c->st));
 
     int launches = 0, count_launches = 0;
     // ---- counting engine: explicit comparisons always go to K1; whole categories go to the int8
