@@ -45,7 +45,7 @@ void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int6
             const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64 * w));
             const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64 * w + 32));
             const uint64_t m1 = eq_mask64(a, b, one);
-            // (plain stores: 8-byte streaming stores into the two planes were measured 45% slower)
+            // (plain stores: 8-byte streaming stores into the two planes were measured 45% slower, 16-byte ones 15%)
             v[w] = m1;
             d[w] = m1 | eq_mask64(a, b, zero);
         }
