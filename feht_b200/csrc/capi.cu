@@ -845,6 +845,8 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     const int64_t R = marker_rows(c);
     if (n_comps > 65535) return fail(c, FEHT_E_INVALID, "more than 65535 comparisons in one run");
     if (R > int64_t(0x7fffffff)) return fail(c, FEHT_E_INVALID, "more than 2^31-1 marker rows in one context");
+    if (c->have_rank != 1 && c->row_base + R > int64_t(0x7fffffff))
+        return fail(c, FEHT_E_INVALID, "row_base + rows exceeds 2^31-1: pass name_rank (the default rank is the global row index)");
     if (bonferroni_n <= 0) bonferroni_n = R;
     c->seg_off.assign(size_t(n_comps) + 1, 0);
     c->n_surv = 0;
@@ -1103,6 +1105,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     tp.n_comps = n_comps;
     tp.ratio_filter = ratio_filter;
     tp.name_rank = c->have_rank == 1 ? c->rank.p : nullptr;
+    tp.row_base = c->row_base;
     tp.dense = ratio_filter <= 0.0 ? 1 : 0;
     if (tp.dense && c->have_rank == 1) {
         if (c->rank_is_perm == -1) {  // does name_rank enumerate [0, rows)?  (checked once per upload)

@@ -140,7 +140,8 @@ struct TestParams {
     int64_t n_rows;
     int n_comps;
     double ratio_filter;
-    const int32_t *name_rank; // may be null
+    const int32_t *name_rank; // may be null: the rank is then the global row index, row_base + row
+    int64_t row_base;
     // survivors: one 32-byte record each + the comparison index (a sort digit source)
     SurvivorRec *rec;
     int32_t *r_comp;

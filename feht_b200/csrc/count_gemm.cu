@@ -430,11 +430,9 @@ cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, 
     CUtensorMap tm_value, tm_valid;
     if (!make_plane_map(&tm_value, d_value, n_rows, W) || !make_plane_map(&tm_valid, d_valid, n_rows, W))
         return cudaErrorNotSupported;
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // per launch: the attribute belongs to the current device's copy of the kernel
         cudaError_t e = cudaFuncSetAttribute(count_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int n_tiles = int((n_rows + kTileRows - 1) / kTileRows);
     int gx = num_sms / n_passes;

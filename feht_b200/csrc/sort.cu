@@ -702,13 +702,11 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec,
         if (e != cudaSuccess) return e;
         ws.coop_clean_rows = num_sms;
     }
-    static const cudaError_t attr = [] {
-        cudaError_t r = cudaFuncSetAttribute(coop_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(kCoopDynSmem));
-        if (r != cudaSuccess) return r;
-        return cudaFuncSetAttribute(coop_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCoopDynSmem));
-    }();
-    if (attr != cudaSuccess) return attr;
+    // (set on every launch: the attribute belongs to the current device's copy of the function, and one process
+    // may drive several GPUs)
+    e = cudaFuncSetAttribute(multi ? coop_sort_kernel<true> : coop_sort_kernel<false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCoopDynSmem));
+    if (e != cudaSuccess) return e;
     void *args[] = {&a};
     const void *fn = multi ? reinterpret_cast<const void *>(coop_sort_kernel<true>)
                            : reinterpret_cast<const void *>(coop_sort_kernel<false>);

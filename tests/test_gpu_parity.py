@@ -858,3 +858,42 @@ def test_filtered_output_single_pass_and_capacity_overflow(ctx):
             for k in ("goa", "gob", "gta", "gtb"):
                 assert (got[k] == want[k][order]).all(), (rf, ci, k)
             assert p_close(got["p"], want["p"][order], np.zeros(len(order), bool)).all()
+
+
+def test_two_devices_in_one_process(cuda_lib):
+    """One host process driving a context per GPU (multi-GPU note): each device needs its own
+    kernel attributes (dynamic shared memory of the cooperative sort and the GEMM) -- rows split over devices 0 and
+    1, host k-way merge, against the oracle.  Skipped on a single-GPU box."""
+    import ctypes
+    try:
+        cudart = ctypes.CDLL("libcudart.so")
+    except OSError:
+        pytest.skip("libcudart not loadable by name")
+    n = ctypes.c_int(0)
+    cudart.cudaGetDeviceCount(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(202)
+    S, R = 900, 6000
+    cells = _random_chars(rng, R, S)
+    vos = rng.integers(0, 12, size=S).astype(np.int32)
+    g1, g2 = np.flatnonzero(vos == 3), np.flatnonzero(vos == 7)
+    ci = None
+    shards = []
+    for dev, (lo_, hi_) in enumerate(((0, 2500), (2500, R))):
+        with capi.Context(dev) as c:
+            c.set_samples(S)
+            c.set_row_base(lo_)
+            c.add_rows_chars(cells[lo_:hi_])
+            c.add_category(vos, 12)
+            c.set_count_engine(capi.ENGINE_GEMM)
+            c.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, R)
+            assert c.timings()["engine"] == capi.ENGINE_GEMM
+            if ci is None:
+                ci = next(i for i in range(c.num_comparisons) if c.comparison_info(i)[2:4] == (3, 7))
+            shards.append(c.fetch(ci))
+    want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=R)
+    order = oracle.filter_and_order(want["ratio"], None, 0.0)
+    out_s, out_i = capi.merge_sorted([s["ratio"] for s in shards], [s["name_rank"] for s in shards])
+    merged_rows = np.array([shards[s]["row"][i] for s, i in zip(out_s, out_i)])
+    assert (merged_rows == order).all()
