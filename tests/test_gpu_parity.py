@@ -897,3 +897,68 @@ def test_two_devices_in_one_process(cuda_lib):
     out_s, out_i = capi.merge_sorted([s["ratio"] for s in shards], [s["name_rank"] for s in shards])
     merged_rows = np.array([shards[s]["row"][i] for s, i in zip(out_s, out_i)])
     assert (merged_rows == order).all()
+
+
+def test_randomised_shapes_against_oracle(cuda_lib):
+    """Forty random jobs -- 1..300 samples, 1..500 rows, binary or SNP, explicit comparisons (disjoint, overlapping,
+    empty, single-column groups) or a whole category, either engine, with / without name ranks, both corrections,
+    dense and filtered -- each checked row by row against the oracle."""
+    import os
+    rng = np.random.default_rng(int(os.environ.get("FEHT_FUZZ_SEED", "20261020")))
+    for case in range(int(os.environ.get("FEHT_FUZZ_CASES", "40"))):
+        S = int(rng.choice([1, 2, 7, 63, 64, 65, 127, 128, 129, int(rng.integers(1, 301))]))
+        R = int(rng.choice([1, 2, 31, 32, 33, int(rng.integers(1, 501))]))
+        snp = bool(rng.random() < 0.3)
+        if snp:
+            alphabet = np.frombuffer(b"ACGTacgt-N", dtype=np.uint8)
+            sites = rng.choice(alphabet, size=(R, S))
+            cells = snp_expand(sites)
+        else:
+            sites = None
+            cells = _random_chars(rng, R, S, p_missing=float(rng.choice([0.0, 0.05, 0.5])))
+        n_marker = cells.shape[0]
+        use_cat = S >= 4 and rng.random() < 0.4
+        comps = []
+        if use_cat:
+            V = int(rng.integers(2, min(S, 9) + 1))
+            vos = rng.integers(-1 if rng.random() < 0.5 else 0, V, size=S).astype(np.int32)
+            groups = [np.flatnonzero(vos == v) for v in range(V)]
+            comps = [(groups[a], groups[b]) for a, b in itertools.combinations(range(V), 2)]
+            if V > 2:
+                comps += [(groups[v], np.flatnonzero((vos != v) & (vos >= 0))) for v in range(V)]
+        else:
+            for _ in range(int(rng.integers(1, 6))):
+                kind = rng.integers(0, 4)
+                cols = rng.permutation(S)
+                if kind == 0:
+                    h = max(1, S // 2)
+                    comps.append((cols[:h], cols[h:]))                       # second group may be empty (S = 1)
+                elif kind == 1:
+                    comps.append((cols[: max(1, S // 3)], cols[: max(1, S // 2)]))   # overlapping
+                elif kind == 2:
+                    comps.append((cols[:1], cols[-1:]))                      # single columns (the same one if S = 1)
+                else:
+                    comps.append((np.array([], dtype=np.int64), cols))       # empty first group
+        rank = rng.permutation(n_marker).astype(np.int32) if rng.random() < 0.5 else None
+        correction = int(rng.integers(0, 2))
+        rf = float(rng.choice([0.0, 0.0, 0.1, 0.34, 1.0]))
+        with capi.Context(0) as c:
+            c.set_samples(S)
+            if snp:
+                c.add_snp_chars(sites, rank)
+            else:
+                c.add_rows_chars(cells, rank)
+            if use_cat:
+                c.add_category(vos, V)
+                if not snp and rng.random() < 0.5:
+                    c.set_count_engine(capi.ENGINE_GEMM)
+            else:
+                for g1, g2 in comps:
+                    c.add_comparison(g1, g2)
+            assert c.num_comparisons == len(comps), case
+            c.run(correction, rf)
+            try:
+                _check_against_oracle(c, cells, comps, correction, rf, rank)
+            except AssertionError as e:
+                raise AssertionError(f"case {case}: S={S} R={R} snp={snp} cat={use_cat} rf={rf} corr={correction} "
+                                     f"rank={'yes' if rank is not None else 'no'}: {e}") from e
