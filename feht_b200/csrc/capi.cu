@@ -91,6 +91,7 @@ struct feht_ctx {
     DevBuf<unsigned char> gemm_passes;
     int gemm_n_passes = 0;
     bool gemm_ready = false;         // gemm_b / gemm_passes match the current categories
+    bool gemm_fp4 = false;           // ... and were baked for the 4-bit (kind::mxf4) flavour
     bool plan_ready = false;         // masks / groups / fracs / gcomps / sdefs on the device match the comparisons
     int plan_groups = 0, plan_max_frac = 0, plan_max_comp = 0, plan_max_slot = 0;
     int last_engine = 0;             // engine the last run counted categories with
@@ -231,6 +232,7 @@ constexpr size_t kHostPackBufWords = size_t(4) << 17;   // 4 MB of 64-bit words
 constexpr size_t kHostPackMinBytes = size_t(64) << 20;  // smaller uploads are not worth waking the cores for
 // AUTO engine: categories go to the GEMM from this many pair-slots on (measured crossover)
 constexpr int kGemmAutoMinSlots = 8;
+constexpr bool kGemmAutoFp4 = true;   // 1.37x the int8 flavour on C4 / C5, bit-identical counts (profiles/README.md r1j)
 
 // Upload `total` bytes from host in pieces chosen by `next_piece` and hand each staged piece to
 // `consume(dev_ptr, piece_index)` on the context stream; two staging buffers so that the copy of
@@ -774,7 +776,7 @@ extern "C" int feht_comparison_info(const feht_ctx *c, int64_t i, int32_t *kind,
 
 extern "C" int feht_set_count_engine(feht_ctx *c, int engine) {
     if (!c) return FEHT_E_INVALID;
-    if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM) return fail(c, FEHT_E_INVALID, "unknown engine");
+    if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM_FP4) return fail(c, FEHT_E_INVALID, "unknown engine");
     c->engine = engine;
     return FEHT_OK;
 }
@@ -787,6 +789,16 @@ extern "C" int feht_set_row_base(feht_ctx *c, int64_t row_base) {
 
 // ====================================================================================== run ==
 namespace {
+// which GEMM flavour FEHT_ENGINE_AUTO uses for categories; FEHT_GEMM=i8 / fp4 overrides
+bool gemm_auto_fp4() {
+    static const bool fp4 = [] {
+        const char *e = getenv("FEHT_GEMM");
+        if (e && std::string(e) == "i8") return false;
+        if (e && std::string(e) == "fp4") return true;
+        return kGemmAutoFp4;
+    }();
+    return fp4;
+}
 // FEHT_SORT=onesweep keeps the tile-per-CTA sort for every size (A/B measurements and tests of that path)
 bool sort_engine_allows_coop() {
     static const bool allow = [] {
@@ -1017,17 +1029,19 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     // tensor pipe to beat one masked popcount stream per value pair.
     const int n_cat_slots = n_slots - n_explicit;
     bool use_gemm = false;
-    if (c->engine == FEHT_ENGINE_GEMM) {
+    // FEHT_ENGINE_GEMM is the kind::i8 GEMM, FEHT_ENGINE_GEMM_FP4 the kind::mxf4 one; AUTO takes the faster (fp4)
+    const bool fp4 = c->engine == FEHT_ENGINE_GEMM_FP4 || (c->engine == FEHT_ENGINE_AUTO && gemm_auto_fp4());
+    if (c->engine == FEHT_ENGINE_GEMM || c->engine == FEHT_ENGINE_GEMM_FP4) {
         if (c->snp == 1) return fail(c, FEHT_E_INVALID, "the GEMM counting engine handles binary rows only");
         if (n_cat_slots == 0) return fail(c, FEHT_E_INVALID, "the GEMM counting engine needs a category (feht_add_category)");
         use_gemm = true;
     } else if (c->engine == FEHT_ENGINE_AUTO) {
         use_gemm = c->snp != 1 && n_cat_slots >= kGemmAutoMinSlots;
     }
-    if (use_gemm && !c->gemm_ready) {
+    if (use_gemm && (!c->gemm_ready || c->gemm_fp4 != fp4)) {
         const int per_pass = gemm_max_pairs_per_pass();
         const int n_passes = (n_cat_slots + per_pass - 1) / per_pass;
-        const int n_stages = gemm_stage_count(c->S);
+        const int n_stages = gemm_bblock_count(c->S, fp4);   // B blocks per pass
         // GEMM column gc = 2 * (slot - n_explicit) + sel  ->  list of samples with a 1
         std::vector<std::vector<int32_t>> cols(size_t(n_cat_slots) * 2);
         for (size_t k = 0; k < c->cats.size(); ++k) {
@@ -1055,7 +1069,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
             const int pairs = std::min(per_pass, n_cat_slots - p * per_pass);
             std::vector<std::vector<int32_t>> pc(cols.begin() + size_t(p) * per_pass * 2,
                                                  cols.begin() + size_t(p) * per_pass * 2 + size_t(pairs) * 2);
-            gemm_bake_b(pc, pad[size_t(p)], c->S, hb.data() + off);
+            gemm_bake_b(pc, pad[size_t(p)], c->S, fp4, hb.data() + off);
             off += size_t(n_stages) * size_t(pad[size_t(p)]) * 128;
         }
         CU(c, ensure(c->gemm_b, total));
@@ -1064,12 +1078,16 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         CU(c, cudaMemcpyAsync(c->gemm_passes.p, hpass.data(), hpass.size(), cudaMemcpyHostToDevice, c->st));
         CU(c, cudaStreamSynchronize(c->st));  // the host vectors die here
         c->gemm_n_passes = n_passes;
+        c->gemm_fp4 = fp4;
         c->gemm_ready = true;
     }
-    c->last_engine = use_gemm ? FEHT_ENGINE_GEMM : FEHT_ENGINE_POPC;
+    c->last_engine = use_gemm ? (fp4 ? FEHT_ENGINE_GEMM_FP4 : FEHT_ENGINE_GEMM) : FEHT_ENGINE_POPC;
 
     CU(c, cudaEventRecord(ev[0], c->st));
     const int n_popc_slots = use_gemm ? n_explicit : n_scanned;
+    if (n_popc_slots > 0 && size_t(2) * plan.w4pad * 16 > size_t(200) * 1024)
+        return fail(c, FEHT_E_INVALID, "%lld samples are too many for the popcount engine (a comparison's two masks must fit "
+                    "in shared memory, about 800k samples); use feht_add_category with the GEMM engine", (long long)c->S);
     if (c->snp == 1)
         CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
                                     c->masks.p, n_popc_slots, c->counts.p, c->num_sms, c->st, &count_launches));
@@ -1078,7 +1096,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
                                 c->counts.p, c->num_sms, c->st, &count_launches));
     if (use_gemm) {
         CU(c, launch_count_gemm(c->plane[0], c->plane[1], c->n_units, c->W, c->S, c->gemm_b.p,
-                                c->gemm_passes.p, c->gemm_n_passes, c->counts.p, c->num_sms, c->st,
+                                c->gemm_passes.p, c->gemm_n_passes, c->gemm_fp4, c->counts.p, c->num_sms, c->st,
                                 &count_launches));
     } else {
         for (size_t k = 0; k < c->cats.size(); ++k)

@@ -105,14 +105,15 @@ cudaError_t launch_sum_slots(int4 *d_counts, int64_t n_rows, int slot0, int n, i
 
 // count_gemm.cu  (K2)
 int gemm_stage_count(int64_t S);
+int gemm_bblock_count(int64_t S, bool fp4);
 size_t gemm_pass_desc_bytes();
 int gemm_max_pairs_per_pass();
 // columns[c] = samples carrying a 1 in GEMM column c of one pass; out: [n_stages][n_pad][128] bytes
-void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, uint8_t *out);
+void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, bool fp4, uint8_t *out);
 void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_offset);
 // counts for pair-slots [slot_base, ...) of every pass, same int4 layout as K1
 cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
-                              int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
+                              int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes, bool fp4,
                               int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
 
 // fet.cu  (K3)

@@ -63,7 +63,7 @@ constexpr int kTmemABase = 256;       // + buf * 128 + (mt * 2 + plane) * 32
 constexpr int kSmemPlanes = 0;                                     // [2 buf][2 plane][32 KiB]
 constexpr int kSmemB = kSmemPlanes + 4 * kPlaneTileBytes;          // [kBStages][8 KiB]
 constexpr int kSmemBars = kSmemB + kBStages * kBStageBytes;        // mbarriers
-constexpr int kNumBars = 2 + 2 + kBStages * 2 + 2 + 2 + 2;
+constexpr int kNumBars = 2 + 2 + kBStages * 2 + 3 + 3 + 2;
 constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16 + 1024;               // + slack for manual alignment
 
@@ -130,6 +130,18 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same contraction with 4-bit operands: kind::mxf4 (e2m1 x e2m1, one UE8M0 scale per 32 K elements, here all
+// 2^0), M = 128, K = 64, FP32 accumulators -- exact below 2^24 samples.  Half the operand bytes per sample, and
+// K2 is bound by operand bytes (profiles/README.md r1g), so a stage of 128 samples needs 8 MMAs instead of 16.
+__device__ __forceinline__ void mma_fp4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t sf_tmem, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%4], [%4], p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(sf_tmem), "r"(accumulate)
+        : "memory");
+}
 // 16 consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -156,6 +168,22 @@ __device__ __forceinline__ void expand_store(uint32_t taddr, uint32_t w) {
     tmem_st8(taddr, y);
 }
 
+// FP4 flavour: 32 calls -> 4 TMEM columns of 8 e2m1 nibbles.  Column j, nibble t holds call 4*t + j as the nibble
+// 1 << j for j < 3 (e2m1 0.5, 1.0, 2.0) and, shifted down, 1 (0.5) for j = 3 (bit 3 of a nibble is the sign);
+// gemm_bake_b() stores the reciprocal (2.0, 1.0, 0.5, 2.0) at the matching K position, so every hit adds 1.0.
+__device__ __forceinline__ void expand4_fp4(uint32_t (&y)[8], int at, uint32_t w) {
+    y[at + 0] = w & 0x11111111u;
+    y[at + 1] = w & 0x22222222u;
+    y[at + 2] = w & 0x44444444u;
+    y[at + 3] = (w >> 3) & 0x11111111u;
+}
+__device__ __forceinline__ void expand_store_fp4(uint32_t taddr, uint32_t w0, uint32_t w1) {
+    uint32_t y[8];
+    expand4_fp4(y, 0, w0);
+    expand4_fp4(y, 4, w1);
+    tmem_st8(taddr, y);
+}
+
 // UMMA shared-memory descriptor: K-major, 128B swizzle, 8-row core-matrix groups 1024 B apart
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -168,6 +196,10 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 }
 
 // ------------------------------------------------------------------------------------ the kernel
+// FP4 = false: kind::i8, one B block (128 samples) per A stage.  FP4 = true: kind::mxf4, A stages still hold 128
+// samples (16 B of a plane row -> 16 TMEM columns per accumulator), one B block (a full 128-byte swizzle row = 256
+// e2m1 values) serves two consecutive A stages.
+template <bool FP4>
 __global__ void __launch_bounds__(kThreads, 1)
 count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tm_valid,
                   const uint8_t *__restrict__ bmat, const GemmPass *__restrict__ passes, int n_stages,
@@ -182,8 +214,8 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
     const uint32_t b_full = bars + 4 * 8;             // [kBStages]
     const uint32_t b_empty = b_full + kBStages * 8;   // [kBStages]
     const uint32_t ta_full = b_empty + kBStages * 8;  // [2]  A stage written to TMEM
-    const uint32_t ta_empty = ta_full + 2 * 8;        // [2]  MMAs of the stage retired
-    const uint32_t acc_full = ta_empty + 2 * 8;       // accumulators complete
+    const uint32_t ta_empty = ta_full + 3 * 8;        // [2..3]  MMAs of the stage retired
+    const uint32_t acc_full = ta_empty + 3 * 8;       // accumulators complete
     const uint32_t acc_empty = acc_full + 8;          // epilogue drained TMEM
     volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(base_ptr + kSmemTmemPtr);
 
@@ -196,6 +228,8 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
         for (int i = 0; i < 2; ++i) {
             mbar_init(a_full + i * 8, 1);
             mbar_init(a_empty + i * 8, kExpandWarps);
+        }
+        for (int i = 0; i < 3; ++i) {
             mbar_init(ta_full + i * 8, kExpandWarps);
             mbar_init(ta_empty + i * 8, 1);
         }
@@ -218,6 +252,11 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int n_chunks = (n_stages + kStagesPerChunk - 1) / kStagesPerChunk;
+    constexpr int kAPerB = FP4 ? 2 : 1;          // A stages served by one B block
+    constexpr int kAColsQ = FP4 ? 16 : 32;       // TMEM columns of one accumulator's A operand per stage
+    constexpr int kABuf = 4 * kAColsQ;           // TMEM columns of one A stage buffer
+    constexpr int kABufs = FP4 ? 3 : 2;          // A stage buffers in TMEM: 256 + 3 * 64 + 8 / 256 + 2 * 128 columns
+    constexpr int kTmemSF = kTmemABase + kABufs * kABuf;   // FP4: eight columns of unit scale factors (0x7F = 2^0)
 
     if (warp < kExpandWarps) {
         // =============================================== expanders + epilogue: thread = marker row
@@ -227,6 +266,14 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
         const uint32_t row_off = uint32_t(r) * kChunkBytes;
         const uint32_t sw = uint32_t(r & 7);
         uint32_t chunk_ctr = 0, stage_ctr = 0, tile_ctr = 0;
+        if (FP4 && warp < 4) {
+            // every byte of these columns is the UE8M0 code of 1.0, whichever of them an MMA picks as its scales
+            uint32_t one[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) one[j] = 0x7F7F7F7Fu;
+            tmem_st8(tmem_base + lane_addr + kTmemSF, one);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
             for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
                 const uint32_t cb = chunk_ctr & 1;
@@ -238,18 +285,25 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
                     const uint32_t phys = (uint32_t(st) ^ sw) << 4;  // TMA 128B swizzle: chunk ^= row % 8
                     const uint4 v = *reinterpret_cast<const uint4 *>(pv + phys);
                     const uint4 d = *reinterpret_cast<const uint4 *>(pd + phys);
-                    const uint32_t tb = stage_ctr & 1;
-                    mbar_wait(ta_empty + tb * 8, ((stage_ctr >> 1) & 1) ^ 1);
+                    const uint32_t tb = stage_ctr % kABufs;
+                    mbar_wait(ta_empty + tb * 8, ((stage_ctr / kABufs) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t ta = tmem_base + lane_addr + kTmemABase + tb * 128 + (mt * 2) * 32;
-                    expand_store(ta + 0, v.x);
-                    expand_store(ta + 8, v.y);
-                    expand_store(ta + 16, v.z);
-                    expand_store(ta + 24, v.w);
-                    expand_store(ta + 32 + 0, d.x);
-                    expand_store(ta + 32 + 8, d.y);
-                    expand_store(ta + 32 + 16, d.z);
-                    expand_store(ta + 32 + 24, d.w);
+                    const uint32_t ta = tmem_base + lane_addr + kTmemABase + tb * kABuf + (mt * 2) * kAColsQ;
+                    if (FP4) {
+                        expand_store_fp4(ta + 0, v.x, v.y);
+                        expand_store_fp4(ta + 8, v.z, v.w);
+                        expand_store_fp4(ta + 16 + 0, d.x, d.y);
+                        expand_store_fp4(ta + 16 + 8, d.z, d.w);
+                    } else {
+                        expand_store(ta + 0, v.x);
+                        expand_store(ta + 8, v.y);
+                        expand_store(ta + 16, v.z);
+                        expand_store(ta + 24, v.w);
+                        expand_store(ta + 32 + 0, d.x);
+                        expand_store(ta + 32 + 8, d.y);
+                        expand_store(ta + 32 + 16, d.z);
+                        expand_store(ta + 32 + 24, d.w);
+                    }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
@@ -273,10 +327,12 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int pair = (c0 >> 1) + j;
-                        if (pair < pass.n_pairs)   // every hit added 128 (expand_store / gemm_bake_b)
+                        if (pair < pass.n_pairs) {
+                            // i8: every hit added 128 (expand_store / gemm_bake_b); FP4: 1.0 in FP32
+                            auto cnt = [](uint32_t x) { return FP4 ? __float2int_rn(__uint_as_float(x)) : int(x >> 7); };
                             counts[size_t(pass.slot_base + pair) * size_t(n_rows) + size_t(row)] =
-                                make_int4(int(P[2 * j] >> 7), int(N[2 * j] >> 7), int(P[2 * j + 1] >> 7),
-                                          int(N[2 * j + 1] >> 7));
+                                make_int4(cnt(P[2 * j]), cnt(N[2 * j]), cnt(P[2 * j + 1]), cnt(N[2 * j + 1]));
+                        }
                     }
                 }
             }
@@ -306,7 +362,8 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
             uint32_t stage_ctr = 0;
             const uint8_t *bsrc = bmat + pass.b_offset;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                const int n_bblocks = (n_stages + kAPerB - 1) / kAPerB;
+                for (int s = 0; s < n_bblocks; ++s, ++stage_ctr) {
                     const uint32_t bs = stage_ctr % kBStages;
                     mbar_wait(b_empty + bs * 8, ((stage_ctr / kBStages) & 1) ^ 1);
                     mbar_expect_tx(b_full + bs * 8, b_bytes);
@@ -318,30 +375,49 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
     } else {
         // =============================================== MMA issuer
         if (lane == 0) {
-            // instruction descriptor: D s32, A/B unsigned 8-bit, both K-major, N = n_pad, M = 128
-            const uint32_t idesc = (2u << 4) | (uint32_t(n_pad >> 3) << 17) | (uint32_t(128 >> 4) << 24);
-            uint32_t stage_ctr = 0, tile_ctr = 0;
+            // instruction descriptor, N = n_pad, M = 128, both operands K-major.  i8: D s32, A/B unsigned 8-bit.
+            // mxf4 (block-scaled layout): A/B e2m1 (format 1), UE8M0 scales, scale ids 0, K = 64.
+            const uint32_t idesc = FP4 ? ((1u << 7) | (1u << 10) | (uint32_t(n_pad >> 3) << 17) | (1u << 23) |
+                                          (uint32_t(128 >> 4) << 24))
+                                       : ((2u << 4) | (uint32_t(n_pad >> 3) << 17) | (uint32_t(128 >> 4) << 24));
+            uint32_t stage_ctr = 0, bblock_ctr = 0, tile_ctr = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
                 mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
                 tc_fence_after();
                 for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
-                    const uint32_t tb = stage_ctr & 1;
-                    const uint32_t bs = stage_ctr % kBStages;
-                    mbar_wait(ta_full + tb * 8, (stage_ctr >> 1) & 1);
-                    mbar_wait(b_full + bs * 8, (stage_ctr / kBStages) & 1);
+                    const uint32_t tb = stage_ctr % kABufs;
+                    const int half = s % kAPerB;                 // which part of the B block this A stage uses
+                    const uint32_t bs = bblock_ctr % kBStages;
+                    mbar_wait(ta_full + tb * 8, (stage_ctr / kABufs) & 1);
+                    if (half == 0) mbar_wait(b_full + bs * 8, (bblock_ctr / kBStages) & 1);
                     tc_fence_after();
                     const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kBStageBytes);
+                    if (FP4) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
+                        for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {  // q = mt * 2 + plane
-                            mma_i8_ts(tmem_base + kTmemAccBase + q * 64,
-                                      tmem_base + kTmemABase + tb * 128 + q * 32 + ks * 8,
-                                      bdesc + uint64_t(ks * 2), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                            for (int q = 0; q < 4; ++q)   // q = mt * 2 + plane
+                                mma_fp4_ts(tmem_base + kTmemAccBase + q * 64,
+                                           tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
+                                           bdesc + uint64_t((half * 2 + ks) * 2), idesc, tmem_base + kTmemSF,
+                                           (s > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {  // q = mt * 2 + plane
+                                mma_i8_ts(tmem_base + kTmemAccBase + q * 64,
+                                          tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
+                                          bdesc + uint64_t(ks * 2), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     tc_commit(ta_empty + tb * 8);
-                    tc_commit(b_empty + bs * 8);
+                    if (half == kAPerB - 1 || s == n_stages - 1) {
+                        tc_commit(b_empty + bs * 8);
+                        ++bblock_ctr;
+                    }
                 }
                 tc_commit(acc_full);
             }
@@ -391,25 +467,42 @@ bool make_plane_map(CUtensorMap *map, const uint64_t *plane, int64_t n_rows, int
 }  // namespace
 
 int gemm_stage_count(int64_t S) { return int((S + kStageSamples - 1) / kStageSamples); }
+// B blocks per pass: one per A stage (i8) or one per two A stages (fp4: a 128-byte row holds 256 e2m1 values)
+int gemm_bblock_count(int64_t S, bool fp4) { return fp4 ? (gemm_stage_count(S) + 1) / 2 : gemm_stage_count(S); }
 size_t gemm_pass_desc_bytes() { return sizeof(GemmPass); }
 int gemm_max_pairs_per_pass() { return kNMax / 2; }
 
 // One pass = up to 32 consecutive pair-slots (64 value columns).  columns[c] lists, for GEMM column c
 // of the pass, which samples carry a 1 (built by capi.cu from the categories).  Writes the baked B
-// blocks [n_stages][n_pad][128] (128B-swizzled, K permuted to the expander's order) at `out`.
-void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, uint8_t *out) {
-    const int n_stages = gemm_stage_count(S);
-    std::memset(out, 0, size_t(n_stages) * size_t(n_pad) * 128);
+// blocks [n_bblocks][n_pad][128] (128B-swizzled, K permuted to the expander's order) at `out`.
+void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, bool fp4, uint8_t *out) {
+    const int n_blocks = gemm_bblock_count(S, fp4);
+    std::memset(out, 0, size_t(n_blocks) * size_t(n_pad) * 128);
     for (size_t n = 0; n < columns.size(); ++n) {
         for (int32_t s : columns[n]) {
-            const int64_t g = s / kStageSamples;       // stage
-            const int w = int(s % kStageSamples);
-            const int i = w >> 5, bit = w & 31;        // word of the 16-byte stage row, bit in the word
-            const int b = bit >> 3, j = bit & 7;       // expander: column j, byte b holds call 8*b + j
-            const int kk = 32 * i + 4 * j + b;         // K position inside the stage
-            const size_t off = size_t(g) * size_t(n_pad) * 128 + n * 128 +
-                               size_t((((kk >> 4) ^ int(n & 7)) << 4) + (kk & 15));
-            out[off] = uint8_t(1u << (7 - j));
+            if (!fp4) {
+                const int64_t g = s / kStageSamples;       // stage
+                const int w = int(s % kStageSamples);
+                const int i = w >> 5, bit = w & 31;        // word of the 16-byte stage row, bit in the word
+                const int b = bit >> 3, j = bit & 7;       // expander: column j, byte b holds call 8*b + j
+                const int kk = 32 * i + 4 * j + b;         // K position inside the stage
+                const size_t off = size_t(g) * size_t(n_pad) * 128 + n * 128 +
+                                   size_t((((kk >> 4) ^ int(n & 7)) << 4) + (kk & 15));
+                out[off] = uint8_t(1u << (7 - j));
+            } else {
+                const int64_t g = s / (2 * kStageSamples);               // B block = two A stages
+                const int half = int((s / kStageSamples) & 1);
+                const int w = int(s % kStageSamples);
+                const int i = w >> 5, bit = w & 31;
+                const int j = bit & 3, t = bit >> 2;                     // expand4_fp4: column 4*i + j, nibble t
+                const int e = half * 128 + (4 * i + j) * 8 + t;          // e2m1 element inside the 256-value row
+                const int kb = e >> 1;
+                const size_t off = size_t(g) * size_t(n_pad) * 128 + n * 128 +
+                                   size_t((((kb >> 4) ^ int(n & 7)) << 4) + (kb & 15));
+                // the expander leaves 0.5, 1.0, 2.0, 0.5 for j = 0..3: B holds 2.0, 1.0, 0.5, 2.0 (e2m1 0x4, 0x2, 0x1, 0x4)
+                static const uint8_t recip[4] = {0x4, 0x2, 0x1, 0x4};
+                out[off] |= uint8_t(recip[j] << (4 * (e & 1)));
+            }
         }
     }
 }
@@ -424,14 +517,15 @@ void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_
 }
 
 cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
-                              int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
+                              int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes, bool fp4,
                               int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
     if (n_rows == 0 || n_passes == 0) return cudaSuccess;
     CUtensorMap tm_value, tm_valid;
     if (!make_plane_map(&tm_value, d_value, n_rows, W) || !make_plane_map(&tm_valid, d_valid, n_rows, W))
         return cudaErrorNotSupported;
     {   // per launch: the attribute belongs to the current device's copy of the kernel
-        cudaError_t e = cudaFuncSetAttribute(count_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+        cudaError_t e = fp4 ? cudaFuncSetAttribute(count_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal)
+                            : cudaFuncSetAttribute(count_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
         if (e != cudaSuccess) return e;
     }
     const int n_tiles = int((n_rows + kTileRows - 1) / kTileRows);
@@ -439,9 +533,14 @@ cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, 
     if (gx < 1) gx = 1;
     if (gx > n_tiles) gx = n_tiles;
     // every pass gets its own set of persistent CTAs; with one pass this is one CTA per SM
-    count_gemm_kernel<<<dim3(unsigned(gx), unsigned(n_passes)), kThreads, kSmemTotal, st>>>(
-        tm_value, tm_valid, d_bmat, static_cast<const GemmPass *>(d_passes), gemm_stage_count(S), n_rows,
-        n_tiles, d_counts);
+    if (fp4)
+        count_gemm_kernel<true><<<dim3(unsigned(gx), unsigned(n_passes)), kThreads, kSmemTotal, st>>>(
+            tm_value, tm_valid, d_bmat, static_cast<const GemmPass *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
+            d_counts);
+    else
+        count_gemm_kernel<false><<<dim3(unsigned(gx), unsigned(n_passes)), kThreads, kSmemTotal, st>>>(
+            tm_value, tm_valid, d_bmat, static_cast<const GemmPass *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
+            d_counts);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -370,9 +370,13 @@ cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p
     const uint4 *b = reinterpret_cast<const uint4 *>(p1);
     const uint4 *c = reinterpret_cast<const uint4 *>(p2);
     constexpr int B = kBatch<SNP>;
+    // The masks of a pass live in shared memory (2 x w4pad x 16 B per pair-slot): ~900k samples is the most one
+    // pair-slot can have; whole categories of wider matrices go to the GEMM engine, which streams its one-hot tiles.
+    constexpr size_t kSmemMax = 200 * 1024;
+    if (size_t(2) * plan.w4pad * 16 > kSmemMax) return cudaErrorInvalidConfiguration;
     // batches of B pair-slots share one read of the planes; the remainder goes one at a time
     int done = 0;
-    const int nb = n_slots / B;
+    const int nb = size_t(B) * 2 * plan.w4pad * 16 <= kSmemMax ? n_slots / B : 0;
     if (nb > 0) {
         const size_t smem = size_t(B) * 2 * plan.w4pad * 16;
         cudaError_t e = dispatch<B, SNP>(plan.ncol, want, nb, smem, num_sms, st, a, b, c, n, w4, plan,

@@ -161,8 +161,9 @@ int64_t feht_num_comparisons(const feht_ctx *ctx);
 int     feht_comparison_info(const feht_ctx *ctx, int64_t c, int32_t *kind, int32_t *category,
                              int32_t *v1, int32_t *v2);
 
-/* Counting engine: 0 auto, 1 popcount scan (K1), 2 int8 tcgen05 GEMM (K2; categories only). */
-enum { FEHT_ENGINE_AUTO = 0, FEHT_ENGINE_POPC = 1, FEHT_ENGINE_GEMM = 2 };
+/* Counting engine: 0 auto, 1 popcount scan (K1), 2 int8 tcgen05 GEMM (K2; categories only), 3 the same GEMM
+ * with 4-bit operands (tcgen05 kind::mxf4, unit scales, FP32 accumulation: exact, half the operand bytes). */
+enum { FEHT_ENGINE_AUTO = 0, FEHT_ENGINE_POPC = 1, FEHT_ENGINE_GEMM = 2, FEHT_ENGINE_GEMM_FP4 = 3 };
 int feht_set_count_engine(feht_ctx *ctx, int engine);
 
 /* ---------------------------------------------------------------- run ---- */
@@ -211,7 +212,7 @@ int feht_set_row_base(feht_ctx *ctx, int64_t row_base);
 /* Device-side milliseconds of the last feht_run, by stage (CUDA events on the run's stream):
  * out[0] count, out[1] test+correct+filter, out[2] order, out[3] total, out[4] launches (count),
  * out[5] count-kernel launches, out[6] algorithmic bytes read by the count stage,
- * out[7] engine that counted the categories (FEHT_ENGINE_POPC or FEHT_ENGINE_GEMM). */
+ * out[7] engine that counted the categories (FEHT_ENGINE_POPC, FEHT_ENGINE_GEMM or FEHT_ENGINE_GEMM_FP4). */
 int feht_last_timings(const feht_ctx *ctx, double *out, int n);
 /* Sums over every run since the last reset (waits for the enqueued runs): out[0] runs, out[1] count ms,
  * out[2] test ms, out[3] order ms, out[4] total ms, out[5] kernel launches, out[6] count-kernel launches. */

@@ -313,8 +313,9 @@ def test_category_api_equals_explicit_comparisons(ctx):
 
 
 @pytest.mark.parametrize("n_samples,n_values", [(130, 3), (1000, 7), (2600, 70), (5000, 50)])
-def test_gemm_engine_counts_equal_oracle(ctx, n_samples, n_values):
-    """K2 (int8 tcgen05 GEMM) against the oracle: same pair / one-vs-rest tables, bit-exact, for one and
+@pytest.mark.parametrize("engine", [capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4])
+def test_gemm_engine_counts_equal_oracle(ctx, n_samples, n_values, engine):
+    """K2 (tcgen05 GEMM, kind::i8 and kind::mxf4 flavours) against the oracle: same pair / one-vs-rest tables, bit-exact, for one and
     for several passes (70 values = 36 pair-slots > 32 per pass), with an explicit comparison mixed in
     (K1 counts that one) and samples that lack the category (-1)."""
     rng = np.random.default_rng(400 + n_values)
@@ -334,9 +335,9 @@ def test_gemm_engine_counts_equal_oracle(ctx, n_samples, n_values):
     for v in range(n_values):
         comps.append((np.flatnonzero(vos == v), np.flatnonzero((vos >= 0) & (vos != v))))
     assert ctx.num_comparisons == len(comps)
-    ctx.set_count_engine(capi.ENGINE_GEMM)
+    ctx.set_count_engine(engine)
     ctx.run(capi.CORRECTION_BONFERRONI, 0.4)
-    assert ctx.timings()["engine"] == capi.ENGINE_GEMM
+    assert ctx.timings()["engine"] == engine
     # every comparison for the small cases, a spread of them for the 2486 / 1276-comparison cases
     pick = range(len(comps)) if len(comps) < 60 else sorted(set(rng.integers(0, len(comps), 60)) | {0, 1, len(comps) - 1})
     for ci in pick:
@@ -362,16 +363,16 @@ def test_gemm_and_popcount_engines_agree_on_two_categories(ctx):
     ctx.add_category(rng.integers(0, 5, size=n_samples).astype(np.int32), 5)
     ctx.add_category(rng.integers(-1, 12, size=n_samples).astype(np.int32), 12)
     res = {}
-    for eng in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_AUTO):
+    for eng in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_AUTO):
         ctx.set_count_engine(eng)
         ctx.run(capi.CORRECTION_NONE, 0.0)
         res[eng] = [ctx.fetch(ci) for ci in range(ctx.num_comparisons)]
-    assert ctx.timings()["engine"] == capi.ENGINE_GEMM       # AUTO: 3+1+6+1 = 11 pair-slots >= 8
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM_FP4   # AUTO: 3+1+6+1 = 11 pair-slots >= 8 -> the 4-bit GEMM
     for ci in range(ctx.num_comparisons):
         for k in ("row", "goa", "gob", "gta", "gtb", "p", "ratio"):
-            a, b, c = (res[e][ci][k] for e in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_AUTO))
+            a, b, c, d = (res[e][ci][k] for e in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_AUTO))
             same = (a == b) | ((a != a) & (b != b))
-            assert same.all() and ((b == c) | ((b != b) & (c != c))).all(), (ci, k)
+            assert same.all() and ((b == c) | ((b != b) & (c != c))).all() and ((c == d) | ((c != c) & (d != d))).all(), (ci, k)
 
 
 def test_gemm_engine_rejects_snp_and_explicit_only(ctx):
@@ -667,7 +668,7 @@ def test_config4_category_gemm_full_size(ctx):
     assert ctx.num_comparisons == V * (V - 1) // 2 + V
     ctx.run(capi.CORRECTION_BONFERRONI, 0.5)
     t = ctx.timings()
-    assert t["engine"] == capi.ENGINE_GEMM
+    assert t["engine"] == capi.ENGINE_GEMM_FP4              # what AUTO picks for a 50-value category
     groups = [np.flatnonzero(vos == v) for v in range(V)]
     # comparison indices: pair (i,j) -> i*V - i(i+1)/2 + j-i-1 ; one-vs-rest v -> V(V-1)/2 + v
     pidx = lambda i, j: i * V - i * (i + 1) // 2 + (j - i - 1)
@@ -685,13 +686,13 @@ def test_config4_category_gemm_full_size(ctx):
     ctx.clear_rows()
     ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, 0, 200_000)
     res = {}
-    for eng in (capi.ENGINE_GEMM, capi.ENGINE_POPC):
+    for eng in (capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_POPC):
         ctx.set_count_engine(eng)
         ctx.run(capi.CORRECTION_BONFERRONI, 0.5, capi.SORT_ABS_RATIO_DESC, R)
         res[eng] = [ctx.fetch(ci) for ci in comps]
-    for a, b in zip(res[capi.ENGINE_GEMM], res[capi.ENGINE_POPC]):
+    for a, b, c in zip(res[capi.ENGINE_GEMM], res[capi.ENGINE_POPC], res[capi.ENGINE_GEMM_FP4]):
         for k in ("row", "goa", "gob", "gta", "gtb", "ratio", "p"):
-            assert (a[k] == b[k]).all(), k
+            assert (a[k] == b[k]).all() and (a[k] == c[k]).all(), k
 
 
 def test_config5_shard_four_categories(ctx):
@@ -709,7 +710,7 @@ def test_config5_shard_four_categories(ctx):
         ctx.add_category(vos, v)
     assert ctx.num_comparisons == 1 + 15 + 55 + 210
     ctx.run(capi.CORRECTION_BONFERRONI, 0.8, capi.SORT_ABS_RATIO_DESC, TOTAL)
-    assert ctx.timings()["engine"] == capi.ENGINE_GEMM
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM_FP4
     assert ctx.result_total() == 0                       # random categories: no |ratio| >= 0.8
     ctx.run(capi.CORRECTION_BONFERRONI, 0.015, capi.SORT_ABS_RATIO_DESC, TOTAL)
     # comparison 0 = the 2-value category; 1 + 15 + 3 = pair (0,3)... of the 10-value one
@@ -950,8 +951,8 @@ def test_randomised_shapes_against_oracle(cuda_lib):
                 c.add_rows_chars(cells, rank)
             if use_cat:
                 c.add_category(vos, V)
-                if not snp and rng.random() < 0.5:
-                    c.set_count_engine(capi.ENGINE_GEMM)
+                if not snp and rng.random() < 0.6:
+                    c.set_count_engine(int(rng.choice([capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4])))
             else:
                 for g1, g2 in comps:
                     c.add_comparison(g1, g2)
