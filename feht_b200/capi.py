@@ -31,7 +31,7 @@ EXPORTS = [
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
-    "feht_set_host_threads", "feht_last_upload_host_rows", "feht_set_fet_mode",
+    "feht_set_host_threads", "feht_last_upload_host_rows", "feht_set_fet_mode", "feht_pack_chars_host",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.feht_set_count_engine.argtypes = [vp, C.c_int]
     L.feht_run.argtypes = [vp, C.c_int, f64, C.c_int, i64]
     L.feht_set_host_threads.argtypes = [vp, C.c_int]
+    L.feht_pack_chars_host.argtypes = [vp, vp, i64, i64, C.c_int, i64, vp, vp, vp, C.c_int]
     L.feht_set_fet_mode.argtypes = [vp, C.c_int]
     L.feht_last_upload_host_rows.argtypes = [vp]
     L.feht_last_upload_host_rows.restype = i64
@@ -180,6 +181,20 @@ def host_show_double(x: float) -> str:
     if n < 0:
         raise FehtHostError("show buffer too small")
     return buf.value.decode()
+
+
+def pack_chars_host(rows, n_samples: int, snp: bool = False, n_threads: int = 0):
+    """feht_pack_chars_host: rows (2-D uint8 or list of bytes) -> (value, valid) or (hi, lo, valid) uint64 planes."""
+    flat, off = Context._rows_to_flat(rows)
+    n = len(off) - 1
+    w = (n_samples + 63) // 64
+    planes = [np.zeros((n, w), dtype=np.uint64) for _ in range(3 if snp else 2)]
+    p2 = _ptr(planes[2]) if snp else None
+    rc = lib().feht_pack_chars_host(_ptr(flat), _ptr(off), n, n_samples, 1 if snp else 0, w, _ptr(planes[0]),
+                                    _ptr(planes[1]), p2, n_threads)
+    if rc != 0:
+        raise FehtError(rc, "feht_pack_chars_host")
+    return tuple(planes)
 
 
 def version() -> str:

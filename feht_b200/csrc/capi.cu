@@ -578,6 +578,40 @@ extern "C" int feht_set_fet_mode(feht_ctx *c, int mode) {
     return FEHT_OK;
 }
 
+// The wire format on its own: a host that keeps the packed copy (or wants the upload off its critical path) packs
+// with its cores and calls feht_add_rows_packed / feht_add_snp_packed later.  No GPU involved.
+extern "C" int feht_pack_chars_host(const uint8_t *chars, const int64_t *row_offsets, int64_t n_rows, int64_t n_samples,
+                                    int snp_mode, int64_t row_stride_words, uint64_t *plane0, uint64_t *plane1,
+                                    uint64_t *plane2, int n_threads) {
+    if (n_rows < 0 || n_samples <= 0 || row_stride_words < (n_samples + 63) / 64) return FEHT_E_INVALID;
+    if (n_rows == 0) return FEHT_OK;
+    if (!chars || !row_offsets || !plane0 || !plane1 || (snp_mode && !plane2)) return FEHT_E_INVALID;
+    for (int64_t r = 0; r < n_rows; ++r)
+        if (row_offsets[r + 1] < row_offsets[r]) return FEHT_E_INVALID;
+    int threads = n_threads > 0 ? n_threads : int(std::thread::hardware_concurrency());
+    threads = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 256), n_rows)));
+    const bool simd = host_pack_available();
+    auto work = [&](int64_t r0, int64_t r1) {
+        const size_t o = size_t(r0) * size_t(row_stride_words);
+        if (snp_mode) {   // planes in the order feht_add_snp_packed takes them: hi, lo, valid
+            if (simd) host_pack_snp(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane2 + o, plane1 + o);
+            else host_pack_snp_scalar(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane2 + o, plane1 + o);
+        } else {
+            if (simd) host_pack_binary(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane1 + o);
+            else host_pack_binary_scalar(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane1 + o);
+        }
+    };
+    if (threads == 1) { work(0, n_rows); return FEHT_OK; }
+    std::vector<std::thread> pool;
+    const int64_t per = (n_rows + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        const int64_t r0 = t * per, r1 = std::min(n_rows, r0 + per);
+        if (r0 < r1) pool.emplace_back(work, r0, r1);
+    }
+    for (std::thread &th : pool) th.join();
+    return FEHT_OK;
+}
+
 extern "C" int feht_set_host_threads(feht_ctx *c, int n_threads) {
     if (!c) return FEHT_E_INVALID;
     c->host_threads = n_threads < 0 ? -1 : n_threads;

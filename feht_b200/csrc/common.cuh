@@ -82,6 +82,10 @@ void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int6
                       uint64_t *value, uint64_t *valid);
 void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                    uint64_t *hi, uint64_t *valid, uint64_t *lo);
+void host_pack_binary_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                             uint64_t *value, uint64_t *valid);
+void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                          uint64_t *hi, uint64_t *valid, uint64_t *lo);
 
 // count_popc.cu  (K1)
 struct PopcPlan {

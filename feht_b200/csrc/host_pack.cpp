@@ -21,6 +21,41 @@ namespace feht {
 
 bool host_pack_available() { return __builtin_cpu_supports("avx2") != 0; }
 
+// portable versions (no AVX2): the same planes, one call at a time -- only feht_pack_chars_host uses them
+void host_pack_binary_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                             uint64_t *value, uint64_t *valid) {
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint8_t *src = chars + off[r];
+        int64_t n = off[r + 1] - off[r];
+        if (n > S) n = S;
+        uint64_t *v = value + (r - r0) * W, *d = valid + (r - r0) * W;
+        for (int64_t w = 0; w < W; ++w) { v[w] = 0; d[w] = 0; }
+        for (int64_t j = 0; j < n; ++j) {
+            const uint64_t bit = uint64_t(1) << (j & 63);
+            if (src[j] == '1') { v[j >> 6] |= bit; d[j >> 6] |= bit; }
+            else if (src[j] == '0') d[j >> 6] |= bit;
+        }
+    }
+}
+void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                          uint64_t *hi, uint64_t *valid, uint64_t *lo) {
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint8_t *src = chars + off[r];
+        int64_t n = off[r + 1] - off[r];
+        if (n > S) n = S;
+        uint64_t *ph = hi + (r - r0) * W, *pv = valid + (r - r0) * W, *pl = lo + (r - r0) * W;
+        for (int64_t w = 0; w < W; ++w) { ph[w] = 0; pv[w] = 0; pl[w] = 0; }
+        for (int64_t j = 0; j < n; ++j) {
+            uint8_t c = src[j];
+            if (c >= 'a' && c <= 'z') c = uint8_t(c - 'a' + 'A');   // toUpper (Table.hs:205)
+            const uint64_t bit = uint64_t(1) << (j & 63);
+            if (c == 'G' || c == 'T') ph[j >> 6] |= bit;
+            if (c == 'C' || c == 'T') pl[j >> 6] |= bit;
+            if (c == 'A' || c == 'C' || c == 'G' || c == 'T') pv[j >> 6] |= bit;
+        }
+    }
+}
+
 namespace {
 
 __attribute__((target("avx2"))) inline uint64_t eq_mask64(const __m256i a, const __m256i b, const __m256i c) {

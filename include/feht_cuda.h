@@ -92,6 +92,15 @@ int feht_add_rows_chars(feht_ctx *ctx, const uint8_t *chars, const int64_t *row_
  * format is produced on the host; there is no CPU path for counting / testing / ordering.
  */
 int feht_set_host_threads(feht_ctx *ctx, int n_threads);
+/*
+ * The same transcoding as a plain host function (no context, no GPU): chars -> bit-planes of row_stride_words
+ * 64-bit words per row, zero padded, on n_threads host threads (<= 0: every core; AVX2 when the CPU has it).
+ * Binary mode: plane0 = value, plane1 = valid, plane2 unused.  SNP mode: plane0 = hi, plane1 = lo, plane2 = valid
+ * -- the argument order of feht_add_rows_packed / feht_add_snp_packed, which take the result.
+ */
+int feht_pack_chars_host(const uint8_t *chars, const int64_t *row_offsets, int64_t n_rows, int64_t n_samples,
+                         int snp_mode, int64_t row_stride_words, uint64_t *plane0, uint64_t *plane1,
+                         uint64_t *plane2, int n_threads);
 /* rows of the last chars upload that the host threads transcoded (diagnostics / tests) */
 int64_t feht_last_upload_host_rows(const feht_ctx *ctx);
 

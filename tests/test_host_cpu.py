@@ -138,3 +138,30 @@ def test_host_errors_are_the_reference_messages(cuda_lib, fixture_bytes):
     with pytest.raises(capi.FehtHostError) as e:
         capi.host_plan(meta, data, one="", two="all all")
     assert "No group one category given" in str(e.value)
+
+
+def test_host_transcoder_equals_numpy_packing(cuda_lib):
+    """feht_pack_chars_host (the AVX2 transcoder of host_pack.cpp, or its scalar twin on CPUs without AVX2) against
+    the numpy restatement of the packed layout: ragged rows, rows longer than S, stray characters, binary and SNP,
+    one thread and several.  No GPU involved."""
+    import numpy as np
+    from feht_b200 import capi
+    from helpers import pack_rows, pack_snp
+    rng = np.random.default_rng(123)
+    for S in (1, 63, 64, 65, 200, 1000):
+        R = 97
+        for snp in (False, True):
+            alphabet = np.frombuffer(b"ACGTacgt-N01x" if snp else b"01-1 0NX", dtype=np.uint8)
+            lens = rng.integers(max(0, S - 70), S + 40, size=R)
+            rows = [alphabet[rng.integers(0, len(alphabet), size=int(n))] for n in lens]
+            # what the layout means: characters at index >= len(row) or >= S contribute nothing
+            dense = np.full((R, S), ord("-"), dtype=np.uint8)
+            for i, r in enumerate(rows):
+                m = min(len(r), S)
+                dense[i, :m] = r[:m]
+            want = pack_snp(dense) if snp else pack_rows(dense)
+            for threads in (1, 5):
+                got = capi.pack_chars_host([bytes(r) for r in rows], S, snp=snp, n_threads=threads)
+                assert len(got) == len(want)
+                for g, w in zip(got, want):
+                    assert (g == w).all(), (S, snp, threads)
