@@ -407,6 +407,27 @@ def main() -> int:
                        + ("feht_result_fetch" if world == 1 else
                           "feht_result_fetch_device, NCCL gather to rank 0, feht_merge_sorted_device (K5), one D2H"),
                "timer": "host perf_counter between barrier+synchronize (covers H2D, kernels, D2H)"}
+        if world == 1:
+            # the same calls with the host transcoder switched off: every byte goes over the link raw and is packed
+            # by the GPU kernel (K0) -- what the upload costs without any help from the host cores
+            ctx.set_host_threads(0)
+            gtimes = []
+            for i in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                ctx.clear_rows()
+                ctx.clear_comparisons()
+                ctx.add_rows_chars_raw(chars.data_ptr(), offsets.data_ptr(), R)
+                ctx.add_comparison(G1, G2)
+                ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, total_rows)
+                ctx.fetch_raw(0, ptrs)
+                barrier()
+                if i > 0:
+                    gtimes.append(time.perf_counter() - t0)
+            ctx.set_host_threads(host_threads)
+            e2e["gpu_pack_only"] = {"value": total_rows / (sum(gtimes) / len(gtimes)), "unit": UNIT,
+                                    "ms_per_step": 1e3 * sum(gtimes) / len(gtimes), "h2d_bytes_per_step": R * S,
+                                    "note": "feht_set_host_threads(0): DMA + GPU pack kernel only"}
         del chars
         # second figure: the host already holds the PACKED planes (what the C++ loader of feht_b200/host
         # produces from the TSV, and the only form configs 2-5 fit in host memory in): feht_add_rows_packed
