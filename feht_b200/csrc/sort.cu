@@ -8,19 +8,17 @@
 //     key64 = ~bits(abs ratio)   (abs ratio in [0,1] => IEEE bits are monotone; inverted = descending)
 //           =  bits(p)           for FEHT_SORT_PVALUE_ASC
 //
-// Two engines.  Up to 8192 keys per SM (1.2M on a B200) the whole sort is one cooperative launch
-// (coop_sort_kernel below); beyond that each pass is ONE kernel ("onesweep"):
-// a CTA claims the next 2048-item tile from an atomic ticket,
-// ranks its items stably per digit (warp match-any + per-warp counters in shared memory), publishes
-// its per-digit counts and resolves the counts of all earlier tiles with a decoupled look-back over
-// a status word per (tile, digit), then scatters (key64, index) to the final positions.  The digit
-// histogram the NEXT pass needs is accumulated by the current pass while it has the keys in
-// registers, so there is no separate histogram/scan kernel per pass (the first version spent 63 us
-// per pass in a single-block scan; profiles/r1_launches.md).  A pass whose digit is identical in
-// every key is skipped (OR/AND reduction of the key words), so a single comparison costs no
-// "comparison" passes; when the survivors are emitted in name-rank order (dense output) the stable
-// sort needs no name-rank passes either.  The sort moves (8-byte key, 4-byte index) pairs; the
-// 40-byte records are gathered once at the end.
+// Two engines.  The default is ONE cooperative launch for all passes (coop_sort_kernel below: a chunk of up to
+// 8192 keys per SM, or several chunks per SM for larger outputs).  The other, kept for cross-checks
+// (FEHT_SORT=onesweep), runs each pass as one kernel ("onesweep"): a CTA claims the next 2048-item tile from an
+// atomic ticket, ranks its items stably per digit (warp match-any + per-warp counters in shared memory), publishes
+// its per-digit counts and resolves the counts of all earlier tiles with a decoupled look-back over a status
+// word per (tile, digit), then scatters (key64, index) to the final positions; the digit histogram the NEXT pass
+// needs is accumulated by the current pass while it has the keys in registers.  In both, a pass whose digit is
+// identical in every key is skipped (OR/AND reduction of the key words), so a single comparison costs no
+// "comparison" passes; when the survivors are emitted in name-rank order (dense output) the stable sort needs no
+// name-rank passes either.  The sort moves (8-byte key, 4-byte index) pairs; the 32-byte survivor records are read
+// once, through the permutation, by the kernel that writes the results (K3b, or gather_kernel for the p-value order).
 //
 // Bound: HBM/L2 traffic, 24 B per item per pass.
 #include "common.cuh"
