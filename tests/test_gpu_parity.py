@@ -808,7 +808,7 @@ def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
     with AVX2 (host_pack.cpp).  Both must produce the same bit-planes: ragged rows, rows longer than S, stray
     characters, binary and SNP."""
     rng = np.random.default_rng(99)
-    S, R = 2100, 36000
+    S, R = 2100, 72000
     lens = rng.integers(S - 70, S + 40, size=R)
     lens[:100] = rng.integers(0, 64, size=100)                      # very short rows too
     alphabet = np.frombuffer(b"01-1 0NX", dtype=np.uint8)
@@ -826,6 +826,16 @@ def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
                 planes[threads] = [c.read_plane(p, 0, R) for p in range(3 if snp else 2)]
         for a, b in zip(planes[0], planes[5]):
             assert (a == b).all(), snp
+        # appended in two calls (the second upload starts at a row offset inside the planes)
+        with capi.Context(0) as c:
+            c.set_samples(S)
+            c.set_host_threads(5)
+            add = c.add_snp_chars if snp else c.add_rows_chars
+            add(data[: R // 2 + 7])
+            add(data[R // 2 + 7:])
+            assert c.num_rows == (4 * R if snp else R)
+            for p, a in enumerate(planes[0]):
+                assert (c.read_plane(p, 0, R) == a).all(), (snp, p)
 
 
 def test_filtered_output_single_pass_and_capacity_overflow(ctx):
