@@ -1244,7 +1244,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         }
         c->sw.control = c->sw_control.p;
         if (tp.dense) {
-            CU(c, launch_test_emit(tp, c->st));
+            if (n_comps == 1 && c->comps[0].kind == 0)
+                CU(c, launch_test_emit_single(tp, 0, c->st));   // the one comparison lives in pair-slot 0
+            else
+                CU(c, launch_test_emit(tp, c->st));
             ++launches;
         }
     }

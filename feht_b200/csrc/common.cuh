@@ -164,6 +164,8 @@ struct TestParams {
 cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t *flags_words,
                                         unsigned long long *out_count, cudaStream_t st);
 cudaError_t launch_test_emit(const TestParams &p, cudaStream_t st);
+// dense output of ONE explicit comparison counted in pair-slot `slot`: thread = row, no shared state
+cudaError_t launch_test_emit_single(const TestParams &p, int slot, cudaStream_t st);
 // OR/AND accumulators of the sort-key words (rank, key lo, key hi, comparison): {0,0,0,0,~0,~0,~0,~0}
 cudaError_t launch_init_or_and(uint32_t *d_or_and, cudaStream_t st);
 // K3b over n survivors: p (+ Bonferroni).
