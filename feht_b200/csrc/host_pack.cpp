@@ -13,6 +13,7 @@
 // Characters at index >= row length or >= S contribute nothing.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -67,7 +68,7 @@ __attribute__((target("avx2"))) inline uint64_t eq_mask64(const __m256i a, const
 }  // namespace
 
 __attribute__((target("avx2")))
-void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+static void host_pack_binary_avx2(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                       uint64_t *value, uint64_t *valid) {
     const __m256i one = _mm256_set1_epi8('1'), zero = _mm256_set1_epi8('0');
     for (int64_t r = r0; r < r1; ++r) {
@@ -100,7 +101,7 @@ void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int6
 }
 
 __attribute__((target("avx2")))
-void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+static void host_pack_snp_avx2(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                    uint64_t *hi, uint64_t *valid, uint64_t *lo) {
     // toUpper on the four letters that matter: (c & 0xDF) == 'A' iff c is 'A' or 'a'
     const __m256i up = _mm256_set1_epi8(char(0xDF));
@@ -136,6 +137,82 @@ void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t
         }
         for (; w < W; ++w) { ph[w] = 0; pl[w] = 0; pv[w] = 0; }
     }
+}
+
+
+// AVX-512BW: one 64-byte load and one compare-into-mask per plane bit and word; the ragged end of a row is a
+// masked load, so there is no scalar tail.  ~12% more bytes per core than the AVX2 loop on Sapphire Rapids
+// (9.0 vs 8.0 GB/s per core against a 12.8 GB/s read-only ceiling), which is what the chars upload is bound by.
+__attribute__((target("avx512f,avx512bw")))
+static void host_pack_binary_avx512(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S,
+                                    int64_t W, uint64_t *value, uint64_t *valid) {
+    const __m512i one = _mm512_set1_epi8('1'), zero = _mm512_set1_epi8('0');
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint8_t *src = chars + off[r];
+        int64_t n = off[r + 1] - off[r];
+        if (n > S) n = S;
+        uint64_t *v = value + (r - r0) * W, *d = valid + (r - r0) * W;
+        const int64_t full = n >> 6;
+        for (int64_t w = 0; w < full; ++w) {
+            const __m512i a = _mm512_loadu_si512(src + 64 * w);
+            const uint64_t m1 = _mm512_cmpeq_epi8_mask(a, one);
+            v[w] = m1;
+            d[w] = m1 | _mm512_cmpeq_epi8_mask(a, zero);
+        }
+        int64_t w = full;
+        if (n & 63) {
+            const __mmask64 k = (uint64_t(1) << (n & 63)) - 1;
+            const __m512i a = _mm512_maskz_loadu_epi8(k, src + 64 * full);
+            const uint64_t m1 = _mm512_mask_cmpeq_epi8_mask(k, a, one);
+            v[w] = m1;
+            d[w] = m1 | _mm512_mask_cmpeq_epi8_mask(k, a, zero);
+            ++w;
+        }
+        for (; w < W; ++w) { v[w] = 0; d[w] = 0; }
+    }
+}
+
+__attribute__((target("avx512f,avx512bw")))
+static void host_pack_snp_avx512(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S,
+                                 int64_t W, uint64_t *hi, uint64_t *valid, uint64_t *lo) {
+    const __m512i up = _mm512_set1_epi8(char(0xDF));
+    const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'),
+                  cT = _mm512_set1_epi8('T');
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint8_t *src = chars + off[r];
+        int64_t n = off[r + 1] - off[r];
+        if (n > S) n = S;
+        uint64_t *ph = hi + (r - r0) * W, *pv = valid + (r - r0) * W, *pl = lo + (r - r0) * W;
+        const int64_t words = (n + 63) >> 6;
+        for (int64_t w = 0; w < words; ++w) {
+            const int64_t left = n - 64 * w;
+            const __mmask64 k = left >= 64 ? ~uint64_t(0) : (uint64_t(1) << left) - 1;
+            const __m512i a = _mm512_and_si512(_mm512_maskz_loadu_epi8(k, src + 64 * w), up);
+            const uint64_t mA = _mm512_mask_cmpeq_epi8_mask(k, a, cA), mC = _mm512_mask_cmpeq_epi8_mask(k, a, cC),
+                           mG = _mm512_mask_cmpeq_epi8_mask(k, a, cG), mT = _mm512_mask_cmpeq_epi8_mask(k, a, cT);
+            ph[w] = mG | mT;
+            pl[w] = mC | mT;
+            pv[w] = mA | mC | mG | mT;
+        }
+        for (int64_t w = words; w < W; ++w) { ph[w] = 0; pl[w] = 0; pv[w] = 0; }
+    }
+}
+
+static bool use_avx512() {
+    static const bool yes = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") &&
+                            getenv("FEHT_HOST_PACK_AVX2") == nullptr;
+    return yes;
+}
+
+void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                      uint64_t *value, uint64_t *valid) {
+    if (use_avx512()) host_pack_binary_avx512(chars, off, r0, r1, S, W, value, valid);
+    else host_pack_binary_avx2(chars, off, r0, r1, S, W, value, valid);
+}
+void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+                   uint64_t *hi, uint64_t *valid, uint64_t *lo) {
+    if (use_avx512()) host_pack_snp_avx512(chars, off, r0, r1, S, W, hi, valid, lo);
+    else host_pack_snp_avx2(chars, off, r0, r1, S, W, hi, valid, lo);
 }
 
 }  // namespace feht
