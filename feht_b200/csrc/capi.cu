@@ -478,7 +478,8 @@ int add_packed_common(feht_ctx *c, const uint64_t *const *src_planes, const int 
         const int64_t r0 = pc * rows_per_piece, r1 = std::min(n, r0 + rows_per_piece);
         uint64_t *dst = c->plane[dst_index[pl]] + (first_unit + r0) * c->W;
         const uint64_t *and_with = nullptr;
-        if (!snp && dst_index[pl] == 0) and_with = c->plane[1] + (first_unit + r0) * c->W;
+        // value / hi / lo bits only count where the call is valid (plane 1, uploaded first): K1 relies on it
+        if (dst_index[pl] != 1) and_with = c->plane[1] + (first_unit + r0) * c->W;
         CU(c, launch_repack_rows(reinterpret_cast<const uint64_t *>(dev), stride, dst, c->W, c->S,
                                  r1 - r0, and_with, c->st));
         return FEHT_OK;

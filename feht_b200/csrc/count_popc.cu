@@ -16,6 +16,8 @@
 //
 // Bound: HBM.  Algorithmic bytes per marker row = 2 planes * 8 * ceil(S/64);
 // the kernel reads 2 * 8 * W (W = that, rounded up to even) and writes 16 B per (row, pair-slot).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace feht {
@@ -59,6 +61,17 @@ struct CountStream {
         const uint32_t c2 = lop3_maj(ones, z, w);
         ones = lop3_xor3(ones, z, w);
         twos += __popc(c1) + __popc(c2);
+    }
+    // the same, with the two popcounts added on the FMA pipe (IMAD by a register that holds 1): the ring kernel is
+    // bound by the ALU pipe (AND / LOP3 / IADD3), the FMA pipe is idle
+    __device__ __forceinline__ void add_fma(const uint4 &a, const uint4 &m, int one) {
+        const uint32_t x = a.x & m.x, y = a.y & m.y, z = a.z & m.z, w = a.w & m.w;
+        const uint32_t c1 = lop3_maj(ones, x, y);
+        ones = lop3_xor3(ones, x, y);
+        const uint32_t c2 = lop3_maj(ones, z, w);
+        ones = lop3_xor3(ones, z, w);
+        asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(twos) : "r"(__popc(c1)), "r"(one));
+        asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(twos) : "r"(__popc(c2)), "r"(one));
     }
     __device__ __forceinline__ int total() const { return 2 * twos + __popc(ones); }
 };
@@ -286,6 +299,230 @@ count_popc_snp_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ va
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SNP planes, TMA-fed ring (the kernel config 3 runs).  The register-staged kernel above needs 16 count streams
+// per 128 bits for a 4-value category (32 registers) next to 15 outstanding 128-bit loads per lane, runs at one or
+// two CTAs per SM and alternates between waiting for its loads and ~1000 ALU instructions per lane: 0.29 of the
+// HBM peak.  Here the loads hold no registers: tiles of consecutive sites (three contiguous blocks, one per
+// plane) are streamed into a ring of shared-memory stages with cp.async.bulk, one `full` mbarrier per stage, and
+// the warps do nothing but LDS + AND / LOP3 / POPC.  Measured on config 3 (profiles/README.md r1l): 0.997 -> 0.48 ms
+// = 3.9 TB/s, ALU pipe 81% busy, XU (POPC) 67%: the scan is bound by the integer pipes (16 masked popcount streams
+// per word = ~150 ALU-pipe instructions and 32 POPC per 48 bytes of planes), no longer by latency.
+// Counted per mask: H = popc(hi&M), Lo = popc(lo&M), T = popc(hi&lo&M), N = popc(valid&M) (hi, lo are subsets of
+// valid); A=0 C=1 G=2 T=3 in (hi, lo) gives  _t = T, _c = Lo - T, _g = H - T, _a = N - H - Lo + T.
+// What did not work (same file history): one producer lane per CTA posting every tile (0.4 us per tile of three
+// bulk copies, serial: 0.71 ms whatever the number of consumer warps; two / four producer warps 0.56 / 0.49 ms);
+// a third carry-save level (half the POPC, +2 LOP3 per stream and column): 0.52 ms.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    uint32_t done = 0;
+    while (done < bytes) {  // <= 32 KiB per instruction
+        uint32_t n = bytes - done;
+        if (n > 32768u) n = 32768u;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                "r"(smem_u32(static_cast<char *>(smem_dst) + done)),
+            "l"(static_cast<const char *>(gmem_src) + done), "r"(n), "r"(smem_u32(bar))
+            : "memory");
+        done += n;
+    }
+}
+
+constexpr int kRingWarps = 16;       // consumer warps per CTA (+ 1 producer warp)
+constexpr int kRingMaxStages = 64;
+
+// Every warp is consumer AND producer: it claims the next tile of the CTA in ring order (a shared counter), waits
+// for the tile's stage, counts, and then refills that very stage with the tile n_stages further on (lane 0:
+// expect_tx + three bulk copies), so there is no producer warp and no `empty` barrier.
+// A tile is kiter * (32 >> LOGL) consecutive sites: three contiguous blocks (hi, lo, valid), one bulk copy each.
+// The L lane partials of the 8 * CB counts are packed two per register (counts <= S < 65536) and combined by a
+// reduce-scatter over the lanes of a site (4 * CB - 1 + ... shuffles instead of 8 * CB * log2 L); the packed totals
+// go through a few words of shared memory so that four lanes write one allele row each.
+template <int CB, int LOGL, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+count_popc_snp_ring_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ valid,
+                           const uint4 *__restrict__ lo, int64_t n_sites, int w4, int w4pad, int kiter,
+                           int n_stages, int one, const uint4 *__restrict__ masks, int4 *__restrict__ counts) {
+    constexpr int L = 1 << LOGL;
+    constexpr int RPW = 32 >> LOGL;
+    constexpr int NP = 4 * CB;          // packed values per site: [c][q], low half = first mask, high = second
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;                          // masks
+    __shared__ __align__(8) uint64_t full_bar[kRingMaxStages];     // producer -> consumer (tx bytes)
+    __shared__ uint32_t red[NW][RPW][NP];
+    __shared__ uint32_t next_tile;                                 // tiles are claimed in ring order
+    uint4 *sm_masks = reinterpret_cast<uint4 *>(smem_raw);         // [CB][2][w4pad]
+    const int tile_sites = kiter * RPW;
+    const uint32_t plane_cols = uint32_t(tile_sites) * uint32_t(w4);   // uint4 per plane block
+    uint4 *ring = sm_masks + size_t(CB) * 2 * w4pad;               // [stage][3][tile_sites][w4]
+
+    const int slot0 = blockIdx.y * CB;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+        }
+        next_tile = 0;
+    }
+    // initialises `bar`, fences the inits, __syncthreads, copies the masks, all threads wait
+    stage_masks_tma(sm_masks, masks + size_t(slot0) * 2 * w4pad, uint32_t(CB) * 2u * uint32_t(w4pad) * 16u,
+                    &bar);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_sites + tile_sites - 1) / tile_sites;
+    const uint32_t ust = uint32_t(n_stages);
+
+    // fills stage `it % n_stages` with tile `it` of this CTA (one lane; the stage must be free)
+    auto fill = [&](uint32_t it) {
+        const int64_t tile = int64_t(blockIdx.x) + int64_t(it) * gridDim.x;
+        if (tile >= n_tiles) return;
+        const uint32_t s = it % ust;
+        const int64_t site0 = tile * tile_sites;
+        const int64_t ns = (n_sites - site0 < tile_sites) ? (n_sites - site0) : tile_sites;
+        const uint32_t bytes = uint32_t(ns) * uint32_t(w4) * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[s])),
+                     "r"(3u * bytes)
+                     : "memory");
+        uint4 *dst = ring + size_t(s) * 3 * plane_cols;
+        const size_t goff = size_t(site0) * size_t(w4);
+        bulk_g2s(dst, hi + goff, bytes, &full_bar[s]);
+        bulk_g2s(dst + plane_cols, lo + goff, bytes, &full_bar[s]);
+        bulk_g2s(dst + 2 * size_t(plane_cols), valid + goff, bytes, &full_bar[s]);
+    };
+    // prologue: the first n_stages tiles, spread over the warps
+    if (lane == 0)
+        for (uint32_t it = uint32_t(warp); it < ust; it += NW) fill(it);
+
+    // ---- consumers
+    const int sub = lane & (L - 1);
+    const int rsub = lane >> LOGL;
+    const int64_t n_rows = 4 * n_sites;
+    for (;;) {
+        // the next tile of this CTA in ring order goes to whichever warp is free first, so stages come back to the
+        // producer in (nearly) the order it filled them
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(&next_tile, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        const int64_t tile = int64_t(blockIdx.x) + int64_t(it) * gridDim.x;
+        if (tile >= n_tiles) break;
+        const uint32_t s = it % ust;
+        mbar_wait(&full_bar[s], (it / ust) & 1u);
+        const int64_t site0 = tile * tile_sites;
+        const int ns = int((n_sites - site0 < tile_sites) ? (n_sites - site0) : tile_sites);
+        const uint4 *ph = ring + size_t(s) * 3 * plane_cols;
+        const uint4 *pl = ph + plane_cols;
+        const uint4 *pv = pl + plane_cols;
+        for (int g = 0; g < ns; g += RPW) {
+            const int ls = g + rsub;          // site inside the tile
+            const bool ok = ls < ns;
+            // st[c][mask][0..3] = H, Lo, T, N
+            CountStream st[CB][2][4];
+#pragma unroll
+            for (int c = 0; c < CB; ++c)
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st[c][m][q].reset();
+            if (ok) {
+                const uint32_t base = uint32_t(ls) * uint32_t(w4);
+#pragma unroll 2
+                for (int col = sub; col < w4; col += L) {
+                    // hi and lo are subsets of valid (every producer of SNP planes guarantees it, capi.cu)
+                    const uint4 v = pv[base + col];
+                    const uint4 h = ph[base + col];
+                    const uint4 l = pl[base + col];
+                    const uint4 t = make_uint4(h.x & l.x, h.y & l.y, h.z & l.z, h.w & l.w);
+#pragma unroll
+                    for (int c = 0; c < CB; ++c)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const uint4 mk = sm_masks[(c * 2 + m) * w4pad + col];
+                            st[c][m][0].add_fma(h, mk, one);
+                            st[c][m][1].add_fma(l, mk, one);
+                            st[c][m][2].add_fma(t, mk, one);
+                            st[c][m][3].add_fma(v, mk, one);
+                        }
+                }
+            }
+            // packed lane partials, then reduce-scatter over the L lanes of the site
+            uint32_t pk[NP];
+#pragma unroll
+            for (int c = 0; c < CB; ++c)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    pk[c * 4 + q] = uint32_t(st[c][0][q].total()) | (uint32_t(st[c][1][q].total()) << 16);
+            int n = NP;
+#pragma unroll
+            for (int o = L >> 1; o > 0; o >>= 1) {
+                if (n > 1) {
+                    const int half = n >> 1;
+                    const bool up = (sub & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < NP / 2; ++i)
+                        if (i < half) {
+                            const uint32_t send = up ? pk[i] : pk[i + half];
+                            const uint32_t keep = up ? pk[i + half] : pk[i];
+                            pk[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    n = half;
+                } else {
+                    pk[0] += __shfl_xor_sync(0xffffffffu, pk[0], o);
+                }
+            }
+            // lane `sub` now holds packed values [first, first + n) of its site
+            {
+                constexpr int kSteps = (LOGL < (CB == 1 ? 2 : 3)) ? LOGL : (CB == 1 ? 2 : 3);   // scatter steps taken
+                const int first = (sub >> (LOGL - kSteps)) * (NP >> kSteps);
+                const bool writer = (sub & ((1 << (LOGL - kSteps)) - 1)) == 0;
+                if (writer) {
+#pragma unroll
+                    for (int i = 0; i < (NP >> kSteps); ++i) red[warp][rsub][first + i] = pk[i];
+                }
+            }
+            __syncwarp();
+            for (int r = sub; r < 4 * CB; r += L) {
+                const int c = r >> 2, row = r & 3;
+                if (ok) {
+                    const uint32_t H = red[warp][rsub][c * 4 + 0], Lo = red[warp][rsub][c * 4 + 1],
+                                   T = red[warp][rsub][c * 4 + 2], N = red[warp][rsub][c * 4 + 3];
+                    // packed arithmetic would borrow across the halves: unpack first
+                    const int n1 = int(N & 0xffffu), n2 = int(N >> 16);
+                    const int h1 = int(H & 0xffffu), h2 = int(H >> 16);
+                    const int l1 = int(Lo & 0xffffu), l2 = int(Lo >> 16);
+                    const int t1 = int(T & 0xffffu), t2 = int(T >> 16);
+                    int x1, x2;
+                    if (row == 0) { x1 = n1 - h1 - l1 + t1; x2 = n2 - h2 - l2 + t2; }        // _a
+                    else if (row == 1) { x1 = t1; x2 = t2; }                                  // _t
+                    else if (row == 2) { x1 = l1 - t1; x2 = l2 - t2; }                        // _c
+                    else { x1 = h1 - t1; x2 = h2 - t2; }                                      // _g
+                    counts[size_t(slot0 + c) * n_rows + 4 * (site0 + ls) + row] = make_int4(x1, n1, x2, n2);
+                }
+            }
+            __syncwarp();
+        }
+        // every lane is done with the stage (the shuffles above consumed its loads): the warp that emptied it refills
+        // it with the tile n_stages further on -- no producer warp, no `empty` barrier, and the latency of posting
+        // a tile (expect_tx + three bulk copies, ~0.4 us for one thread) is spread over all warps
+        __syncwarp();
+        if (lane == 0) fill(it + ust);
+    }
+}
+
 // "whole category" record = sum of the category's value records: the values partition the category's genomes
 // (Table.hs:111-115,243-247), so the total mask never has to be scanned
 __global__ void __launch_bounds__(256)
@@ -354,6 +591,68 @@ cudaError_t dispatch(int ncol, int64_t want_ctas, int n_batches, size_t smem, in
 #undef FEHT_CASE
 }
 
+// ---- ring kernel launch (SNP).  Returns cudaErrorNotSupported when the shape does not suit it (every consumer warp
+// needs a tile of its own plus a few in flight, and the packed lane partials need S < 65536); the caller then takes
+// the register-staged kernel.
+template <int CB, int LOGL, int NW>
+cudaError_t launch_snp_ring_t(const uint4 *hi, const uint4 *valid, const uint4 *lo, int64_t n_sites, int w4,
+                              const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
+                              cudaStream_t st) {
+    constexpr size_t kSmemTotal = 208 * 1024;   // + up to 17.5 KB static (barriers, reduction scratch)
+    constexpr int RPW = 32 >> LOGL;
+    const size_t mask_bytes = size_t(CB) * 2 * pl.w4pad * 16;
+    if (mask_bytes >= kSmemTotal) return cudaErrorNotSupported;
+    const size_t site_bytes = size_t(48) * w4;                       // three planes
+    // tiles of ~8 KB: large enough for the bulk copies, small enough for kRingWarps + 8 stages
+    int kiter = int(size_t(8192) / (site_bytes * RPW));
+    if (kiter < 1) kiter = 1;
+    // small inputs: keep several tiles per consumer warp
+    while (kiter > 1 && (n_sites / (int64_t(kiter) * RPW)) < int64_t(num_sms) * NW * 2) kiter >>= 1;
+    const size_t stage_bytes = site_bytes * RPW * kiter;
+    int n_stages = int((kSmemTotal - mask_bytes) / stage_bytes);
+    if (n_stages > kRingMaxStages) n_stages = kRingMaxStages;
+    if (n_stages < NW + 4) return cudaErrorNotSupported;
+    const int64_t n_tiles = (n_sites + int64_t(kiter) * RPW - 1) / (int64_t(kiter) * RPW);
+    const size_t smem = mask_bytes + size_t(n_stages) * stage_bytes;
+    auto kernel = count_popc_snp_ring_kernel<CB, LOGL, NW>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    int64_t gx = num_sms / n_batches;
+    if (gx < 1) gx = 1;
+    if (gx > n_tiles) gx = n_tiles;
+    kernel<<<dim3(unsigned(gx), unsigned(n_batches)), NW * 32, smem, st>>>(
+        hi, valid, lo, n_sites, w4, pl.w4pad, kiter, n_stages, 1, masks, counts);
+    return cudaGetLastError();
+}
+
+inline bool snp_ring_enabled() {   // FEHT_SNP_RING=0: register-staged kernel (cross-checks)
+    static const bool v = [] {
+        const char *e = getenv("FEHT_SNP_RING");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+
+template <int CB>
+cudaError_t launch_snp_ring_any(const uint4 *hi, const uint4 *valid, const uint4 *lo, int64_t n_sites, int w4,
+                                const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
+                                cudaStream_t st) {
+    if (!snp_ring_enabled() || int64_t(w4) * 128 >= 65536) return cudaErrorNotSupported;
+    cudaError_t e = cudaErrorNotSupported;
+    switch (pl.logL) {
+        // 16 consumer warps; 8 when the stages of 16 do not fit (wide rows)
+#define FEHT_RING(LL)                                                                                                   \
+    case LL:                                                                                                            \
+        e = launch_snp_ring_t<CB, LL, kRingWarps>(hi, valid, lo, n_sites, w4, pl, masks, n_batches, counts, num_sms, st); \
+        if (e == cudaErrorNotSupported)                                                                                 \
+            e = launch_snp_ring_t<CB, LL, 8>(hi, valid, lo, n_sites, w4, pl, masks, n_batches, counts, num_sms, st);     \
+        return e;
+        FEHT_RING(0) FEHT_RING(1) FEHT_RING(2) FEHT_RING(3) FEHT_RING(4) FEHT_RING(5)
+#undef FEHT_RING
+        default: return cudaErrorNotSupported;
+    }
+}
+
 // pair-slots counted per read of the planes (register budget: 8 count streams per slot for SNP)
 template <bool SNP> constexpr int kBatch = SNP ? 2 : 4;
 
@@ -379,8 +678,10 @@ cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p
     const int nb = size_t(B) * 2 * plan.w4pad * 16 <= kSmemMax ? n_slots / B : 0;
     if (nb > 0) {
         const size_t smem = size_t(B) * 2 * plan.w4pad * 16;
-        cudaError_t e = dispatch<B, SNP>(plan.ncol, want, nb, smem, num_sms, st, a, b, c, n, w4, plan,
-                                         d_masks, d_counts);
+        cudaError_t e = cudaErrorNotSupported;
+        if constexpr (SNP) e = launch_snp_ring_any<B>(a, b, c, n, w4, plan, d_masks, nb, d_counts, num_sms, st);
+        if (e == cudaErrorNotSupported)
+            e = dispatch<B, SNP>(plan.ncol, want, nb, smem, num_sms, st, a, b, c, n, w4, plan, d_masks, d_counts);
         if (e != cudaSuccess) return e;
         if (launches) ++*launches;
         done = nb * B;
@@ -388,9 +689,14 @@ cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p
     if (done < n_slots) {
         const size_t smem = size_t(2) * plan.w4pad * 16;
         const size_t rows_out = SNP ? size_t(4) * n : size_t(n);
-        cudaError_t e = dispatch<1, SNP>(plan.ncol, want, n_slots - done, smem, num_sms, st, a, b, c, n,
-                                         w4, plan, d_masks + size_t(done) * 2 * plan.w4pad,
-                                         d_counts + size_t(done) * rows_out);
+        cudaError_t e = cudaErrorNotSupported;
+        if constexpr (SNP)
+            e = launch_snp_ring_any<1>(a, b, c, n, w4, plan, d_masks + size_t(done) * 2 * plan.w4pad, n_slots - done,
+                                       d_counts + size_t(done) * rows_out, num_sms, st);
+        if (e == cudaErrorNotSupported)
+            e = dispatch<1, SNP>(plan.ncol, want, n_slots - done, smem, num_sms, st, a, b, c, n,
+                                 w4, plan, d_masks + size_t(done) * 2 * plan.w4pad,
+                                 d_counts + size_t(done) * rows_out);
         if (e != cudaSuccess) return e;
         if (launches) ++*launches;
     }

@@ -416,6 +416,54 @@ def test_snp_packed_equals_expanded_binary_rows(ctx):
         _check_against_oracle(ctx, expanded, comps, 1, 0.1)
 
 
+@pytest.mark.parametrize("n_samples,n_sites,n_values", [
+    (1, 700, 2), (64, 5000, 3), (129, 3001, 4), (1000, 2500, 5), (5000, 1203, 4), (10000, 641, 4),
+    (20000, 300, 3), (40000, 97, 4), (70000, 40, 2)])
+def test_snp_count_kernels_shape_sweep(ctx, n_samples, n_sites, n_values):
+    """K1 for SNP planes over the shapes that select its variants (count_popc.cu): the TMA-fed ring with 16 or 8 warps,
+    several sites per lane group, tiles that end inside the matrix, an odd number of pair-slots, rows too wide for
+    the ring (register-staged kernel).  hi / lo planes deliberately carry bits where the call is missing.  Every
+    2x2 table of every comparison against numpy popcounts (bit-exact), for a whole category."""
+    rng = np.random.default_rng(n_samples * 7 + n_values)
+    W = (n_samples + 63) // 64
+    hi = rng.integers(0, 2**63, size=(n_sites, W), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n_sites, W), dtype=np.uint64)
+    lo = rng.integers(0, 2**63, size=(n_sites, W), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n_sites, W), dtype=np.uint64)
+    missing = rng.integers(0, 2**63, size=(n_sites, W), dtype=np.uint64) & rng.integers(0, 2**63, size=(n_sites, W), dtype=np.uint64) \
+        & rng.integers(0, 2**63, size=(n_sites, W), dtype=np.uint64)
+    valid = ~missing
+    if n_samples % 64:
+        valid[:, -1] &= np.uint64((1 << (n_samples % 64)) - 1)
+    vos = rng.integers(-1, n_values, size=n_samples).astype(np.int32)    # -1: genome without the category
+    ctx.set_samples(n_samples)
+    ctx.clear_comparisons()
+    ctx.add_snp_packed(hi, lo, valid)
+    ctx.add_category(vos, n_values)
+    ctx.run(capi.CORRECTION_NONE, 0.0)
+    # numpy: bits of the four allele rows of every site
+    def bits(a):
+        return np.unpackbits(a.view(np.uint8), axis=1, bitorder="little")[:, :n_samples].astype(bool)
+    bh, bl, bv = bits(hi), bits(lo), bits(valid)
+    allele = {0: ~bh & ~bl & bv, 1: bh & bl & bv, 2: ~bh & bl & bv, 3: bh & ~bl & bv}   # _a _t _c _g (A=0 C=1 G=2 T=3)
+    P = np.stack([allele[k] for k in range(4)], axis=1).reshape(4 * n_sites, n_samples)
+    V = np.repeat(bv, 4, axis=0)
+    onehot = np.stack([vos == v for v in range(n_values)], axis=1).astype(np.int64)       # [S][V]
+    pos = P.astype(np.int64) @ onehot
+    tot = V.astype(np.int64) @ onehot
+    assert ctx.num_comparisons == n_values * (n_values - 1) // 2 + (n_values if n_values > 2 else 0)
+    for c in range(ctx.num_comparisons):
+        kind, _cat, v1, v2 = ctx.comparison_info(c)
+        got = ctx.fetch(c)
+        order = np.argsort(got["row"])
+        assert (got["row"][order] == np.arange(4 * n_sites)).all()
+        a, n1 = pos[:, v1], tot[:, v1]
+        if kind == 1:    # pair
+            b, n2 = pos[:, v2], tot[:, v2]
+        else:            # one-vs-rest
+            b, n2 = pos.sum(axis=1) - a, tot.sum(axis=1) - n1
+        assert (got["goa"][order] == a).all() and (got["gob"][order] == n1 - a).all(), (c, kind, v1, v2)
+        assert (got["gta"][order] == b).all() and (got["gtb"][order] == n2 - b).all(), (c, kind, v1, v2)
+
+
 def test_row_sharding_and_merge_equals_single_context(cuda_lib):
     """shard marker rows, pass the global Bonferroni n, k-way merge the sorted shards."""
     rng = np.random.default_rng(55)

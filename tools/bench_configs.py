@@ -15,7 +15,7 @@ from feht_b200 import capi  # noqa: E402
 from helpers import make_spec  # noqa: E402
 
 
-def run(cfg, rows, engine, steps, ratio_filter=None):
+def run(cfg, rows, engine, steps, ratio_filter=None, samples=None):
     eng = {"popc": capi.ENGINE_POPC, "gemm": capi.ENGINE_GEMM, "fp4": capi.ENGINE_GEMM_FP4, "auto": capi.ENGINE_AUTO}[engine]
     with capi.Context(0) as ctx:
         if cfg == "c3":      # SNP 500k sites x 10k, one 4-value category -> 10 comparisons x 2M allele rows
@@ -39,6 +39,9 @@ def run(cfg, rows, engine, steps, ratio_filter=None):
             raise SystemExit("unknown config")
         if ratio_filter is not None:
             rf = ratio_filter
+        if samples is not None and cfg == "c3":     # shape experiments (row alignment)
+            S = samples
+            cats = [[(np.arange(S) * 4 // S).astype(np.int32), 4]]
         ctx.set_samples(S)
         ctx.reserve_rows(rows)
         sp = make_spec(capi.SynthSpec, S, law="uniform_half" if snp else "beta")
@@ -89,5 +92,6 @@ if __name__ == "__main__":
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--ratio-filter", type=float, default=None)
+    ap.add_argument("--samples", type=int, default=None)
     a = ap.parse_args()
-    run(a.cfg, a.rows, a.engine, a.steps, a.ratio_filter)
+    run(a.cfg, a.rows, a.engine, a.steps, a.ratio_filter, a.samples)
