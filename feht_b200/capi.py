@@ -31,7 +31,7 @@ EXPORTS = [
     "feht_result_fetch", "feht_set_row_base", "feht_last_timings", "feht_merge_sorted",
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
-    "feht_set_host_threads", "feht_last_upload_host_rows", "feht_set_fet_mode", "feht_pack_chars_host",
+    "feht_set_host_threads", "feht_last_upload_host_rows", "feht_add_rows_text", "feht_text_lines", "feht_set_name_rank", "feht_set_fet_mode", "feht_pack_chars_host",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -110,6 +110,12 @@ def lib() -> C.CDLL:
     L.feht_set_fet_mode.argtypes = [vp, C.c_int]
     L.feht_last_upload_host_rows.argtypes = [vp]
     L.feht_last_upload_host_rows.restype = i64
+    L.feht_add_rows_text.argtypes = [vp, vp, i64, C.c_char, C.c_int, vp]
+    L.feht_add_rows_text.restype = C.c_int
+    L.feht_text_lines.argtypes = [vp, vp, vp, i64]
+    L.feht_text_lines.restype = C.c_int
+    L.feht_set_name_rank.argtypes = [vp, vp, i64]
+    L.feht_set_name_rank.restype = C.c_int
     L.feht_run_async.argtypes = [vp, C.c_int, f64, C.c_int, i64]
     L.feht_timings_accumulated.argtypes = [vp, P(f64), C.c_int, C.c_int]
     L.feht_result_count.argtypes = [vp, i64]
@@ -311,6 +317,26 @@ class Context:
         flat, off = self._rows_to_flat(rows)
         nr = _i32(name_rank)
         self._check(self._L.feht_add_snp_chars(self._h, _ptr(flat), _ptr(off), len(off) - 1, _ptr(nr)))
+
+    def add_rows_text(self, text, delimiter: str = "\t", snp: bool = False):
+        """Body of the data file (bytes / pinned buffer address + length) -> rows on the device; returns
+        (line_begin, name_len) of the lines (feht_add_rows_text + feht_text_lines)."""
+        if isinstance(text, tuple):
+            ptr, n = text
+        else:
+            buf = np.frombuffer(text, dtype=np.uint8)
+            self._keep_text = buf
+            ptr, n = (buf.ctypes.data if len(buf) else None), len(buf)
+        nl = C.c_int64(0)
+        self._check(self._L.feht_add_rows_text(self._h, ptr, n, delimiter.encode()[0:1], 1 if snp else 0, C.byref(nl)))
+        begin = np.empty(nl.value, np.int64)
+        name_len = np.empty(nl.value, np.int32)
+        self._check(self._L.feht_text_lines(self._h, _ptr(begin), _ptr(name_len), nl.value))
+        return begin, name_len
+
+    def set_name_rank(self, name_rank):
+        r = _i32(name_rank)
+        self._check(self._L.feht_set_name_rank(self._h, _ptr(r), len(r)))
 
     def add_rows_packed(self, value, valid, name_rank=None):
         value = np.ascontiguousarray(value, dtype=np.uint64)

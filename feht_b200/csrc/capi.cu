@@ -115,6 +115,13 @@ struct feht_ctx {
     int64_t n_surv = 0;
     std::vector<int64_t> seg_off;
     Timings tm;
+
+    // text upload (text_load.cu): scratch on the device, and the lines of the last call for the host
+    DevBuf<uint32_t> txt_counts;
+    DevBuf<int32_t> txt_starts, txt_name_len;
+    DevBuf<unsigned long long> txt_flags;
+    std::vector<int64_t> text_line_begin;
+    std::vector<int32_t> text_name_len;
 };
 
 namespace {
@@ -554,6 +561,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->r_p); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
+    release(c->txt_counts); release(c->txt_starts); release(c->txt_name_len); release(c->txt_flags);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
         for (int i = 0; i < 5; ++i) if (c->evr[k][i]) cudaEventDestroy(c->evr[k][i]);
@@ -681,6 +689,143 @@ extern "C" int feht_add_rows_chars(feht_ctx *c, const uint8_t *chars, const int6
 extern "C" int feht_add_snp_chars(feht_ctx *c, const uint8_t *chars, const int64_t *row_offsets,
                                   int64_t n_sites, const int32_t *name_rank) {
     return add_chars_common(c, chars, row_offsets, n_sites, name_rank, 1);
+}
+
+// ------------------------------------------------------------------------- text upload (N2) --
+// Pieces of whole lines (<= 64 MB) go to the device as they are; text_load.cu finds the lines and packs them.
+// The copy of piece i + 1 runs while the kernels of piece i do.
+extern "C" int feht_add_rows_text(feht_ctx *c, const char *text, int64_t len, char delimiter, int snp_mode,
+                                  int64_t *n_lines_out) {
+    if (!c) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    const int snp = snp_mode ? 1 : 0;
+    if (int rc = check_mode(c, snp)) return rc;
+    if (len < 0 || (len > 0 && !text)) return fail(c, FEHT_E_INVALID, "null text");
+    if (delimiter == '\n' || delimiter == '\r') return fail(c, FEHT_E_INVALID, "the delimiter cannot be a line break");
+    if (c->have_rank == 1)
+        return fail(c, FEHT_E_INVALID, "text rows get their name ranks afterwards (feht_set_name_rank); the context "
+                    "already holds rows with ranks");
+    c->text_line_begin.clear();
+    c->text_name_len.clear();
+    if (n_lines_out) *n_lines_out = 0;
+    if (len == 0) return FEHT_OK;
+    constexpr int64_t kTextPiece = int64_t(64) << 20;
+    static_assert(size_t(kTextPiece) <= kStageBytes, "a text piece must fit a staging buffer");
+    for (int b = 0; b < 2; ++b) CU(c, ensure(c->stage[b], kStageBytes));
+    CU(c, ensure(c->txt_counts, text_scratch_words(size_t(kTextPiece))));
+    CU(c, ensure(c->txt_flags, 3));
+    const unsigned long long flags0[3] = {~0ull, 0ull, 0ull};
+    CU(c, cudaMemcpyAsync(c->txt_flags.p, flags0, sizeof(flags0), cudaMemcpyHostToDevice, c->st));
+    CU(c, cudaStreamSynchronize(c->st));   // (also: nothing of an earlier call still reads the staging buffers)
+
+    // piece boundaries: back up from every 64 MB mark to the last newline
+    std::vector<int64_t> cut{0};
+    while (cut.back() < len) {
+        int64_t end = std::min(len, cut.back() + kTextPiece);
+        if (end < len) {
+            const void *nl = memrchr(text + cut.back(), '\n', size_t(end - cut.back()));
+            if (!nl) return fail(c, FEHT_E_INVALID, "a line of the data file is longer than 64 MB");
+            end = static_cast<const char *>(nl) - text + 1;
+        }
+        cut.push_back(end);
+    }
+    const int n_pieces = int(cut.size()) - 1;
+    const int n_planes = snp ? 3 : 2;
+    const int64_t first_unit = c->n_units;
+    int64_t units = first_unit;
+    auto issue_copy = [&](int i) -> cudaError_t {
+        const int b = i & 1;
+        cudaError_t e = cudaMemcpyAsync(c->stage[b].p, text + cut[size_t(i)], size_t(cut[size_t(i) + 1] - cut[size_t(i)]),
+                                        cudaMemcpyHostToDevice, c->copy_stream);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(c->ev_copied[b], c->copy_stream);
+    };
+    CU(c, issue_copy(0));
+    std::vector<int32_t> h_starts, h_names;
+    for (int i = 0; i < n_pieces; ++i) {
+        const int b = i & 1;
+        const int64_t bytes = cut[size_t(i) + 1] - cut[size_t(i)];
+        // (the kernels of piece i - 1, which read the other staging buffer, were waited for at the end of the last turn)
+        if (i + 1 < n_pieces) CU(c, issue_copy(i + 1));
+        CU(c, cudaStreamWaitEvent(c->st, c->ev_copied[b], 0));
+        const uint8_t *d_text = c->stage[b].p;
+        CU(c, launch_text_count(d_text, bytes, c->txt_counts.p, c->st));
+        const int nb = int((bytes + 4095) / 4096);
+        uint32_t newlines = 0;
+        CU(c, cudaMemcpyAsync(&newlines, c->txt_counts.p + nb, 4, cudaMemcpyDeviceToHost, c->st));
+        CU(c, cudaStreamSynchronize(c->st));
+        const bool open_end = text[cut[size_t(i) + 1] - 1] != '\n';   // only the last piece can end without a newline
+        const int64_t n_lines = int64_t(newlines) + (open_end ? 1 : 0);
+        if (size_t(n_lines) + 2 > c->txt_starts.cap || !c->txt_starts.p) CU(c, ensure(c->txt_starts, size_t(n_lines) * 5 / 4 + 64));
+        if (size_t(n_lines) > c->txt_name_len.cap || !c->txt_name_len.p) CU(c, ensure(c->txt_name_len, size_t(n_lines) * 5 / 4 + 64));
+        // rows: one allocation sized from the first piece's line density, then grow_rows' own policy
+        int64_t want = units + n_lines;
+        if (i == 0 && n_pieces > 1) want = first_unit + int64_t(double(n_lines) * double(len) / double(bytes) * 1.01) + 64;
+        if (int rc = grow_rows(c, want, n_planes)) return rc;
+        CU(c, launch_text_starts(d_text, bytes, c->txt_counts.p, c->txt_starts.p, c->st));
+        if (open_end) {
+            const int32_t sentinel = int32_t(bytes + 1);
+            CU(c, cudaMemcpyAsync(c->txt_starts.p + n_lines, &sentinel, 4, cudaMemcpyHostToDevice, c->st));
+        }
+        CU(c, launch_text_pack(d_text, c->txt_starts.p, n_lines, uint8_t(delimiter), snp, c->S, c->W,
+                               c->plane[0] + units * c->W, c->plane[1] + units * c->W,
+                               snp ? c->plane[2] + units * c->W : nullptr, c->txt_name_len.p, c->txt_flags.p,
+                               c->num_sms, c->st));
+        h_starts.resize(size_t(n_lines));
+        h_names.resize(size_t(n_lines));
+        if (n_lines > 0) {
+            CU(c, cudaMemcpyAsync(h_starts.data(), c->txt_starts.p, size_t(n_lines) * 4, cudaMemcpyDeviceToHost, c->st));
+            CU(c, cudaMemcpyAsync(h_names.data(), c->txt_name_len.p, size_t(n_lines) * 4, cudaMemcpyDeviceToHost, c->st));
+        }
+        CU(c, cudaStreamSynchronize(c->st));
+        for (int64_t k = 0; k < n_lines; ++k) c->text_line_begin.push_back(cut[size_t(i)] + h_starts[size_t(k)]);
+        c->text_name_len.insert(c->text_name_len.end(), h_names.begin(), h_names.end());
+        units += n_lines;
+    }
+    unsigned long long flags[3] = {0, 0, 0};
+    CU(c, cudaMemcpyAsync(flags, c->txt_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, c->st));
+    CU(c, cudaStreamSynchronize(c->st));
+    if (flags[1]) {
+        c->text_line_begin.clear(); c->text_name_len.clear();
+        // `g:gnxs = xs` on the [] that BS.split gives for an empty line (Table.hs:168)
+        return fail(c, FEHT_E_INVALID, "Irrefutable pattern failed for pattern g : gnxs (an empty line in the data file)");
+    }
+    if (snp && flags[2]) {
+        c->text_line_begin.clear(); c->text_name_len.clear();
+        return fail(c, FEHT_E_INVALID, "the SNP text holds literal '0' / '1' calls, which count for all four alleles "
+                    "(Table.hs:194-205): upload the expanded rows with feht_add_rows_chars");
+    }
+    if (units > first_unit) {
+        c->min_row_len = std::min<int64_t>(c->min_row_len, int64_t(flags[0]));
+        if (c->have_rank == -1) c->have_rank = 0;
+    }
+    c->n_units = units;
+    c->rank_is_perm = -1;
+    c->has_results = false;
+    if (n_lines_out) *n_lines_out = units - first_unit;
+    return FEHT_OK;
+}
+
+extern "C" int feht_text_lines(feht_ctx *c, int64_t *line_begin, int32_t *name_len, int64_t cap) {
+    if (!c) return FEHT_E_INVALID;
+    const int64_t n = int64_t(c->text_line_begin.size());
+    if (cap < n) return fail(c, FEHT_E_INVALID, "feht_text_lines: %lld lines, room for %lld", (long long)n, (long long)cap);
+    if (n > 0 && line_begin) std::memcpy(line_begin, c->text_line_begin.data(), size_t(n) * 8);
+    if (n > 0 && name_len) std::memcpy(name_len, c->text_name_len.data(), size_t(n) * 4);
+    return FEHT_OK;
+}
+
+extern "C" int feht_set_name_rank(feht_ctx *c, const int32_t *name_rank, int64_t n_marker_rows) {
+    if (!c || !name_rank) return FEHT_E_INVALID;
+    if (int rc = use_device(c)) return rc;
+    if (n_marker_rows != marker_rows(c))
+        return fail(c, FEHT_E_INVALID, "feht_set_name_rank: %lld ranks for %lld marker rows", (long long)n_marker_rows,
+                    (long long)marker_rows(c));
+    if (n_marker_rows == 0) return FEHT_OK;
+    c->have_rank = 1;
+    c->rank_is_perm = -1;
+    c->has_results = false;
+    return append_rank(c, name_rank, n_marker_rows, 0);
 }
 
 extern "C" int feht_add_rows_packed(feht_ctx *c, const uint64_t *value_plane, const uint64_t *valid_plane,

@@ -87,6 +87,17 @@ void host_pack_binary_scalar(const uint8_t *chars, const int64_t *off, int64_t r
 void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                           uint64_t *hi, uint64_t *valid, uint64_t *lo);
 
+// text_load.cu: lines of a piece of the data file's text, and their rows packed (N2 of SURVEY.md 8f)
+size_t text_scratch_words(size_t piece_bytes);
+// d_block_counts: per 4 KB block the lines before it (in place), [n_blocks] = newlines of the piece
+cudaError_t launch_text_count(const uint8_t *d_text, int64_t len, uint32_t *d_block_counts, cudaStream_t st);
+cudaError_t launch_text_starts(const uint8_t *d_text, int64_t len, const uint32_t *d_block_base,
+                               int32_t *d_line_start, cudaStream_t st);
+// d_flags: [0] min row length (init ~0), [1] an empty line, [2] literal '0'/'1' in SNP text
+cudaError_t launch_text_pack(const uint8_t *d_text, const int32_t *d_line_start, int64_t n_lines, uint8_t delim,
+                             int snp, int64_t S, int64_t W, uint64_t *p0, uint64_t *valid, uint64_t *lo,
+                             int32_t *d_name_len, unsigned long long *d_flags, int num_sms, cudaStream_t st);
+
 // count_popc.cu  (K1)
 struct PopcPlan {
     int logL;      // lanes per row = 1 << logL

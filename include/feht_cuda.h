@@ -105,6 +105,26 @@ int feht_pack_chars_host(const uint8_t *chars, const int64_t *row_offsets, int64
 int64_t feht_last_upload_host_rows(const feht_ctx *ctx);
 
 /*
+ * The data file's text, straight to the device.  Replaces Table.hs:267-279 (`BS.lines`, the '\r'
+ * filter, `BS.split d`) and Table.hs:160-191 (first cell = marker name, the remaining cells concatenated; the
+ * character index in that concatenation is the column number) for the BODY of the file: `text` starts after the
+ * header line.  Every line becomes one row (binary) or one site (snp_mode; expanded to _a,_t,_c,_g on the device,
+ * Table.hs:184-205), in file order; lines are split at '\n', a final line without one counts.  The text is copied
+ * in pieces of whole lines and parsed + packed by text_load.cu; nothing is parsed on the host.
+ * Errors (nothing is appended): an empty line (the reference dies on `g:gnxs = xs`), a line longer than 64 MB,
+ * SNP text with literal '0' / '1' calls (they count for all four alleles: use feht_add_rows_chars with the expanded
+ * rows).  Marker names stay in the caller's text: feht_text_lines() gives, per line of the last call, the offset of
+ * the line in `text` and the byte length of its first cell (a '\r' inside the name is counted; duplicate names are
+ * the caller's to detect -- the reference keeps the last of them, Table.hs:210-224).  Name ranks for the tie-break
+ * are set afterwards for all marker rows at once with feht_set_name_rank() (SNP: four per site, in the order
+ * _a,_t,_c,_g); without it the rank is the global row index.
+ */
+int feht_add_rows_text(feht_ctx *ctx, const char *text, int64_t len, char delimiter, int snp_mode,
+                       int64_t *n_lines_out);
+int feht_text_lines(feht_ctx *ctx, int64_t *line_begin, int32_t *name_len, int64_t cap);
+int feht_set_name_rank(feht_ctx *ctx, const int32_t *name_rank, int64_t n_marker_rows);
+
+/*
  * Append rows already packed: bit s of word (s/64) of a row = sample s; value bit set iff the
  * call is '1', valid bit set iff it is '1' or '0'.  row_stride_words >= ceil(S/64) 64-bit words.
  * Benchmark-scale entry (the reference layout is 4 B per call and cannot hold configs 2-5).

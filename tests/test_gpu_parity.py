@@ -464,6 +464,116 @@ def test_snp_count_kernels_shape_sweep(ctx, n_samples, n_sites, n_values):
         assert (got["gta"][order] == b).all() and (got["gtb"][order] == n2 - b).all(), (c, kind, v1, v2)
 
 
+def _random_table_text(rng, n_lines, n_cols, delim, snp, crlf=True):
+    """Body of a data file the way Table.hs reads it, with the quirks that matter: cells wider than one character
+    (they shift the later columns), empty cells, '\\r' line ends and stray '\\r', ragged lines, a last line without
+    a newline, names of any length (also empty).  Returns (text, names, rows) with rows = what parseDataFile hands on."""
+    cells_bin = [b"1", b"0", b"1", b"0", b"-", b"1 ", b"NA", b"", b"?"]
+    cells_snp = [b"A", b"C", b"G", b"T", b"a", b"c", b"g", b"t", b"-", b"N", b"AC", b""]
+    pool = cells_snp if snp else cells_bin
+    weights = np.array([6, 6, 6, 6, 1, 0.3, 0.3, 0.3, 0.3][: len(pool)] + [0.3] * max(0, len(pool) - 9), dtype=float)
+    if snp:
+        weights = np.array([5, 5, 5, 5, 1, 1, 1, 1, 1, 0.5, 0.3, 0.3])
+    weights /= weights.sum()
+    d = delim.encode()
+    lines, names, rows = [], [], []
+    for i in range(n_lines):
+        k = n_cols if rng.random() < 0.9 else int(rng.integers(0, n_cols + 3))
+        name = (b"m%d" % i) * int(rng.integers(0, 3)) + (b"x" if rng.random() < 0.5 else b"")
+        cells = [pool[j] for j in rng.choice(len(pool), size=k, p=weights)]
+        line = d.join([name] + cells)
+        if line == b"":
+            line = b"q"                      # (an empty line is an error: tested separately)
+        if crlf and rng.random() < 0.3:
+            line = line[: len(line) // 2] + b"\r" + line[len(line) // 2:]
+        lines.append(line + (b"\r" if crlf and i % 3 == 0 else b""))
+        clean = lines[-1].replace(b"\r", b"").split(d)
+        names.append(clean[0])
+        rows.append(b"".join(clean[1:]))
+    return b"\n".join(lines) + (b"\n" if n_lines % 2 else b""), names, rows
+
+
+@pytest.mark.parametrize("snp", [False, True])
+@pytest.mark.parametrize("delim", ["\t", ","])
+def test_text_upload_equals_host_parsed_rows(ctx, snp, delim):
+    """feht_add_rows_text (text_load.cu: lines, first cell = name, the rest concatenated, packed on the device) against
+    the rows a host parser following Table.hs:267-279,160-191 would hand to feht_add_rows_chars: same planes, same
+    line offsets and name lengths, same shortest row (bounds check of V.!)."""
+    rng = np.random.default_rng(5 + snp)
+    for n_lines, n_cols in ((1, 1), (37, 12), (500, 200), (1200, 1031)):
+        text, names, rows = _random_table_text(rng, n_lines, n_cols, delim, snp)
+        S = n_cols
+        ctx.set_samples(S)
+        begin, name_len = ctx.add_rows_text(text, delim, snp)
+        assert len(begin) == n_lines
+        got = [ctx.read_plane(k, 0, n_lines) for k in range(3 if snp else 2)]
+        raw_lines = text.split(b"\n")
+        pos = 0
+        for i in range(n_lines):
+            assert begin[i] == pos, i
+            assert name_len[i] == len(raw_lines[i].split(delim.encode())[0]), i
+            pos += len(raw_lines[i]) + 1
+        ctx.set_samples(S)
+        (ctx.add_snp_chars if snp else ctx.add_rows_chars)(rows)
+        want = [ctx.read_plane(k, 0, n_lines) for k in range(3 if snp else 2)]
+        for g, w in zip(got, want):
+            assert (g == w).all()
+
+
+def test_text_upload_errors_and_name_ranks(ctx):
+    S = 6
+    ctx.set_samples(S)
+    with pytest.raises(capi.FehtError) as e:
+        ctx.add_rows_text(b"a\t1\t0\n\nb\t1\t1\n", "\t", False)
+    assert "Irrefutable pattern" in str(e.value) and ctx.num_rows == 0
+    ctx.set_samples(S)
+    with pytest.raises(capi.FehtError) as e:
+        ctx.add_rows_text(b"s1\tA\tC\t1\n", "\t", True)
+    assert "literal" in str(e.value)
+    # ranks set afterwards order the ties: three identical rows, ranks 2,0,1
+    ctx.set_samples(S)
+    ctx.add_rows_text(b"z\t1\t1\t1\t0\t0\t0\ny\t1\t1\t1\t0\t0\t0\nx\t1\t1\t1\t0\t0\t0", "\t", False)
+    assert ctx.num_rows == 3
+    ctx.set_name_rank(np.array([2, 0, 1], dtype=np.int32))
+    ctx.clear_comparisons()
+    ctx.add_comparison(np.arange(0, 3), np.arange(3, 6))
+    ctx.run(capi.CORRECTION_NONE, 0.0)
+    got = ctx.fetch(0)
+    assert list(got["row"]) == [1, 2, 0] and list(got["goa"]) == [3, 3, 3] and list(got["gtb"]) == [3, 3, 3]
+    # a row shorter than a group's columns is the reference's V.! error
+    ctx.set_samples(S)
+    ctx.add_rows_text(b"a\t1\t1\t1\t0\t0\t0\nb\t1\t1\n", "\t", False)
+    ctx.clear_comparisons()
+    ctx.add_comparison(np.arange(0, 3), np.arange(3, 6))
+    with pytest.raises(capi.FehtError):
+        ctx.run(capi.CORRECTION_NONE, 0.0)
+
+
+def test_text_upload_many_pieces(cuda_lib):
+    """150 MB of text = three pieces of whole lines: planes equal those of the character rows, line offsets
+    continue across the pieces."""
+    rng = np.random.default_rng(8)
+    S = 300
+    block_text, _names, block_rows = _random_table_text(rng, 4000, S, "\t", False, crlf=False)
+    if not block_text.endswith(b"\n"):
+        block_text += b"\n"
+    reps = (150 << 20) // len(block_text) + 1
+    text = block_text * reps
+    n_lines = 4000 * reps
+    with capi.Context(0) as c:
+        c.set_samples(S)
+        begin, name_len = c.add_rows_text(text, "\t", False)
+        assert len(begin) == n_lines and begin[4000] == len(block_text) and begin[-4000] == len(block_text) * (reps - 1)
+        assert (np.diff(begin) > 0).all()
+        got = [c.read_plane(k, n_lines - 4000, 4000) for k in range(2)]
+        first = [c.read_plane(k, 0, 4000) for k in range(2)]
+        c.set_samples(S)
+        c.add_rows_chars(block_rows)
+        want = [c.read_plane(k, 0, 4000) for k in range(2)]
+    for g, f, w in zip(got, first, want):
+        assert (g == w).all() and (f == w).all()
+
+
 def test_row_sharding_and_merge_equals_single_context(cuda_lib):
     """shard marker rows, pass the global Bonferroni n, k-way merge the sorted shards."""
     rng = np.random.default_rng(55)
