@@ -383,24 +383,72 @@ extern "C" int feht_host_run(const char *metadata, int64_t meta_len, const char 
     try {
         // ---- Main.hs:16-25: categories, parse, metadata, comparison list
         const GroupCategories gc = generate_categories(one, two);
-        const ParsedDataFile pd = parse_data_file(delimiter, snp_mode != 0, std::string_view(data, size_t(data_len)));
+        const std::string_view whole(data, size_t(data_len));
+        // The header line is parsed here; the body goes to the device as text (feht_add_rows_text, N2) unless
+        // FEHT_HOST_TEXT=0, marker names repeat (the reference keeps one row per name) or SNP text holds literal
+        // '0' / '1' -- then parse_data_file reads the body on the host as before.
+        const size_t hdr_end = whole.find('\n');
+        const std::string_view header = whole.substr(0, hdr_end == std::string_view::npos ? whole.size() : hdr_end + 1);
+        const std::string_view body = hdr_end == std::string_view::npos ? std::string_view() : whole.substr(hdr_end + 1);
+        ParsedDataFile pd = parse_data_file(delimiter, snp_mode != 0, header);
+        // (metadata and comparisons need the header only: their errors come before anything is uploaded)
         const Table t = get_metadata_from_file(delimiter, pd, std::string_view(metadata, size_t(meta_len)));
         const Plan plan = get_comparison_list(t, gc, pd.n_columns);
+        const char *text_env = std::getenv("FEHT_HOST_TEXT");
+        bool text_path = !(text_env && std::atoi(text_env) == 0) && pd.n_columns > 0 && !body.empty() && !plan.comps.empty();
+        Ctx ctx(device);
+        if (text_path) {
+            ctx.check(feht_set_samples(ctx.c, pd.n_columns));
+            int64_t n_lines = 0;
+            const int rc = feht_add_rows_text(ctx.c, body.data(), int64_t(body.size()), delimiter, snp_mode, &n_lines);
+            if (rc != FEHT_OK) {
+                const std::string msg = feht_last_error(ctx.c);
+                if (msg.find("Irrefutable pattern") != std::string::npos)
+                    throw HostError("Irrefutable pattern failed for pattern g : gnxs");
+                if (msg.find("literal") == std::string::npos) ctx.check(rc);
+                text_path = false;
+            } else {
+                std::vector<int64_t> begin(static_cast<size_t>(n_lines));
+                std::vector<int32_t> nlen(begin.size());
+                ctx.check(feht_text_lines(ctx.c, begin.data(), nlen.data(), n_lines));
+                static const char *sfx[4] = {"_a", "_t", "_c", "_g"};
+                pd.gene_names.reserve(begin.size() * (snp_mode ? 4 : 1));
+                for (size_t i = 0; i < begin.size(); ++i) {
+                    Bytes nm(body.data() + begin[i], size_t(nlen[i]));
+                    nm.erase(std::remove(nm.begin(), nm.end(), '\r'), nm.end());
+                    if (!snp_mode) pd.gene_names.push_back(std::move(nm));
+                    else for (int a = 0; a < 4; ++a) pd.gene_names.push_back(nm + sfx[a]);
+                }
+            }
+        }
+        std::vector<int32_t> by_name, name_rank;
+        auto rank_names = [&]() -> bool {   // false: a name occurs twice
+            const size_t n = pd.gene_names.size();
+            by_name.resize(n); name_rank.resize(n);
+            for (size_t i = 0; i < n; ++i) by_name[i] = int32_t(i);
+            std::sort(by_name.begin(), by_name.end(),
+                      [&](int32_t a, int32_t b) { return pd.gene_names[size_t(a)] < pd.gene_names[size_t(b)]; });
+            for (size_t r = 0; r < n; ++r) name_rank[size_t(by_name[r])] = int32_t(r);
+            for (size_t r = 1; r < n; ++r)
+                if (pd.gene_names[size_t(by_name[r])] == pd.gene_names[size_t(by_name[r - 1])]) return false;
+            return true;
+        };
+        if (text_path && !rank_names()) text_path = false;
+        if (!text_path) {
+            ctx.check(feht_clear_rows(ctx.c));
+            pd = parse_data_file(delimiter, snp_mode != 0, whole);
+        }
 
         std::string text;
         const size_t n_rows = pd.gene_names.size();
         if (!plan.comps.empty() && n_rows > 0 && pd.n_columns > 0) {
             // name rank = position of the marker name in byte order (tie-break of the final ordering)
-            std::vector<int32_t> by_name(n_rows), name_rank(n_rows);
-            for (size_t i = 0; i < n_rows; ++i) by_name[i] = int32_t(i);
-            std::sort(by_name.begin(), by_name.end(),
-                      [&](int32_t a, int32_t b) { return pd.gene_names[size_t(a)] < pd.gene_names[size_t(b)]; });
-            for (size_t r = 0; r < n_rows; ++r) name_rank[size_t(by_name[r])] = int32_t(r);
+            if (!text_path) rank_names();
 
             // ---- Main.hs:26-29 on the GPU
-            Ctx ctx(device);
-            ctx.check(feht_set_samples(ctx.c, pd.n_columns));
+            if (!text_path) ctx.check(feht_set_samples(ctx.c, pd.n_columns));
             ctx.check(feht_set_count_engine(ctx.c, engine));
+            if (text_path) ctx.check(feht_set_name_rank(ctx.c, name_rank.data(), int64_t(name_rank.size())));
             // SNP sites go up as one character per sample and are expanded on the device, unless the file
             // holds literal '0'/'1' (those count for all four alleles, Table.hs:194-205: only the expanded
             // character rows can express that) or rows are ragged
@@ -414,7 +462,8 @@ extern "C" int feht_host_run(const char *metadata, int64_t meta_len, const char 
             for (const Bytes &r : rows) flat += r;
             flat.push_back('\0');
             const uint8_t *chars = reinterpret_cast<const uint8_t *>(flat.data());
-            if (use_sites) ctx.check(feht_add_snp_chars(ctx.c, chars, off.data(), int64_t(rows.size()), name_rank.data()));
+            if (text_path) {}   // the rows are on the device already
+            else if (use_sites) ctx.check(feht_add_snp_chars(ctx.c, chars, off.data(), int64_t(rows.size()), name_rank.data()));
             else ctx.check(feht_add_rows_chars(ctx.c, chars, off.data(), int64_t(rows.size()), name_rank.data()));
             if (!plan.cats.empty()) {
                 for (const PlannedCategory &pc : plan.cats)

@@ -734,6 +734,38 @@ def test_host_run_prints_what_feht_prints(cuda_lib, fixture_bytes, data_name, me
                     assert got == want, (one, two, correction, rf, engine)
 
 
+def test_host_run_device_text_path_equals_host_parser(cuda_lib, fixture_bytes, monkeypatch):
+    """feht_host_run sends the body of the data file to the device as text (feht_add_rows_text) and falls back to
+    parse_data_file when marker names repeat or SNP text holds literal 0/1; FEHT_HOST_TEXT=0 forces the host
+    parser.  Same bytes out either way: the fixtures, CRLF line ends, a cell wider than one character, a ragged
+    line, a repeated name, a literal '1' in SNP data."""
+    meta = fixture_bytes["test_metadata.txt"]
+    binary = fixture_bytes["test_binary.txt"]
+    snps = fixture_bytes["test_snps.txt"]
+    blines = binary.split(b"\n")
+    variants = [
+        ("binary", binary),
+        ("binary", binary.replace(b"\n", b"\r\n")),
+        ("binary", b"\n".join(blines[:3] + [blines[3] + b"\t1"] + blines[4:])),            # one line longer
+        ("binary", b"\n".join(blines[:5] + [blines[5].rsplit(b"\t", 2)[0]] + blines[6:])),  # one line shorter
+        ("binary", b"\n".join(blines[:8] + [blines[2]] + blines[8:])),                       # a name twice
+        ("snp", snps),
+        ("snp", snps.replace(b"\n", b"\r\n")),
+        ("snp", snps.replace(b"\tA\t", b"\t1\t", 1)),                                      # literal 1
+    ]
+    for mode, data in variants:
+        for one, two, rf in (("all all", "all all", 0.0), ("group A", "group B", 0.5)):
+            outs = []
+            for env in ("1", "0"):
+                monkeypatch.setenv("FEHT_HOST_TEXT", env)
+                try:
+                    outs.append(capi.host_run(meta, data, one, two, b"\t", mode, "none", rf))
+                except capi.FehtHostError as e:
+                    outs.append(("error", str(e)))
+            assert outs[0] == outs[1], (mode, one, two, rf, outs[0][:200], outs[1][:200])
+    monkeypatch.delenv("FEHT_HOST_TEXT")
+
+
 def test_host_run_readme_rows(cuda_lib, fixture_bytes):
     """README.md:133: `binary9 2 0 1 4 ... 0.8` in the position sideways-vs-up block."""
     out = capi.host_run(fixture_bytes["test_metadata.txt"], fixture_bytes["test_binary.txt"],
