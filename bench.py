@@ -401,7 +401,7 @@ def main() -> int:
                "rank0_breakdown_ms": parts,
                "host_transcoder": {"threads": host_threads, "rows_packed_on_host": ctx.last_upload_host_rows_chars,
                                    "note": "feht_add_rows_chars splits the upload: DMA + GPU pack kernel for one end "
-                                           "of the row range, AVX2 host threads packing to 2 bits/call for the other"},
+                                           "of the row range, AVX-512 / AVX2 host threads packing to 2 bits/call for the other"},
                "input_gbs_per_gpu": R * S / (parts["upload_pack_ms"] * 1e-3) / 1e9,
                "path": "feht_add_rows_chars(pinned host chars, 1 B/call; DMA+K0 and host transcoder threads) -> feht_run -> "
                        + ("feht_result_fetch" if world == 1 else
@@ -428,7 +428,6 @@ def main() -> int:
             e2e["gpu_pack_only"] = {"value": total_rows / (sum(gtimes) / len(gtimes)), "unit": UNIT,
                                     "ms_per_step": 1e3 * sum(gtimes) / len(gtimes), "h2d_bytes_per_step": R * S,
                                     "note": "feht_set_host_threads(0): DMA + GPU pack kernel only"}
-        del chars
         # second figure: the host already holds the PACKED planes (what the C++ loader of feht_b200/host
         # produces from the TSV, and the only form configs 2-5 fit in host memory in): feht_add_rows_packed
         if world == 1:
@@ -458,6 +457,38 @@ def main() -> int:
                 "d2h_bytes_per_step": d2h,
                 "path": "feht_add_rows_packed(pinned host bit-planes, 2 bits/call) -> feht_run -> feht_result_fetch"}
             del pv, pd
+        if world == 1:
+            # third figure: the data file's TEXT (tab separated, 2 bytes per call + an 8-character name per line) parsed
+            # and packed on the device (feht_add_rows_text) -- a 200k-line slice of the same matrix
+            Rt = min(R, 200_000)
+            row_b = 8 + 2 * S + 1
+            text = torch.empty((Rt, row_b), dtype=torch.uint8, pin_memory=True)
+            tn = text.numpy()
+            tn[:, 0] = ord("m")
+            tn[:, 1:8] = np.frombuffer("".join(np.char.zfill(np.arange(Rt).astype(str), 7)).encode(), dtype=np.uint8).reshape(Rt, 7)
+            tn[:, 8:8 + 2 * S:2] = ord("\t")
+            tn[:, 9:9 + 2 * S:2] = chars.numpy()[:Rt]
+            tn[:, -1] = ord("\n")
+            ttimes = []
+            for i in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                ctx.clear_rows()
+                ctx.clear_comparisons()
+                ctx.add_rows_text((text.data_ptr(), Rt * row_b), "\t", False)
+                ctx.add_comparison(G1, G2)
+                ctx.run(capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC, Rt)
+                ctx.fetch_raw(0, ptrs)
+                barrier()
+                if i > 0:
+                    ttimes.append(time.perf_counter() - t0)
+            e2e["text_input"] = {"value": Rt / (sum(ttimes) / len(ttimes)), "unit": UNIT, "rows": Rt,
+                                 "ms_per_step": 1e3 * sum(ttimes) / len(ttimes), "h2d_bytes_per_step": Rt * row_b,
+                                 "text_gbs": Rt * row_b / (sum(ttimes) / len(ttimes)) / 1e9,
+                                 "path": "feht_add_rows_text(pinned host text of the data file body, parsed and packed by "
+                                         "text_load.cu) -> feht_run -> feht_result_fetch"}
+            del text
+        del chars
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N=1)
     cpu = None

@@ -16,7 +16,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "libfeht_cuda.so"
 OK = 0
 CORRECTION_NONE, CORRECTION_BONFERRONI = 0, 1
 SORT_ABS_RATIO_DESC, SORT_PVALUE_ASC = 0, 1
-ENGINE_AUTO, ENGINE_POPC, ENGINE_GEMM, ENGINE_GEMM_FP4 = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_POPC, ENGINE_GEMM, ENGINE_GEMM_FP4, ENGINE_GEMM_F8 = 0, 1, 2, 3, 4
 FET_TWO_TAIL, FET_ONE_TAIL = 0, 1
 E_INVALID, E_CUDA, E_BOUNDS, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5
 

@@ -92,6 +92,7 @@ struct feht_ctx {
     int gemm_n_passes = 0;
     bool gemm_ready = false;         // gemm_b / gemm_passes match the current categories
     bool gemm_fp4 = false;           // ... and were baked for the 4-bit (kind::mxf4) flavour
+    bool gemm_f8 = false;            // ... or for the e5m2 one (both planes in one GEMM)
     bool plan_ready = false;         // masks / groups / fracs / gcomps / sdefs on the device match the comparisons
     int plan_groups = 0, plan_max_frac = 0, plan_max_comp = 0, plan_max_slot = 0;
     int last_engine = 0;             // engine the last run counted categories with
@@ -956,7 +957,7 @@ extern "C" int feht_comparison_info(const feht_ctx *c, int64_t i, int32_t *kind,
 
 extern "C" int feht_set_count_engine(feht_ctx *c, int engine) {
     if (!c) return FEHT_E_INVALID;
-    if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM_FP4) return fail(c, FEHT_E_INVALID, "unknown engine");
+    if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM_F8) return fail(c, FEHT_E_INVALID, "unknown engine");
     c->engine = engine;
     return FEHT_OK;
 }
@@ -978,6 +979,54 @@ bool gemm_auto_fp4() {
         return kGemmAutoFp4;
     }();
     return fp4;
+}
+// The e5m2 flavour (one GEMM for both planes) issues half the MMAs but needs ~6 instructions per 4 calls in the
+// expanders and ends up bound by them (config 4: 4.87 ms against 3.85 ms, profiles/README.md r1q): AUTO only takes
+// it with FEHT_GEMM=f8
+bool gemm_auto_f8() {
+    static const bool f8 = [] {
+        const char *e = getenv("FEHT_GEMM");
+        return e && std::string(e) == "f8";
+    }();
+    return f8;
+}
+
+// GEMM columns of the e5m2 flavour, pass by pass: every value of every category gets ceil(members / 4095) columns
+// (at least one), a category never straddles two passes.  Empty result = the categories do not fit.
+std::vector<std::vector<GemmF8Column>> f8_columns(const feht_ctx *c, const std::vector<int> &cat_slot0,
+                                                  const std::vector<int> &cat_tot) {
+    std::vector<std::vector<GemmF8Column>> passes;
+    const int max_cols = gemm_f8_max_cols(), max_members = gemm_f8_max_members();
+    for (size_t k = 0; k < c->cats.size(); ++k) {
+        const Cat &cat = c->cats[k];
+        std::vector<std::vector<int32_t>> members(static_cast<size_t>(cat.n_values));
+        for (int64_t s = 0; s < c->S; ++s) {
+            const int v = cat.value_of_sample[size_t(s)];
+            if (v >= 0) members[size_t(v)].push_back(int32_t(s));
+        }
+        std::vector<GemmF8Column> cols;
+        for (int v = 0; v < cat.n_values; ++v) {
+            const std::vector<int32_t> &m = members[size_t(v)];
+            const size_t chunks = std::max<size_t>(1, (m.size() + size_t(max_members) - 1) / size_t(max_members));
+            for (size_t q = 0; q < chunks; ++q) {
+                GemmF8Column col;
+                const size_t lo = q * size_t(max_members), hi = std::min(m.size(), lo + size_t(max_members));
+                if (lo < hi) col.samples.assign(m.begin() + long(lo), m.begin() + long(hi));
+                col.slot = cat_slot0[k] + v / 2;
+                col.flags = uint8_t(v & 1);
+                if (q + 1 == chunks) {
+                    col.flags |= 2;
+                    if ((v & 1) || v == cat.n_values - 1) col.flags |= 4;
+                    if (v == cat.n_values - 1) { col.flags |= 8; col.tot_slot = cat_tot[k]; }
+                }
+                cols.push_back(std::move(col));
+            }
+        }
+        if (int(cols.size()) > max_cols) return {};
+        if (passes.empty() || int(passes.back().size() + cols.size()) > max_cols) passes.emplace_back();
+        for (GemmF8Column &col : cols) passes.back().push_back(std::move(col));
+    }
+    return passes;
 }
 // FEHT_SORT=onesweep keeps the tile-per-CTA sort for every size (A/B measurements and tests of that path)
 bool sort_engine_allows_coop() {
@@ -1211,14 +1260,51 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     bool use_gemm = false;
     // FEHT_ENGINE_GEMM is the kind::i8 GEMM, FEHT_ENGINE_GEMM_FP4 the kind::mxf4 one; AUTO takes the faster (fp4)
     const bool fp4 = c->engine == FEHT_ENGINE_GEMM_FP4 || (c->engine == FEHT_ENGINE_AUTO && gemm_auto_fp4());
-    if (c->engine == FEHT_ENGINE_GEMM || c->engine == FEHT_ENGINE_GEMM_FP4) {
+    bool f8 = c->engine == FEHT_ENGINE_GEMM_F8 || (c->engine == FEHT_ENGINE_AUTO && gemm_auto_f8());
+    if (c->engine == FEHT_ENGINE_GEMM || c->engine == FEHT_ENGINE_GEMM_FP4 || c->engine == FEHT_ENGINE_GEMM_F8) {
         if (c->snp == 1) return fail(c, FEHT_E_INVALID, "the GEMM counting engine handles binary rows only");
         if (n_cat_slots == 0) return fail(c, FEHT_E_INVALID, "the GEMM counting engine needs a category (feht_add_category)");
         use_gemm = true;
     } else if (c->engine == FEHT_ENGINE_AUTO) {
         use_gemm = c->snp != 1 && n_cat_slots >= kGemmAutoMinSlots;
     }
-    if (use_gemm && (!c->gemm_ready || c->gemm_fp4 != fp4)) {
+    if (use_gemm && f8 && !(c->gemm_ready && c->gemm_f8)) {
+        // ---- e5m2 flavour: columns, pass descriptors and baked B blocks
+        const std::vector<std::vector<GemmF8Column>> fp = f8_columns(c, cat_slot0, cat_tot);
+        if (fp.empty()) {
+            if (c->engine == FEHT_ENGINE_GEMM_F8)
+                return fail(c, FEHT_E_INVALID, "a category needs more than %d GEMM columns (one per value and 4,095 of its "
+                            "samples): use FEHT_ENGINE_GEMM_FP4", gemm_f8_max_cols());
+            f8 = false;
+        } else {
+            const int n_passes = int(fp.size());
+            const int n_stages = gemm_stage_count(c->S);
+            std::vector<unsigned char> hpass(size_t(n_passes) * gemm_f8_pass_desc_bytes());
+            std::vector<int> pad(static_cast<size_t>(n_passes));
+            size_t total = 0;
+            for (int p = 0; p < n_passes; ++p) {
+                pad[size_t(p)] = ((int(fp[size_t(p)].size()) + 15) / 16) * 16;
+                gemm_f8_fill_pass(hpass.data() + size_t(p) * gemm_f8_pass_desc_bytes(), fp[size_t(p)], pad[size_t(p)],
+                                  int64_t(total));
+                total += size_t(n_stages) * size_t(pad[size_t(p)]) * 128;
+            }
+            std::vector<uint8_t> hb(total);
+            size_t off = 0;
+            for (int p = 0; p < n_passes; ++p) {
+                gemm_f8_bake_b(fp[size_t(p)], pad[size_t(p)], c->S, hb.data() + off);
+                off += size_t(n_stages) * size_t(pad[size_t(p)]) * 128;
+            }
+            CU(c, ensure(c->gemm_b, total));
+            CU(c, ensure(c->gemm_passes, hpass.size()));
+            CU(c, cudaMemcpyAsync(c->gemm_b.p, hb.data(), total, cudaMemcpyHostToDevice, c->st));
+            CU(c, cudaMemcpyAsync(c->gemm_passes.p, hpass.data(), hpass.size(), cudaMemcpyHostToDevice, c->st));
+            CU(c, cudaStreamSynchronize(c->st));  // the host vectors die here
+            c->gemm_n_passes = n_passes;
+            c->gemm_f8 = true;
+            c->gemm_ready = true;
+        }
+    }
+    if (use_gemm && !f8 && (!c->gemm_ready || c->gemm_f8 || c->gemm_fp4 != fp4)) {
         const int per_pass = gemm_max_pairs_per_pass();
         const int n_passes = (n_cat_slots + per_pass - 1) / per_pass;
         const int n_stages = gemm_bblock_count(c->S, fp4);   // B blocks per pass
@@ -1259,9 +1345,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         CU(c, cudaStreamSynchronize(c->st));  // the host vectors die here
         c->gemm_n_passes = n_passes;
         c->gemm_fp4 = fp4;
+        c->gemm_f8 = false;
         c->gemm_ready = true;
     }
-    c->last_engine = use_gemm ? (fp4 ? FEHT_ENGINE_GEMM_FP4 : FEHT_ENGINE_GEMM) : FEHT_ENGINE_POPC;
+    c->last_engine = use_gemm ? (f8 ? FEHT_ENGINE_GEMM_F8 : (fp4 ? FEHT_ENGINE_GEMM_FP4 : FEHT_ENGINE_GEMM)) : FEHT_ENGINE_POPC;
 
     CU(c, cudaEventRecord(ev[0], c->st));
     const int n_popc_slots = use_gemm ? n_explicit : n_scanned;
@@ -1274,7 +1361,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     else
         CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_popc_slots,
                                 c->counts.p, c->num_sms, c->st, &count_launches));
-    if (use_gemm) {
+    if (use_gemm && f8) {
+        CU(c, launch_count_gemm_f8(c->plane[0], c->plane[1], c->n_units, c->W, c->S, c->gemm_b.p, c->gemm_passes.p,
+                                   c->gemm_n_passes, c->counts.p, c->num_sms, c->st, &count_launches));
+    } else if (use_gemm) {
         CU(c, launch_count_gemm(c->plane[0], c->plane[1], c->n_units, c->W, c->S, c->gemm_b.p,
                                 c->gemm_passes.p, c->gemm_n_passes, c->gemm_fp4, c->counts.p, c->num_sms, c->st,
                                 &count_launches));

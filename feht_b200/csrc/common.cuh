@@ -123,6 +123,22 @@ int gemm_stage_count(int64_t S);
 int gemm_bblock_count(int64_t S, bool fp4);
 size_t gemm_pass_desc_bytes();
 int gemm_max_pairs_per_pass();
+// e5m2 flavour (both planes in one contraction, count_gemm.cu "third flavour"): a GEMM column = one value's samples,
+// or a chunk of at most gemm_f8_max_members() of them
+struct GemmF8Column {
+    std::vector<int32_t> samples;
+    int32_t slot = 0;        // pair-slot of the value
+    int32_t tot_slot = -1;   // whole-category slot written after this column (last column of a category that has one)
+    uint8_t flags = 0;       // 1 second value of the pair-slot, 2 last column of the value, 4 last of the pair-slot, 8 last of the category
+};
+size_t gemm_f8_pass_desc_bytes();
+int gemm_f8_max_cols();
+int gemm_f8_max_members();
+void gemm_f8_fill_pass(void *dst, const std::vector<GemmF8Column> &cols, int n_pad, int64_t b_offset);
+void gemm_f8_bake_b(const std::vector<GemmF8Column> &cols, int n_pad, int64_t S, uint8_t *out);
+cudaError_t launch_count_gemm_f8(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
+                                 int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
+                                 int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
 // columns[c] = samples carrying a 1 in GEMM column c of one pass; out: [n_stages][n_pad][128] bytes
 void gemm_bake_b(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, bool fp4, uint8_t *out);
 void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_offset);

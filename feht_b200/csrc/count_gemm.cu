@@ -433,6 +433,270 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------ third flavour
+// kind::f8f6f4 with e5m2 operands: BOTH planes in ONE contraction.  value is a subset of valid, so a call is one of
+// three things -- missing, valid and absent, valid and present -- and one 8-bit operand can carry it as
+//     0.0 (0x00)        4096.0 (0x6C)        1.0 (0x3C)
+// against a one-hot B of 1.0: the FP32 accumulator of a column then holds  P + 4096 * (N - P)  exactly as long as the
+// column has at most 4,095 member samples (4095 * 4096 + 4095 = 2^24 - 1), and the epilogue splits it with a mask
+// and a shift.  Larger value groups are spread over several columns whose sums the epilogue adds; the "whole
+// category" record is the sum of the category's value records, so it needs no column of its own.  An e5m2 MMA costs
+// what an int8 MMA costs (measured: 5.41 vs 5.25 ms on config 4 with the int8 data flow), and this flavour issues
+// half of them per sample: one operand set instead of two.  What it costs instead: the expanders need two shifts, two
+// masks and two multiplies per 4 calls (the int8 / fp4 flavours: one AND per plane), 2,450 warp instructions per
+// 128-sample stage, and the kernel is bound by their issue (ALU pipe 58%, tensor pipe 22%; 16 expander warps instead
+// of 8 changed 5.01 into 4.87 ms): config 4 counts in 4.87 ms against 3.85 ms for kind::mxf4, config 5 in 5.98 against
+// 4.78.  Kept as FEHT_ENGINE_GEMM_F8 (bit-identical counts, tests/test_gpu_parity.py); AUTO does not pick it.
+// A 2-bit interleaved plane layout (missing / absent / present per call) would bring the expansion down to a shift,
+// a mask and one multiply by 0x18 (codes 0x18 = 2^-9 and 0x48 = 8 = 4096 x 2^-9) -- a layout change for every kernel.
+constexpr int kF8NMax = 128;
+constexpr int kF8BStages = 4;
+constexpr int kF8BStageBytes = kF8NMax * 128;
+constexpr int kF8ExpandWarps = 16;
+constexpr int kF8Threads = (kF8ExpandWarps + 3) * 32;
+constexpr int kF8ABufs = 4;                  // A stage buffers in TMEM: 2 x 128 accumulator + 4 x 64 operand columns
+constexpr int kF8SmemBars = kSmemB + kF8BStages * kF8BStageBytes;
+constexpr int kF8NumBars = 2 + 2 + kF8BStages * 2 + kF8ABufs * 2 + 2;
+constexpr int kF8SmemTmemPtr = kF8SmemBars + kF8NumBars * 8;
+constexpr int kF8SmemTotal = kF8SmemTmemPtr + 16 + 1024;
+
+struct GemmPassF8 {
+    int32_t n_cols;            // GEMM columns in use
+    int32_t n_pad;             // N of the MMA: multiple of 16, <= 128
+    int64_t b_offset;          // byte offset of the pass's baked B blocks: [n_stages][n_pad * 128]
+    int32_t slot[kF8NMax];     // pair-slot (index into counts) the column's value belongs to
+    int32_t tot_slot[kF8NMax]; // "whole category" slot to write after this column, or -1
+    uint8_t flags[kF8NMax];    // 1: second value of its pair-slot; 2: last column of its value; 4: last column of its
+                               // pair-slot; 8: last column of its category
+};
+
+__device__ __forceinline__ void mma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
+// 32 calls (one word of each plane) -> 8 TMEM columns of 4 e5m2 bytes; column j, byte b holds call 8*b + j (the
+// order of expand_store, so B is baked at the same K positions)
+__device__ __forceinline__ void expand_store_f8(uint32_t taddr, uint32_t v, uint32_t d) {
+    uint32_t y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t x = (v >> j) & 0x01010101u, t = (d >> j) & 0x01010101u;
+        y[j] = t * 0x6cu - x * 0x30u;     // valid: 0x6c (4096.0); valid and present: 0x3c (1.0)
+    }
+    tmem_st8(taddr, y);
+}
+
+__global__ void __launch_bounds__(kF8Threads, 1)
+count_gemm_f8_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tm_valid,
+                     const uint8_t *__restrict__ bmat, const GemmPassF8 *__restrict__ passes, int n_stages,
+                     int64_t n_rows, int n_tiles, int4 *__restrict__ counts) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char *base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t bars = base + kF8SmemBars;
+    const uint32_t a_full = bars;                          // [2]  planes landed in smem
+    const uint32_t a_empty = a_full + 2 * 8;               // [2]  expanders done with a plane buffer
+    const uint32_t b_full = a_empty + 2 * 8;               // [kF8BStages]
+    const uint32_t b_empty = b_full + kF8BStages * 8;      // [kF8BStages]
+    const uint32_t ta_full = b_empty + kF8BStages * 8;     // [kF8ABufs]  A stage written to TMEM
+    const uint32_t ta_empty = ta_full + kF8ABufs * 8;      // [kF8ABufs]  MMAs of the stage retired
+    const uint32_t acc_full = ta_empty + kF8ABufs * 8;
+    const uint32_t acc_empty = acc_full + 8;
+    volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(base_ptr + kF8SmemTmemPtr);
+    __shared__ int32_t s_slot[kF8NMax], s_tot[kF8NMax];
+    __shared__ uint8_t s_flags[kF8NMax];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GemmPassF8 *pass = passes + blockIdx.y;
+    const int n_pad = pass->n_pad, n_cols = pass->n_cols;
+    const uint32_t b_bytes = uint32_t(n_pad) * 128u;
+    for (int i = threadIdx.x; i < kF8NMax; i += blockDim.x) {
+        s_slot[i] = pass->slot[i];
+        s_tot[i] = pass->tot_slot[i];
+        s_flags[i] = pass->flags[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(a_full + i * 8, 1);
+            mbar_init(a_empty + i * 8, kF8ExpandWarps);
+        }
+        for (int i = 0; i < kF8ABufs; ++i) {
+            mbar_init(ta_full + i * 8, kF8ExpandWarps);
+            mbar_init(ta_empty + i * 8, 1);
+        }
+        for (int i = 0; i < kF8BStages; ++i) {
+            mbar_init(b_full + i * 8, 1);
+            mbar_init(b_empty + i * 8, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, kExpandWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kF8ExpandWarps + 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(const_cast<uint32_t *>(tmem_ptr_smem))), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int n_chunks = (n_stages + kStagesPerChunk - 1) / kStagesPerChunk;
+    constexpr int kABuf = 64;                    // TMEM columns of one A stage buffer: 2 M tiles x 32
+    constexpr uint32_t kAcc = 0, kA = 256;
+
+    if (warp < kF8ExpandWarps) {
+        // =============================================== expanders (16 warps: two per 32 marker rows, each taking two of
+        // the four words of a stage -- the e5m2 bytes cost ~6 instructions per 4 calls, three times the int8
+        // flavour's, and 8 warps could not keep up with the MMAs) + epilogue (the first 8 of them): thread = marker row
+        const int r = threadIdx.x & 255;
+        const int half = threadIdx.x >> 8;
+        const int mt = r >> 7;
+        const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+        const uint32_t row_off = uint32_t(r) * kChunkBytes;
+        const uint32_t sw = uint32_t(r & 7);
+        uint32_t chunk_ctr = 0, stage_ctr = 0, tile_ctr = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
+            for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+                const uint32_t cb = chunk_ctr & 1;
+                mbar_wait(a_full + cb * 8, (chunk_ctr >> 1) & 1);
+                const unsigned char *pv = base_ptr + kSmemPlanes + (cb * 2 + 0) * kPlaneTileBytes + row_off;
+                const unsigned char *pd = base_ptr + kSmemPlanes + (cb * 2 + 1) * kPlaneTileBytes + row_off;
+                const int st_n = min(kStagesPerChunk, n_stages - ch * kStagesPerChunk);
+                for (int st = 0; st < st_n; ++st, ++stage_ctr) {
+                    const uint32_t phys = (uint32_t(st) ^ sw) << 4;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(pv + phys);
+                    const uint4 d = *reinterpret_cast<const uint4 *>(pd + phys);
+                    const uint32_t tb = stage_ctr % kF8ABufs;
+                    mbar_wait(ta_empty + tb * 8, ((stage_ctr / kF8ABufs) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + lane_addr + kA + tb * kABuf + mt * 32 + half * 16;
+                    expand_store_f8(ta + 0, half ? v.z : v.x, half ? d.z : d.x);
+                    expand_store_f8(ta + 8, half ? v.w : v.y, half ? d.w : d.y);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ta_full + tb * 8);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_empty + cb * 8);
+            }
+            // ---- epilogue: P + 4096 * (N - P) per column -> pair-slot records, whole-category records
+            if (half) continue;
+            mbar_wait(acc_full, tile_ctr & 1);
+            tc_fence_after();
+            const int64_t row = int64_t(tile) * kTileRows + r;
+            const bool live = row < n_rows;
+            const uint32_t acc = tmem_base + lane_addr + kAcc + mt * kF8NMax;
+            int aP = 0, aN = 0, p0 = 0, n0 = 0, p1 = 0, n1 = 0, tP = 0, tN = 0;
+            for (int c = 0; c < n_cols; ++c) {
+                const uint32_t x = tmem_ld1(acc + c);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int vv = __float2int_rn(__uint_as_float(x));
+                aP += vv & 4095;
+                aN += (vv & 4095) + (vv >> 12);
+                const uint32_t f = s_flags[c];
+                if (f & 2u) {
+                    if (f & 1u) { p1 = aP; n1 = aN; } else { p0 = aP; n0 = aN; }
+                    tP += aP; tN += aN;
+                    aP = 0; aN = 0;
+                }
+                if (f & 4u) {
+                    if (live) counts[size_t(s_slot[c]) * size_t(n_rows) + size_t(row)] = make_int4(p0, n0, p1, n1);
+                    p0 = n0 = p1 = n1 = 0;
+                }
+                if (f & 8u) {
+                    const int ts = s_tot[c];
+                    if (ts >= 0 && live) counts[size_t(ts) * size_t(n_rows) + size_t(row)] = make_int4(tP, tN, 0, 0);
+                    tP = 0; tN = 0;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    } else if (warp == kF8ExpandWarps) {
+        // =============================================== TMA producer: bit-plane boxes
+        if (lane == 0) {
+            uint32_t chunk_ctr = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+                    const uint32_t cb = chunk_ctr & 1;
+                    mbar_wait(a_empty + cb * 8, ((chunk_ctr >> 1) & 1) ^ 1);
+                    mbar_expect_tx(a_full + cb * 8, 2u * kPlaneTileBytes);
+                    tma_load_2d(base + kSmemPlanes + (cb * 2 + 0) * kPlaneTileBytes, &tm_value,
+                                ch * kChunkBytes, tile * kTileRows, a_full + cb * 8);
+                    tma_load_2d(base + kSmemPlanes + (cb * 2 + 1) * kPlaneTileBytes, &tm_valid,
+                                ch * kChunkBytes, tile * kTileRows, a_full + cb * 8);
+                }
+            }
+        }
+    } else if (warp == kF8ExpandWarps + 1) {
+        // =============================================== bulk-copy producer: baked one-hot B blocks
+        if (lane == 0) {
+            uint32_t stage_ctr = 0;
+            const uint8_t *bsrc = bmat + pass->b_offset;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                    const uint32_t bs = stage_ctr % kF8BStages;
+                    mbar_wait(b_empty + bs * 8, ((stage_ctr / kF8BStages) & 1) ^ 1);
+                    mbar_expect_tx(b_full + bs * 8, b_bytes);
+                    bulk_load_1d(base + kSmemB + bs * kF8BStageBytes, bsrc + size_t(s) * b_bytes, b_bytes,
+                                 b_full + bs * 8);
+                }
+            }
+        }
+    } else {
+        // =============================================== MMA issuer
+        if (lane == 0) {
+            // D f32, A / B e5m2, both K-major, N = n_pad, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n_pad >> 3) << 17) |
+                                   (uint32_t(128 >> 4) << 24);
+            uint32_t stage_ctr = 0, tile_ctr = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
+                mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
+                tc_fence_after();
+                for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                    const uint32_t tb = stage_ctr % kF8ABufs;
+                    const uint32_t bs = stage_ctr % kF8BStages;
+                    mbar_wait(ta_full + tb * 8, (stage_ctr / kF8ABufs) & 1);
+                    mbar_wait(b_full + bs * 8, (stage_ctr / kF8BStages) & 1);
+                    tc_fence_after();
+                    const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kF8BStageBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                        for (int m = 0; m < 2; ++m)
+                            mma_f8_ts(tmem_base + kAcc + m * kF8NMax, tmem_base + kA + tb * kABuf + m * 32 + ks * 8,
+                                      bdesc + uint64_t(ks * 2), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(ta_empty + tb * 8);
+                    tc_commit(b_empty + bs * 8);
+                }
+                tc_commit(acc_full);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kF8ExpandWarps + 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+                     : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -514,6 +778,61 @@ void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_
     p.n_pad = n_pad;
     p.b_offset = b_offset;
     std::memcpy(dst, &p, sizeof(p));
+}
+
+// ---- e5m2 flavour: one GEMM column per (value, chunk of <= 4095 member samples)
+size_t gemm_f8_pass_desc_bytes() { return sizeof(GemmPassF8); }
+int gemm_f8_max_cols() { return kF8NMax; }
+int gemm_f8_max_members() { return 4095; }
+
+void gemm_f8_fill_pass(void *dst, const std::vector<GemmF8Column> &cols, int n_pad, int64_t b_offset) {
+    GemmPassF8 p{};
+    p.n_cols = int(cols.size());
+    p.n_pad = n_pad;
+    p.b_offset = b_offset;
+    for (int i = 0; i < kF8NMax; ++i) { p.slot[i] = 0; p.tot_slot[i] = -1; p.flags[i] = 0; }
+    for (size_t i = 0; i < cols.size(); ++i) {
+        p.slot[i] = cols[i].slot;
+        p.tot_slot[i] = cols[i].tot_slot;
+        p.flags[i] = cols[i].flags;
+    }
+    std::memcpy(dst, &p, sizeof(p));
+}
+
+// B blocks [n_stages][n_pad][128]: e5m2 1.0 (0x3c) where column n has sample s, at the K position expand_store_f8
+// gives that sample (the int8 flavour's order)
+void gemm_f8_bake_b(const std::vector<GemmF8Column> &cols, int n_pad, int64_t S, uint8_t *out) {
+    const int n_blocks = gemm_stage_count(S);
+    std::memset(out, 0, size_t(n_blocks) * size_t(n_pad) * 128);
+    for (size_t n = 0; n < cols.size(); ++n)
+        for (int32_t s : cols[n].samples) {
+            const int64_t g = s / kStageSamples;
+            const int w = int(s % kStageSamples);
+            const int i = w >> 5, bit = w & 31;
+            const int b = bit >> 3, j = bit & 7;
+            const int kk = 32 * i + 4 * j + b;
+            out[size_t(g) * size_t(n_pad) * 128 + n * 128 + size_t((((kk >> 4) ^ int(n & 7)) << 4) + (kk & 15))] = 0x3c;
+        }
+}
+
+cudaError_t launch_count_gemm_f8(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
+                                 int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
+                                 int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+    if (n_rows == 0 || n_passes == 0) return cudaSuccess;
+    CUtensorMap tm_value, tm_valid;
+    if (!make_plane_map(&tm_value, d_value, n_rows, W) || !make_plane_map(&tm_valid, d_valid, n_rows, W))
+        return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(count_gemm_f8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF8SmemTotal);
+    if (e != cudaSuccess) return e;
+    const int n_tiles = int((n_rows + kTileRows - 1) / kTileRows);
+    int gx = num_sms / n_passes;
+    if (gx < 1) gx = 1;
+    if (gx > n_tiles) gx = n_tiles;
+    count_gemm_f8_kernel<<<dim3(unsigned(gx), unsigned(n_passes)), kF8Threads, kF8SmemTotal, st>>>(
+        tm_value, tm_valid, d_bmat, static_cast<const GemmPassF8 *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
+        d_counts);
+    if (launches) ++*launches;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,

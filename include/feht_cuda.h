@@ -191,8 +191,10 @@ int     feht_comparison_info(const feht_ctx *ctx, int64_t c, int32_t *kind, int3
                              int32_t *v1, int32_t *v2);
 
 /* Counting engine: 0 auto, 1 popcount scan (K1), 2 int8 tcgen05 GEMM (K2; categories only), 3 the same GEMM
- * with 4-bit operands (tcgen05 kind::mxf4, unit scales, FP32 accumulation: exact, half the operand bytes). */
-enum { FEHT_ENGINE_AUTO = 0, FEHT_ENGINE_POPC = 1, FEHT_ENGINE_GEMM = 2, FEHT_ENGINE_GEMM_FP4 = 3 };
+ * with 4-bit operands (tcgen05 kind::mxf4, unit scales, FP32 accumulation: exact, half the operand bytes), 4 both
+ * planes in one e5m2 GEMM (kind::f8f6f4: a call is 0, 1 or 4096, the FP32 sum P + 4096 (N - P) is exact for columns of
+ * at most 4,095 samples; larger value groups take several columns; a category must fit 128 columns). */
+enum { FEHT_ENGINE_AUTO = 0, FEHT_ENGINE_POPC = 1, FEHT_ENGINE_GEMM = 2, FEHT_ENGINE_GEMM_FP4 = 3, FEHT_ENGINE_GEMM_F8 = 4 };
 int feht_set_count_engine(feht_ctx *ctx, int engine);
 
 /* ---------------------------------------------------------------- run ---- */

@@ -312,16 +312,17 @@ def test_category_api_equals_explicit_comparisons(ctx):
         assert kinds.count(2) == (n_values if n_values > 2 else 0)
 
 
-@pytest.mark.parametrize("n_samples,n_values", [(130, 3), (1000, 7), (2600, 70), (5000, 50)])
-@pytest.mark.parametrize("engine", [capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4])
+@pytest.mark.parametrize("n_samples,n_values", [(130, 3), (1000, 7), (2600, 70), (5000, 50), (9100, 2)])
+@pytest.mark.parametrize("engine", [capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_GEMM_F8])
 def test_gemm_engine_counts_equal_oracle(ctx, n_samples, n_values, engine):
-    """K2 (tcgen05 GEMM, kind::i8 and kind::mxf4 flavours) against the oracle: same pair / one-vs-rest tables, bit-exact, for one and
-    for several passes (70 values = 36 pair-slots > 32 per pass), with an explicit comparison mixed in
-    (K1 counts that one) and samples that lack the category (-1)."""
+    """K2 (tcgen05 GEMM: kind::i8, kind::mxf4, and the one-GEMM e5m2 flavour) against the oracle: same pair / one-vs-rest
+    tables, bit-exact, for one and for several passes (70 values = 36 pair-slots > 32 per pass), with an explicit
+    comparison mixed in (K1 counts that one), samples that lack the category (-1), and value groups of more than
+    4,095 samples (9100 / 2: the e5m2 flavour spreads them over two columns each)."""
     rng = np.random.default_rng(400 + n_values)
     n_rows = 300 if n_values < 50 else 140
     cells = _random_chars(rng, n_rows, n_samples)
-    vos = rng.integers(-1, n_values, size=n_samples).astype(np.int32)
+    vos = rng.integers(-1 if n_values > 2 else 0, n_values, size=n_samples).astype(np.int32)
     rank = rng.permutation(n_rows).astype(np.int32)
     ctx.set_samples(n_samples)
     ctx.add_rows_chars(cells, rank)
@@ -332,7 +333,7 @@ def test_gemm_engine_counts_equal_oracle(ctx, n_samples, n_values, engine):
     for i in range(n_values):
         for j in range(i + 1, n_values):
             comps.append((np.flatnonzero(vos == i), np.flatnonzero(vos == j)))
-    for v in range(n_values):
+    for v in range(n_values if n_values > 2 else 0):        # one-vs-rest only for more than two values (Comparison.hs:329)
         comps.append((np.flatnonzero(vos == v), np.flatnonzero((vos >= 0) & (vos != v))))
     assert ctx.num_comparisons == len(comps)
     ctx.set_count_engine(engine)
@@ -363,16 +364,49 @@ def test_gemm_and_popcount_engines_agree_on_two_categories(ctx):
     ctx.add_category(rng.integers(0, 5, size=n_samples).astype(np.int32), 5)
     ctx.add_category(rng.integers(-1, 12, size=n_samples).astype(np.int32), 12)
     res = {}
-    for eng in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_AUTO):
+    for eng in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_GEMM_F8, capi.ENGINE_AUTO):
         ctx.set_count_engine(eng)
         ctx.run(capi.CORRECTION_NONE, 0.0)
         res[eng] = [ctx.fetch(ci) for ci in range(ctx.num_comparisons)]
     assert ctx.timings()["engine"] == capi.ENGINE_GEMM_FP4   # AUTO: 3+1+6+1 = 11 pair-slots >= 8 -> the 4-bit GEMM
     for ci in range(ctx.num_comparisons):
         for k in ("row", "goa", "gob", "gta", "gtb", "p", "ratio"):
-            a, b, c, d = (res[e][ci][k] for e in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_AUTO))
+            a, b, c, d, e8 = (res[e][ci][k] for e in (capi.ENGINE_POPC, capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_AUTO, capi.ENGINE_GEMM_F8))
             same = (a == b) | ((a != a) & (b != b))
             assert same.all() and ((b == c) | ((b != b) & (c != c))).all() and ((c == d) | ((c != c) & (d != d))).all(), (ci, k)
+            assert ((d == e8) | ((d != d) & (e8 != e8))).all(), (ci, k)
+
+
+def test_gemm_f8_two_passes_and_fallback(ctx):
+    """The e5m2 flavour keeps a category inside one pass of 128 columns: two 70-value categories make two passes;
+    a 130-value category does not fit (asking for the flavour is an error; AUTO uses the 4-bit GEMM anyway)."""
+    rng = np.random.default_rng(412)
+    n_samples, n_rows = 2600, 333
+    cells = _random_chars(rng, n_rows, n_samples)
+    ctx.set_samples(n_samples)
+    ctx.add_rows_chars(cells)
+    ctx.add_category(rng.integers(0, 70, size=n_samples).astype(np.int32), 70)
+    ctx.add_category(rng.integers(-1, 70, size=n_samples).astype(np.int32), 70)
+    res = {}
+    for eng in (capi.ENGINE_GEMM_FP4, capi.ENGINE_GEMM_F8):
+        ctx.set_count_engine(eng)
+        ctx.run(capi.CORRECTION_NONE, 0.3)
+        assert ctx.timings()["engine"] == eng
+        res[eng] = [ctx.fetch(ci) for ci in range(0, ctx.num_comparisons, 37)]
+    for a, b in zip(res[capi.ENGINE_GEMM_FP4], res[capi.ENGINE_GEMM_F8]):
+        for k in ("row", "goa", "gob", "gta", "gtb", "ratio"):
+            assert (a[k] == b[k]).all(), k
+    ctx.set_samples(n_samples)
+    ctx.add_rows_chars(cells)
+    ctx.clear_comparisons()
+    ctx.add_category(rng.integers(0, 130, size=n_samples).astype(np.int32), 130)
+    ctx.set_count_engine(capi.ENGINE_AUTO)
+    ctx.run(capi.CORRECTION_NONE, 0.5)
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM_FP4
+    ctx.set_count_engine(capi.ENGINE_GEMM_F8)
+    with pytest.raises(capi.FehtError):
+        ctx.run(capi.CORRECTION_NONE, 0.5)
+    ctx.set_count_engine(capi.ENGINE_AUTO)
 
 
 def test_gemm_engine_rejects_snp_and_explicit_only(ctx):
@@ -518,6 +552,27 @@ def test_text_upload_equals_host_parsed_rows(ctx, snp, delim):
         want = [ctx.read_plane(k, 0, n_lines) for k in range(3 if snp else 2)]
         for g, w in zip(got, want):
             assert (g == w).all()
+
+
+def test_text_upload_randomised_shapes(ctx):
+    """60 random files (1..3000 lines, 1..700 columns, either delimiter, binary and SNP, with and without CR):
+    planes of the device text path against the character rows."""
+    rng = np.random.default_rng(2024)
+    for it in range(60):
+        snp = bool(rng.integers(0, 2))
+        delim = "\t" if rng.integers(0, 2) else ","
+        n_lines = int(rng.choice([1, 2, 31, 32, 33, 257, 1000, 3000]))
+        n_cols = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 300, 700]))
+        text, _names, rows = _random_table_text(rng, n_lines, n_cols, delim, snp, crlf=bool(rng.integers(0, 2)))
+        ctx.set_samples(n_cols)
+        begin, name_len = ctx.add_rows_text(text, delim, snp)
+        assert len(begin) == n_lines
+        got = [ctx.read_plane(k, 0, n_lines) for k in range(3 if snp else 2)]
+        ctx.set_samples(n_cols)
+        (ctx.add_snp_chars if snp else ctx.add_rows_chars)(rows)
+        want = [ctx.read_plane(k, 0, n_lines) for k in range(3 if snp else 2)]
+        for k, (g, w) in enumerate(zip(got, want)):
+            assert (g == w).all(), (it, snp, delim, n_lines, n_cols, k)
 
 
 def test_text_upload_errors_and_name_ranks(ctx):

@@ -16,7 +16,7 @@ from helpers import make_spec  # noqa: E402
 
 
 def run(cfg, rows, engine, steps, ratio_filter=None, samples=None):
-    eng = {"popc": capi.ENGINE_POPC, "gemm": capi.ENGINE_GEMM, "fp4": capi.ENGINE_GEMM_FP4, "auto": capi.ENGINE_AUTO}[engine]
+    eng = {"popc": capi.ENGINE_POPC, "gemm": capi.ENGINE_GEMM, "fp4": capi.ENGINE_GEMM_FP4, "f8": capi.ENGINE_GEMM_F8, "auto": capi.ENGINE_AUTO}[engine]
     with capi.Context(0) as ctx:
         if cfg == "c3":      # SNP 500k sites x 10k, one 4-value category -> 10 comparisons x 2M allele rows
             S, snp, rf = 10_000, True, 0.0
@@ -72,7 +72,7 @@ def run(cfg, rows, engine, steps, ratio_filter=None, samples=None):
                "tests_per_s_device": tests / (avg["total_ms"] * 1e-3),
                "count_gbs": avg["count_bytes"] / (avg["count_ms"] * 1e-3) / 1e9,
                "launches": avg["launches"]}
-        if t["engine"] in (capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4):
+        if t["engine"] in (capi.ENGINE_GEMM, capi.ENGINE_GEMM_FP4, capi.ENGINE_GEMM_F8):
             npad = 0
             for vos, nv in cats:
                 npad += 2 * ((nv + 1) // 2) + (2 if nv > 2 else 0)
