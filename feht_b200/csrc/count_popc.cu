@@ -18,6 +18,8 @@
 // the kernel reads 2 * 8 * W (W = that, rounded up to even) and writes 16 B per (row, pair-slot).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace feht {
@@ -348,34 +350,46 @@ constexpr int kRingMaxStages = 64;
 
 // Every warp is consumer AND producer: it claims the next tile of the CTA in ring order (a shared counter), waits
 // for the tile's stage, counts, and then refills that very stage with the tile n_stages further on (lane 0:
-// expect_tx + three bulk copies), so there is no producer warp and no `empty` barrier.
-// A tile is kiter * (32 >> LOGL) consecutive sites: three contiguous blocks (hi, lo, valid), one bulk copy each.
-// The L lane partials of the 8 * CB counts are packed two per register (counts <= S < 65536) and combined by a
-// reduce-scatter over the lanes of a site (4 * CB - 1 + ... shuffles instead of 8 * CB * log2 L); the packed totals
-// go through a few words of shared memory so that four lanes write one allele row each.
-template <int CB, int LOGL, int NW>
+// expect_tx + one bulk copy per plane), so there is no producer warp and no `empty` barrier.
+// A tile is kiter * (32 >> LOGL) consecutive rows (SNP: sites): one contiguous block per plane.
+// SNP = true: planes (hi, lo, valid), four counts per mask (H, Lo, T, N), CB <= 2 pair-slots, four allele rows out.
+// SNP = false: planes (value, valid), two counts per mask (P, N), CB <= 4 pair-slots -- the path of the few-comparison
+// scan when several pair-slots share one read of the planes (16 count streams make the register-staged kernel
+// latency-bound: 0.65 ms for 4 pair-slots on config 2's matrix against 0.21 ms for one).
+// The L lane partials of the NP * 2 counts are packed two per register (counts <= S < 65536) and combined by a
+// reduce-scatter over the lanes of a row (NP - 1 + ... shuffles instead of 2 * NP * log2 L); the packed totals go
+// through a few words of shared memory so that a few lanes write one record each.
+template <bool SNP, int CB, int LOGL, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-count_popc_snp_ring_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict__ valid,
-                           const uint4 *__restrict__ lo, int64_t n_sites, int w4, int w4pad, int kiter,
-                           int n_stages, int one, const uint4 *__restrict__ masks, int4 *__restrict__ counts) {
+count_popc_ring_kernel(const uint4 *__restrict__ pl0, const uint4 *__restrict__ valid,
+                       const uint4 *__restrict__ pl2, int64_t n_units, int w4, int w4pad, int kiter,
+                       int n_stages, int one, const uint4 *__restrict__ masks, int4 *__restrict__ counts) {
     constexpr int L = 1 << LOGL;
     constexpr int RPW = 32 >> LOGL;
-    constexpr int NP = 4 * CB;          // packed values per site: [c][q], low half = first mask, high = second
+    constexpr int NPL = SNP ? 3 : 2;    // planes
+    constexpr int NQ = SNP ? 4 : 2;     // counts per mask
+    constexpr int NP = NQ * CB;         // packed values per unit: [c][q], low half = first mask, high = second
+    constexpr int LOGNP = NP == 2 ? 1 : (NP == 4 ? 2 : 3);
+    static_assert(NP == 2 || NP == 4 || NP == 8, "2, 4 or 8 packed counts per row");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;                          // masks
-    __shared__ __align__(8) uint64_t full_bar[kRingMaxStages];     // producer -> consumer (tx bytes)
+    __shared__ __align__(8) uint64_t full_bar[kRingMaxStages];     // bulk copies -> consumers (tx bytes)
     __shared__ uint32_t red[NW][RPW][NP];
     __shared__ uint32_t next_tile;                                 // tiles are claimed in ring order
+    // seen[s] = number of times stage s has been handed back (= the phase of full_bar[s] that is armed or about to
+    // be).  A parity wait only tells the current phase from the one before it, and tiles are claimed without
+    // regard to what has landed: a warp could claim tile it + n_stages while the data of tile it (same stage) is
+    // still in flight and its wait on the opposite parity would return at once.  So the claimer of a tile first
+    // waits until the stage's previous tile has been consumed.
+    __shared__ volatile uint32_t seen[kRingMaxStages];
     uint4 *sm_masks = reinterpret_cast<uint4 *>(smem_raw);         // [CB][2][w4pad]
-    const int tile_sites = kiter * RPW;
-    const uint32_t plane_cols = uint32_t(tile_sites) * uint32_t(w4);   // uint4 per plane block
-    uint4 *ring = sm_masks + size_t(CB) * 2 * w4pad;               // [stage][3][tile_sites][w4]
+    const int tile_units = kiter * RPW;
+    const uint32_t plane_cols = uint32_t(tile_units) * uint32_t(w4);   // uint4 per plane block
+    uint4 *ring = sm_masks + size_t(CB) * 2 * w4pad;               // [stage][NPL][tile_units][w4]
 
     const int slot0 = blockIdx.y * CB;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < n_stages; ++s) {
-            mbar_init(&full_bar[s], 1);
-        }
+        for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); seen[s] = 0u; }
         next_tile = 0;
     }
     // initialises `bar`, fences the inits, __syncthreads, copies the masks, all threads wait
@@ -384,88 +398,96 @@ count_popc_snp_ring_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int64_t n_tiles = (n_sites + tile_sites - 1) / tile_sites;
+    const int64_t n_tiles = (n_units + tile_units - 1) / tile_units;
     const uint32_t ust = uint32_t(n_stages);
 
-    // fills stage `it % n_stages` with tile `it` of this CTA (one lane; the stage must be free)
+    // fills stage `it % n_stages` with tile `it` of this CTA (one lane; the stage must be free).
+    // Stage layout: SNP hi, lo, valid; binary value, valid.
     auto fill = [&](uint32_t it) {
         const int64_t tile = int64_t(blockIdx.x) + int64_t(it) * gridDim.x;
         if (tile >= n_tiles) return;
         const uint32_t s = it % ust;
-        const int64_t site0 = tile * tile_sites;
-        const int64_t ns = (n_sites - site0 < tile_sites) ? (n_sites - site0) : tile_sites;
-        const uint32_t bytes = uint32_t(ns) * uint32_t(w4) * 16u;
+        const int64_t u0 = tile * tile_units;
+        const int64_t nu = (n_units - u0 < tile_units) ? (n_units - u0) : tile_units;
+        const uint32_t bytes = uint32_t(nu) * uint32_t(w4) * 16u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full_bar[s])),
-                     "r"(3u * bytes)
+                     "r"(uint32_t(NPL) * bytes)
                      : "memory");
-        uint4 *dst = ring + size_t(s) * 3 * plane_cols;
-        const size_t goff = size_t(site0) * size_t(w4);
-        bulk_g2s(dst, hi + goff, bytes, &full_bar[s]);
-        bulk_g2s(dst + plane_cols, lo + goff, bytes, &full_bar[s]);
-        bulk_g2s(dst + 2 * size_t(plane_cols), valid + goff, bytes, &full_bar[s]);
+        uint4 *dst = ring + size_t(s) * NPL * plane_cols;
+        const size_t goff = size_t(u0) * size_t(w4);
+        bulk_g2s(dst, pl0 + goff, bytes, &full_bar[s]);
+        if (SNP) bulk_g2s(dst + plane_cols, pl2 + goff, bytes, &full_bar[s]);
+        bulk_g2s(dst + size_t(NPL - 1) * plane_cols, valid + goff, bytes, &full_bar[s]);
     };
     // prologue: the first n_stages tiles, spread over the warps
     if (lane == 0)
         for (uint32_t it = uint32_t(warp); it < ust; it += NW) fill(it);
 
-    // ---- consumers
     const int sub = lane & (L - 1);
     const int rsub = lane >> LOGL;
-    const int64_t n_rows = 4 * n_sites;
+    const int64_t n_rows = (SNP ? 4 : 1) * n_units;
     for (;;) {
-        // the next tile of this CTA in ring order goes to whichever warp is free first, so stages come back to the
-        // producer in (nearly) the order it filled them
+        // the next tile of this CTA in ring order goes to whichever warp is free first, so stages come back in
+        // (nearly) the order they were filled
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(&next_tile, 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         const int64_t tile = int64_t(blockIdx.x) + int64_t(it) * gridDim.x;
         if (tile >= n_tiles) break;
-        const uint32_t s = it % ust;
-        mbar_wait(&full_bar[s], (it / ust) & 1u);
-        const int64_t site0 = tile * tile_sites;
-        const int ns = int((n_sites - site0 < tile_sites) ? (n_sites - site0) : tile_sites);
-        const uint4 *ph = ring + size_t(s) * 3 * plane_cols;
-        const uint4 *pl = ph + plane_cols;
-        const uint4 *pv = pl + plane_cols;
-        for (int g = 0; g < ns; g += RPW) {
-            const int ls = g + rsub;          // site inside the tile
-            const bool ok = ls < ns;
-            // st[c][mask][0..3] = H, Lo, T, N
-            CountStream st[CB][2][4];
+        const uint32_t s = it % ust, phase = it / ust;
+        if (lane == 0)
+            while (seen[s] < phase) {}
+        __syncwarp();
+        mbar_wait(&full_bar[s], phase & 1u);
+        const int64_t u0 = tile * tile_units;
+        const int nu = int((n_units - u0 < tile_units) ? (n_units - u0) : tile_units);
+        const uint4 *p0 = ring + size_t(s) * NPL * plane_cols;      // SNP: hi, binary: value
+        const uint4 *p1 = p0 + plane_cols;                          // SNP: lo (binary: valid)
+        const uint4 *pv = p0 + size_t(NPL - 1) * plane_cols;        // valid
+        for (int g = 0; g < nu; g += RPW) {
+            const int ls = g + rsub;          // unit inside the tile
+            const bool ok = ls < nu;
+            // SNP: st[c][mask][0..3] = H, Lo, T, N; binary: st[c][mask][0..1] = P, N
+            CountStream st[CB][2][NQ];
 #pragma unroll
             for (int c = 0; c < CB; ++c)
 #pragma unroll
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) st[c][m][q].reset();
+                    for (int q = 0; q < NQ; ++q) st[c][m][q].reset();
             if (ok) {
                 const uint32_t base = uint32_t(ls) * uint32_t(w4);
 #pragma unroll 2
                 for (int col = sub; col < w4; col += L) {
-                    // hi and lo are subsets of valid (every producer of SNP planes guarantees it, capi.cu)
+                    // hi / lo / value are subsets of valid (every producer of the planes guarantees it, capi.cu)
                     const uint4 v = pv[base + col];
-                    const uint4 h = ph[base + col];
-                    const uint4 l = pl[base + col];
-                    const uint4 t = make_uint4(h.x & l.x, h.y & l.y, h.z & l.z, h.w & l.w);
+                    const uint4 h = p0[base + col];
+                    uint4 l = h, t = h;
+                    if (SNP) {
+                        l = p1[base + col];
+                        t = make_uint4(h.x & l.x, h.y & l.y, h.z & l.z, h.w & l.w);
+                    }
 #pragma unroll
                     for (int c = 0; c < CB; ++c)
 #pragma unroll
                         for (int m = 0; m < 2; ++m) {
                             const uint4 mk = sm_masks[(c * 2 + m) * w4pad + col];
                             st[c][m][0].add_fma(h, mk, one);
-                            st[c][m][1].add_fma(l, mk, one);
-                            st[c][m][2].add_fma(t, mk, one);
-                            st[c][m][3].add_fma(v, mk, one);
+                            if (SNP) {
+                                st[c][m][1].add_fma(l, mk, one);
+                                st[c][m][2].add_fma(t, mk, one);
+                            }
+                            st[c][m][NQ - 1].add_fma(v, mk, one);
                         }
                 }
             }
-            // packed lane partials, then reduce-scatter over the L lanes of the site
+            // packed lane partials, then reduce-scatter over the L lanes of the unit
             uint32_t pk[NP];
 #pragma unroll
             for (int c = 0; c < CB; ++c)
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    pk[c * 4 + q] = uint32_t(st[c][0][q].total()) | (uint32_t(st[c][1][q].total()) << 16);
+                for (int q = 0; q < NQ; ++q)
+                    pk[c * NQ + q] = uint32_t(st[c][0][q].total()) | (uint32_t(st[c][1][q].total()) << 16);
             int n = NP;
 #pragma unroll
             for (int o = L >> 1; o > 0; o >>= 1) {
@@ -484,9 +506,9 @@ count_popc_snp_ring_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict
                     pk[0] += __shfl_xor_sync(0xffffffffu, pk[0], o);
                 }
             }
-            // lane `sub` now holds packed values [first, first + n) of its site
+            // lane `sub` now holds packed values [first, first + n) of its unit
             {
-                constexpr int kSteps = (LOGL < (CB == 1 ? 2 : 3)) ? LOGL : (CB == 1 ? 2 : 3);   // scatter steps taken
+                constexpr int kSteps = LOGL < LOGNP ? LOGL : LOGNP;   // scatter steps taken
                 const int first = (sub >> (LOGL - kSteps)) * (NP >> kSteps);
                 const bool writer = (sub & ((1 << (LOGL - kSteps)) - 1)) == 0;
                 if (writer) {
@@ -495,31 +517,44 @@ count_popc_snp_ring_kernel(const uint4 *__restrict__ hi, const uint4 *__restrict
                 }
             }
             __syncwarp();
-            for (int r = sub; r < 4 * CB; r += L) {
-                const int c = r >> 2, row = r & 3;
-                if (ok) {
-                    const uint32_t H = red[warp][rsub][c * 4 + 0], Lo = red[warp][rsub][c * 4 + 1],
-                                   T = red[warp][rsub][c * 4 + 2], N = red[warp][rsub][c * 4 + 3];
-                    // packed arithmetic would borrow across the halves: unpack first
-                    const int n1 = int(N & 0xffffu), n2 = int(N >> 16);
-                    const int h1 = int(H & 0xffffu), h2 = int(H >> 16);
-                    const int l1 = int(Lo & 0xffffu), l2 = int(Lo >> 16);
-                    const int t1 = int(T & 0xffffu), t2 = int(T >> 16);
-                    int x1, x2;
-                    if (row == 0) { x1 = n1 - h1 - l1 + t1; x2 = n2 - h2 - l2 + t2; }        // _a
-                    else if (row == 1) { x1 = t1; x2 = t2; }                                  // _t
-                    else if (row == 2) { x1 = l1 - t1; x2 = l2 - t2; }                        // _c
-                    else { x1 = h1 - t1; x2 = h2 - t2; }                                      // _g
-                    counts[size_t(slot0 + c) * n_rows + 4 * (site0 + ls) + row] = make_int4(x1, n1, x2, n2);
+            if (SNP) {
+                for (int r = sub; r < 4 * CB; r += L) {
+                    const int c = r >> 2, row = r & 3;
+                    if (ok) {
+                        const uint32_t H = red[warp][rsub][c * 4 + 0], Lo = red[warp][rsub][c * 4 + 1],
+                                       T = red[warp][rsub][c * 4 + 2], N = red[warp][rsub][c * 4 + 3];
+                        // packed arithmetic would borrow across the halves: unpack first
+                        const int n1 = int(N & 0xffffu), n2 = int(N >> 16);
+                        const int h1 = int(H & 0xffffu), h2 = int(H >> 16);
+                        const int l1 = int(Lo & 0xffffu), l2 = int(Lo >> 16);
+                        const int t1 = int(T & 0xffffu), t2 = int(T >> 16);
+                        int x1, x2;
+                        if (row == 0) { x1 = n1 - h1 - l1 + t1; x2 = n2 - h2 - l2 + t2; }        // _a
+                        else if (row == 1) { x1 = t1; x2 = t2; }                                  // _t
+                        else if (row == 2) { x1 = l1 - t1; x2 = l2 - t2; }                        // _c
+                        else { x1 = h1 - t1; x2 = h2 - t2; }                                      // _g
+                        counts[size_t(slot0 + c) * n_rows + 4 * (u0 + ls) + row] = make_int4(x1, n1, x2, n2);
+                    }
+                }
+            } else {
+                for (int c = sub; c < CB; c += L) {
+                    if (ok) {
+                        const uint32_t P = red[warp][rsub][c * 2 + 0], N = red[warp][rsub][c * 2 + 1];
+                        counts[size_t(slot0 + c) * n_rows + (u0 + ls)] =
+                            make_int4(int(P & 0xffffu), int(N & 0xffffu), int(P >> 16), int(N >> 16));
+                    }
                 }
             }
             __syncwarp();
         }
         // every lane is done with the stage (the shuffles above consumed its loads): the warp that emptied it refills
         // it with the tile n_stages further on -- no producer warp, no `empty` barrier, and the latency of posting
-        // a tile (expect_tx + three bulk copies, ~0.4 us for one thread) is spread over all warps
+        // a tile (expect_tx + the bulk copies, ~0.4 us for one thread) is spread over all warps
         __syncwarp();
-        if (lane == 0) fill(it + ust);
+        if (lane == 0) {
+            seen[s] = phase + 1u;
+            fill(it + ust);
+        }
     }
 }
 
@@ -591,70 +626,67 @@ cudaError_t dispatch(int ncol, int64_t want_ctas, int n_batches, size_t smem, in
 #undef FEHT_CASE
 }
 
-// ---- ring kernel launch (SNP).  Returns cudaErrorNotSupported when the shape does not suit it (every consumer warp
-// needs a tile of its own plus a few in flight, and the packed lane partials need S < 65536); the caller then takes
-// the register-staged kernel.
-template <int CB, int LOGL, int NW>
-cudaError_t launch_snp_ring_t(const uint4 *hi, const uint4 *valid, const uint4 *lo, int64_t n_sites, int w4,
-                              const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
-                              cudaStream_t st) {
+// ---- ring kernel launch.  Returns cudaErrorNotSupported when the shape does not suit it (every warp needs a tile of
+// its own plus a few in flight, and the packed lane partials need S < 65536); the caller then takes the
+// register-staged kernel.
+template <bool SNP, int CB, int LOGL, int NW>
+cudaError_t launch_ring_t(const uint4 *p0, const uint4 *valid, const uint4 *p2, int64_t n_units, int w4,
+                          const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
+                          cudaStream_t st) {
     constexpr size_t kSmemTotal = 208 * 1024;   // + up to 17.5 KB static (barriers, reduction scratch)
     constexpr int RPW = 32 >> LOGL;
     const size_t mask_bytes = size_t(CB) * 2 * pl.w4pad * 16;
     if (mask_bytes >= kSmemTotal) return cudaErrorNotSupported;
-    const size_t site_bytes = size_t(48) * w4;                       // three planes
-    // tiles of ~8 KB: large enough for the bulk copies, small enough for kRingWarps + 8 stages
-    int kiter = int(size_t(8192) / (site_bytes * RPW));
+    const size_t unit_bytes = size_t(SNP ? 48 : 32) * w4;            // all planes of one row / site
+    // tiles of ~8 KB: large enough for the bulk copies, small enough for NW + 8 stages
+    int kiter = int(size_t(8192) / (unit_bytes * RPW));
     if (kiter < 1) kiter = 1;
-    // small inputs: keep several tiles per consumer warp
-    while (kiter > 1 && (n_sites / (int64_t(kiter) * RPW)) < int64_t(num_sms) * NW * 2) kiter >>= 1;
-    const size_t stage_bytes = site_bytes * RPW * kiter;
+    // small inputs: keep several tiles per warp
+    while (kiter > 1 && (n_units / (int64_t(kiter) * RPW)) < int64_t(num_sms) * NW * 2) kiter >>= 1;
+    const size_t stage_bytes = unit_bytes * RPW * kiter;
     int n_stages = int((kSmemTotal - mask_bytes) / stage_bytes);
     if (n_stages > kRingMaxStages) n_stages = kRingMaxStages;
     if (n_stages < NW + 4) return cudaErrorNotSupported;
-    const int64_t n_tiles = (n_sites + int64_t(kiter) * RPW - 1) / (int64_t(kiter) * RPW);
+    const int64_t n_tiles = (n_units + int64_t(kiter) * RPW - 1) / (int64_t(kiter) * RPW);
     const size_t smem = mask_bytes + size_t(n_stages) * stage_bytes;
-    auto kernel = count_popc_snp_ring_kernel<CB, LOGL, NW>;
+    auto kernel = count_popc_ring_kernel<SNP, CB, LOGL, NW>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int64_t gx = num_sms / n_batches;
     if (gx < 1) gx = 1;
     if (gx > n_tiles) gx = n_tiles;
     kernel<<<dim3(unsigned(gx), unsigned(n_batches)), NW * 32, smem, st>>>(
-        hi, valid, lo, n_sites, w4, pl.w4pad, kiter, n_stages, 1, masks, counts);
+        p0, valid, p2, n_units, w4, pl.w4pad, kiter, n_stages, 1, masks, counts);
     return cudaGetLastError();
 }
 
-inline bool snp_ring_enabled() {   // FEHT_SNP_RING=0: register-staged kernel (cross-checks)
+inline bool ring_enabled() {   // FEHT_SNP_RING=0 / FEHT_POPC_RING=0: register-staged kernels only (cross-checks)
     static const bool v = [] {
-        const char *e = getenv("FEHT_SNP_RING");
-        return !(e && atoi(e) == 0);
+        const char *e = getenv("FEHT_SNP_RING"), *f = getenv("FEHT_POPC_RING");
+        return !(e && atoi(e) == 0) && !(f && atoi(f) == 0);
     }();
     return v;
 }
 
-template <int CB>
-cudaError_t launch_snp_ring_any(const uint4 *hi, const uint4 *valid, const uint4 *lo, int64_t n_sites, int w4,
-                                const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
-                                cudaStream_t st) {
-    if (!snp_ring_enabled() || int64_t(w4) * 128 >= 65536) return cudaErrorNotSupported;
+template <bool SNP, int CB>
+cudaError_t launch_ring_any(const uint4 *p0, const uint4 *valid, const uint4 *p2, int64_t n_units, int w4,
+                            const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
+                            cudaStream_t st) {
+    if (!ring_enabled() || int64_t(w4) * 128 >= 65536) return cudaErrorNotSupported;
     cudaError_t e = cudaErrorNotSupported;
     switch (pl.logL) {
-        // 16 consumer warps; 8 when the stages of 16 do not fit (wide rows)
-#define FEHT_RING(LL)                                                                                                   \
-    case LL:                                                                                                            \
-        e = launch_snp_ring_t<CB, LL, kRingWarps>(hi, valid, lo, n_sites, w4, pl, masks, n_batches, counts, num_sms, st); \
-        if (e == cudaErrorNotSupported)                                                                                 \
-            e = launch_snp_ring_t<CB, LL, 8>(hi, valid, lo, n_sites, w4, pl, masks, n_batches, counts, num_sms, st);     \
+        // 16 warps; 8 when the stages of 16 do not fit (wide rows)
+#define FEHT_RING(LL)                                                                                                     \
+    case LL:                                                                                                              \
+        e = launch_ring_t<SNP, CB, LL, kRingWarps>(p0, valid, p2, n_units, w4, pl, masks, n_batches, counts, num_sms, st); \
+        if (e == cudaErrorNotSupported)                                                                                   \
+            e = launch_ring_t<SNP, CB, LL, 8>(p0, valid, p2, n_units, w4, pl, masks, n_batches, counts, num_sms, st);      \
         return e;
         FEHT_RING(0) FEHT_RING(1) FEHT_RING(2) FEHT_RING(3) FEHT_RING(4) FEHT_RING(5)
 #undef FEHT_RING
         default: return cudaErrorNotSupported;
     }
 }
-
-// pair-slots counted per read of the planes (register budget: 8 count streams per slot for SNP)
-template <bool SNP> constexpr int kBatch = SNP ? 2 : 4;
 
 template <bool SNP>
 cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p2, int64_t n,
@@ -668,37 +700,45 @@ cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p
     const uint4 *a = reinterpret_cast<const uint4 *>(p0);
     const uint4 *b = reinterpret_cast<const uint4 *>(p1);
     const uint4 *c = reinterpret_cast<const uint4 *>(p2);
-    constexpr int B = kBatch<SNP>;
     // The masks of a pass live in shared memory (2 x w4pad x 16 B per pair-slot): ~900k samples is the most one
     // pair-slot can have; whole categories of wider matrices go to the GEMM engine, which streams its one-hot tiles.
     constexpr size_t kSmemMax = 200 * 1024;
     if (size_t(2) * plan.w4pad * 16 > kSmemMax) return cudaErrorInvalidConfiguration;
-    // batches of B pair-slots share one read of the planes; the remainder goes one at a time
+    // Batches of pair-slots share one read of the planes: 4 at a time (binary) or 2 (SNP: 8 count streams per
+    // slot), then 2, then single ones.  Several pair-slots, and SNP, go to the TMA-fed ring kernel when its stages fit;
+    // one binary pair-slot stays with the register-staged kernel (the config-2 path, 0.92 of the HBM peak).
+    const size_t rows_out = SNP ? size_t(4) * n : size_t(n);
     int done = 0;
-    const int nb = size_t(B) * 2 * plan.w4pad * 16 <= kSmemMax ? n_slots / B : 0;
-    if (nb > 0) {
-        const size_t smem = size_t(B) * 2 * plan.w4pad * 16;
+    auto run = [&](auto cb_tag, int n_batches) -> cudaError_t {
+        constexpr int CB = decltype(cb_tag)::value;
+        const uint4 *m = d_masks + size_t(done) * 2 * plan.w4pad;
+        int4 *out = d_counts + size_t(done) * rows_out;
         cudaError_t e = cudaErrorNotSupported;
-        if constexpr (SNP) e = launch_snp_ring_any<B>(a, b, c, n, w4, plan, d_masks, nb, d_counts, num_sms, st);
+        // (one binary pair-slot through the ring: 0.2215 ms on config 2 against 0.2126 ms for the register-staged kernel)
+        if (SNP || CB > 1) e = launch_ring_any<SNP, CB>(a, b, c, n, w4, plan, m, n_batches, out, num_sms, st);
         if (e == cudaErrorNotSupported)
-            e = dispatch<B, SNP>(plan.ncol, want, nb, smem, num_sms, st, a, b, c, n, w4, plan, d_masks, d_counts);
+            e = dispatch<CB, SNP>(plan.ncol, want, n_batches, size_t(CB) * 2 * plan.w4pad * 16, num_sms, st, a, b, c, n,
+                                  w4, plan, m, out);
+        if (e == cudaSuccess) {
+            if (launches) ++*launches;
+            done += n_batches * CB;
+        }
+        return e;
+    };
+    auto fits = [&](int cb) { return size_t(cb) * 2 * plan.w4pad * 16 <= kSmemMax; };
+    if constexpr (!SNP) {
+        if (n_slots - done >= 4 && fits(4)) {
+            cudaError_t e = run(std::integral_constant<int, 4>{}, (n_slots - done) / 4);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    if (n_slots - done >= 2 && fits(2)) {
+        cudaError_t e = run(std::integral_constant<int, 2>{}, (n_slots - done) / 2);
         if (e != cudaSuccess) return e;
-        if (launches) ++*launches;
-        done = nb * B;
     }
     if (done < n_slots) {
-        const size_t smem = size_t(2) * plan.w4pad * 16;
-        const size_t rows_out = SNP ? size_t(4) * n : size_t(n);
-        cudaError_t e = cudaErrorNotSupported;
-        if constexpr (SNP)
-            e = launch_snp_ring_any<1>(a, b, c, n, w4, plan, d_masks + size_t(done) * 2 * plan.w4pad, n_slots - done,
-                                       d_counts + size_t(done) * rows_out, num_sms, st);
-        if (e == cudaErrorNotSupported)
-            e = dispatch<1, SNP>(plan.ncol, want, n_slots - done, smem, num_sms, st, a, b, c, n,
-                                 w4, plan, d_masks + size_t(done) * 2 * plan.w4pad,
-                                 d_counts + size_t(done) * rows_out);
+        cudaError_t e = run(std::integral_constant<int, 1>{}, n_slots - done);
         if (e != cudaSuccess) return e;
-        if (launches) ++*launches;
     }
     return cudaSuccess;
 }

@@ -629,6 +629,52 @@ def test_text_upload_many_pieces(cuda_lib):
         assert (g == w).all() and (f == w).all()
 
 
+@pytest.mark.parametrize("n_samples,n_rows,n_values", [
+    (64, 20000, 4), (129, 9001, 8), (1000, 5000, 5), (5000, 3001, 14), (10000, 500, 9), (40000, 100, 4),
+    (70000, 40, 3), (300, 400000, 7)])
+def test_popcount_engine_category_shape_sweep(ctx, n_samples, n_rows, n_values):
+    """K1 for binary planes with several pair-slots per read of the planes (count_popc.cu: the TMA-fed ring with 4 / 2
+    pair-slots per pass, 16 or 8 warps, stages refilled many times over on the long matrix; one pair-slot and rows
+    too wide for the ring through the register-staged kernel).  Every 2x2 table of every comparison of a whole
+    category against numpy popcounts (bit-exact)."""
+    rng = np.random.default_rng(n_samples * 3 + n_values)
+    W = (n_samples + 63) // 64
+    def words():
+        return rng.integers(0, 2**63, size=(n_rows, W), dtype=np.uint64) * np.uint64(2) + \
+            rng.integers(0, 2, size=(n_rows, W), dtype=np.uint64)
+    value = words()
+    valid = words() | words() | words()
+    if n_samples % 64:
+        valid[:, -1] &= np.uint64((1 << (n_samples % 64)) - 1)
+    vos = rng.integers(-1, n_values, size=n_samples).astype(np.int32)
+    ctx.set_samples(n_samples)
+    ctx.clear_comparisons()
+    ctx.add_rows_packed(value, valid)        # value bits outside valid are dropped by the upload
+    ctx.add_category(vos, n_values)
+    ctx.set_count_engine(capi.ENGINE_POPC)
+    ctx.run(capi.CORRECTION_NONE, 0.0)
+    ctx.set_count_engine(capi.ENGINE_AUTO)
+    def bits(a):
+        return np.unpackbits(a.view(np.uint8), axis=1, bitorder="little")[:, :n_samples]
+    bv = bits(valid)
+    bp = bits(value) & bv
+    onehot = np.stack([vos == v for v in range(n_values)], axis=1).astype(np.float32)
+    pos = (bp.astype(np.float32) @ onehot).astype(np.int64)      # exact: counts < 2^24
+    tot = (bv.astype(np.float32) @ onehot).astype(np.int64)
+    for c in sorted(set(rng.integers(0, ctx.num_comparisons, 12)) | {0, ctx.num_comparisons - 1}):
+        kind, _cat, v1, v2 = ctx.comparison_info(int(c))
+        got = ctx.fetch(int(c))
+        order = np.argsort(got["row"])
+        assert (got["row"][order] == np.arange(n_rows)).all()
+        a, n1 = pos[:, v1], tot[:, v1]
+        if kind == 1:
+            b, n2 = pos[:, v2], tot[:, v2]
+        else:
+            b, n2 = pos.sum(axis=1) - a, tot.sum(axis=1) - n1
+        assert (got["goa"][order] == a).all() and (got["gob"][order] == n1 - a).all(), (c, kind, v1, v2)
+        assert (got["gta"][order] == b).all() and (got["gtb"][order] == n2 - b).all(), (c, kind, v1, v2)
+
+
 def test_row_sharding_and_merge_equals_single_context(cuda_lib):
     """shard marker rows, pass the global Bonferroni n, k-way merge the sorted shards."""
     rng = np.random.default_rng(55)

@@ -35,6 +35,10 @@ def run(cfg, rows, engine, steps, ratio_filter=None, samples=None):
         elif cfg == "c2b":   # 1M x 5k, groups of 300 / 400 genomes: hypergeometric branch (l ~ 693)
             S, snp, rf = 5_000, False, 0.0
             cats = []
+        elif cfg.startswith("c2cat"):   # C2 shape with one V-value category counted by K1: c2cat4 -> 2 pair-slots, c2cat8 -> 4, ...
+            S, snp, rf = 5_000, False, 0.0
+            nv = int(cfg[5:])
+            cats = [[(np.arange(S) * nv // S).astype(np.int32), nv]]
         else:
             raise SystemExit("unknown config")
         if ratio_filter is not None:
