@@ -55,6 +55,11 @@ constexpr int kBStages = 6;
 constexpr int kPlaneTileBytes = kTileRows * kChunkBytes;  // 32 KiB
 constexpr int kExpandWarps = 8;
 constexpr int kThreads = (kExpandWarps + 3) * 32;
+#ifndef FEHT_MMA_WARPS
+#define FEHT_MMA_WARPS 4
+#endif
+constexpr int kMmaWarps = FEHT_MMA_WARPS;                       // i8 / mxf4 kernels: MMA-issuing warps (1, 2 or 4), each owns 4 / kMmaWarps accumulators
+constexpr int kThreads2 = (kExpandWarps + 2 + kMmaWarps) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kTmemAccBase = 0;       // + (mt * 2 + plane) * 64
 constexpr int kTmemABase = 256;       // + buf * 128 + (mt * 2 + plane) * 32
@@ -200,7 +205,7 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // samples (16 B of a plane row -> 16 TMEM columns per accumulator), one B block (a full 128-byte swizzle row = 256
 // e2m1 values) serves two consecutive A stages.
 template <bool FP4>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads2, 1)
 count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tm_valid,
                   const uint8_t *__restrict__ bmat, const GemmPass *__restrict__ passes, int n_stages,
                   int64_t n_rows, int n_tiles, int4 *__restrict__ counts) {
@@ -231,13 +236,13 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
         }
         for (int i = 0; i < 3; ++i) {
             mbar_init(ta_full + i * 8, kExpandWarps);
-            mbar_init(ta_empty + i * 8, 1);
+            mbar_init(ta_empty + i * 8, kMmaWarps);
         }
         for (int i = 0; i < kBStages; ++i) {
             mbar_init(b_full + i * 8, 1);
-            mbar_init(b_empty + i * 8, 1);
+            mbar_init(b_empty + i * 8, kMmaWarps);
         }
-        mbar_init(acc_full, 1);
+        mbar_init(acc_full, kMmaWarps);
         mbar_init(acc_empty, kExpandWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -373,7 +378,12 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
             }
         }
     } else {
-        // =============================================== MMA issuer
+        // =============================================== MMA issuers: one warp per M tile.  A single issuing thread was the
+        // pace of the kernel (profiles/README.md r1s: ~530 cycles of waits, fence and commits per stage + ~48 per MMA,
+        // whatever the expanders and producers did); two threads issue disjoint accumulators and each commits to the
+        // same barriers (which therefore expect kMmaWarps arrivals).
+        const int mw = warp - (kExpandWarps + 2);   // this issuer's accumulators: q = mw * kQPer .. + kQPer - 1
+        constexpr int kQPer = 4 / kMmaWarps;
         if (lane == 0) {
             // instruction descriptor, N = n_pad, M = 128, both operands K-major.  i8: D s32, A/B unsigned 8-bit.
             // mxf4 (block-scaled layout): A/B e2m1 (format 1), UE8M0 scales, scale ids 0, K = 64.
@@ -396,7 +406,7 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)   // q = mt * 2 + plane
+                            for (int q = kQPer * mw; q < kQPer * mw + kQPer; ++q)   // q = mt * 2 + plane
                                 mma_fp4_ts(tmem_base + kTmemAccBase + q * 64,
                                            tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
                                            bdesc + uint64_t((half * 2 + ks) * 2), idesc, tmem_base + kTmemSF,
@@ -406,7 +416,7 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {  // q = mt * 2 + plane
+                            for (int q = kQPer * mw; q < kQPer * mw + kQPer; ++q) {  // q = mt * 2 + plane
                                 mma_i8_ts(tmem_base + kTmemAccBase + q * 64,
                                           tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
                                           bdesc + uint64_t(ks * 2), idesc, (s > 0 || ks > 0) ? 1u : 0u);
@@ -853,11 +863,11 @@ cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, 
     if (gx > n_tiles) gx = n_tiles;
     // every pass gets its own set of persistent CTAs; with one pass this is one CTA per SM
     if (fp4)
-        count_gemm_kernel<true><<<dim3(unsigned(gx), unsigned(n_passes)), kThreads, kSmemTotal, st>>>(
+        count_gemm_kernel<true><<<dim3(unsigned(gx), unsigned(n_passes)), kThreads2, kSmemTotal, st>>>(
             tm_value, tm_valid, d_bmat, static_cast<const GemmPass *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
             d_counts);
     else
-        count_gemm_kernel<false><<<dim3(unsigned(gx), unsigned(n_passes)), kThreads, kSmemTotal, st>>>(
+        count_gemm_kernel<false><<<dim3(unsigned(gx), unsigned(n_passes)), kThreads2, kSmemTotal, st>>>(
             tm_value, tm_valid, d_bmat, static_cast<const GemmPass *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
             d_counts);
     if (launches) ++*launches;
