@@ -102,6 +102,8 @@ struct feht_ctx {
     DevBuf<GroupComp> gcomps;
     DevBuf<SlotDef> sdefs;
     DevBuf<unsigned long long> seg_count;  // [2][n_comps]: counts, cursors
+    DevBuf<int32_t> live_rows;             // [n_groups][rows]: rows the prescreen lets through (filtered runs)
+    DevBuf<unsigned int> live_count;       // [n_groups]
     int64_t survivor_hint = 0;             // survivors of the last filtered run (sizes the next run's arrays)
     DevBuf<int32_t> r_comp, o_rank, o_goa, o_gob, o_gta, o_gtb;
     DevBuf<SurvivorRec> r_rec;
@@ -562,6 +564,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->r_p); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
+    release(c->live_rows); release(c->live_count);
     release(c->txt_counts); release(c->txt_starts); release(c->txt_name_len); release(c->txt_flags);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
@@ -1395,6 +1398,19 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     tp.name_rank = c->have_rank == 1 ? c->rank.p : nullptr;
     tp.row_base = c->row_base;
     tp.dense = ratio_filter <= 0.0 ? 1 : 0;
+    tp.live_rows = nullptr;
+    tp.live_count = nullptr;
+    if (!tp.dense && R < (int64_t(1) << 31)) {
+        // row lists of the prescreen kernel (FEHT_PRESCREEN=0: the screen kernel walks every tile and decides itself)
+        static const bool off = [] { const char *e = getenv("FEHT_PRESCREEN"); return e && atoi(e) == 0; }();
+        const size_t words = size_t(tp.n_groups) * size_t(R);
+        if (!off && words <= (size_t(1) << 28)) {   // at most 1 GB of row indices
+            CU(c, ensure(c->live_rows, words));
+            CU(c, ensure(c->live_count, size_t(tp.n_groups)));
+            tp.live_rows = c->live_rows.p;
+            tp.live_count = c->live_count.p;
+        }
+    }
     if (tp.dense && c->have_rank == 1) {
         if (c->rank_is_perm == -1) {  // does name_rank enumerate [0, rows)?  (checked once per upload)
             DevBuf<uint32_t> flags;

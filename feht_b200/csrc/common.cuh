@@ -186,6 +186,11 @@ struct TestParams {
     long long capacity;              // filtered output: slots the survivor arrays hold
     int dense;                       // 1: every test survives, index = comp*n_rows + row
     int dense_by_rank;               // dense and name_rank is a permutation: index = comp*n_rows + rank
+    // filtered output: rows that can reach the ratio filter, per group of comparisons, listed by the prescreen kernel:
+    // live_rows[g * n_rows ..], live_count[g] (zeroed by the launcher).  Null: the screen kernel walks every tile and
+    // decides per tile itself.
+    int32_t *live_rows;
+    unsigned int *live_count;
 };
 // counts how many distinct in-range values rank[0..n) holds (== n iff it is a permutation of [0,n))
 cudaError_t launch_count_distinct_ranks(const int32_t *rank, int64_t n, uint32_t *flags_words,
