@@ -1443,6 +1443,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         c->sw.key_a = c->sw_key_a.p; c->sw.key_b = c->sw_key_b.p;
         c->sw.val_a = c->sw_val_a.p; c->sw.val_b = c->sw_val_b.p;
         tp.key = fused ? c->sw.key_a : nullptr;
+        {   // FEHT_SORT_MERGE_COMP=0: the comparison index keeps its own radix pass
+            static const bool off = [] { const char *e = getenv("FEHT_SORT_MERGE_COMP"); return e && atoi(e) == 0; }();
+            tp.merge_comp = (fused && !off && n_comps >= 2 && n_comps <= 51) ? 1 : 0;
+        }
         tp.val = c->sw.val_a;
         tp.or_and = c->sw.or_and;
         return fused ? launch_init_or_and(c->sw.or_and, c->st) : cudaSuccess;

@@ -186,6 +186,7 @@ struct TestParams {
     long long capacity;              // filtered output: slots the survivor arrays hold
     int dense;                       // 1: every test survives, index = comp*n_rows + row
     int dense_by_rank;               // dense and name_rank is a permutation: index = comp*n_rows + rank
+    int merge_comp;                  // 2..51 comparisons: the comparison index rides in the key's top byte (fet.cu)
     // filtered output: rows that can reach the ratio filter, per group of comparisons, listed by the prescreen kernel:
     // live_rows[g * n_rows ..], live_count[g] (zeroed by the launcher).  Null: the screen kernel walks every tile and
     // decides per tile itself.
