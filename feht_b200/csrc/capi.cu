@@ -1518,6 +1518,20 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         }
         return FEHT_OK;
     };
+    // K3b flavour: do the hypergeometric batches keep their parameters in shared memory?  Yes when some comparison's
+    // two groups hold fewer than 1000 samples together (every one of its tests is then an exact test, FET.hs:105-111)
+    bool hyp_heavy = false;
+    {
+        for (const Comp &cp : c->comps)
+            if (cp.kind == 0 && cp.g1.size() + cp.g2.size() < 1000) hyp_heavy = true;
+        for (const Cat &cat : c->cats) {
+            std::vector<int64_t> cnt(static_cast<size_t>(cat.n_values), 0);
+            for (int32_t v : cat.value_of_sample)
+                if (v >= 0) ++cnt[size_t(v)];
+            std::sort(cnt.begin(), cnt.end());
+            if (cnt.size() >= 2 && cnt[0] + cnt[1] < 1000) hyp_heavy = true;   // the two smallest values make a pair
+        }
+    }
     PvalueIo io{};
     io.rec = c->r_rec.p;
     io.r_comp = c->r_comp.p;
@@ -1530,7 +1544,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         io.d_sel = use_coop ? coop_sort_selector(c->sw, c->num_sms) : nullptr;
         io.out = out;
         io.row_base = c->row_base;
-        CU(c, launch_pvalues(io, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode, c->st));
+        CU(c, launch_pvalues(io, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode, hyp_heavy, c->st));
         ++launches;
     } else if (n > 0) {
         // p-value order: K3b computes p and the keys, then K4 and the gather
@@ -1538,7 +1552,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         io.d_key = c->sw.key_a;
         io.d_val = c->sw.val_a;
         io.d_or_and = c->sw.or_and;
-        CU(c, launch_pvalues(io, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode, c->st));
+        CU(c, launch_pvalues(io, n, c->d_choose, correction, double(bonferroni_n), c->fet_mode, hyp_heavy, c->st));
         ++launches;
         CU(c, cudaEventRecord(ev[3], c->st));
         if (int rc = order()) return rc;

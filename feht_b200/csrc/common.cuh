@@ -217,7 +217,7 @@ struct PvalueIo {
     int64_t row_base;
 };
 cudaError_t launch_pvalues(const PvalueIo &io, int64_t n, const double *d_choose, int correction,
-                           double bonferroni_n, int one_tail, cudaStream_t st);
+                           double bonferroni_n, int one_tail, bool hyp_heavy, cudaStream_t st);
 cudaError_t launch_eval_tables(const int4 *d_tables, int64_t n, const double *d_choose, int one_tail,
                                double *d_p, double *d_ratio, SurvivorRec *d_rec, cudaStream_t st);
 
