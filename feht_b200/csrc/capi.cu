@@ -94,6 +94,7 @@ struct feht_ctx {
     bool gemm_fp4 = false;           // ... and were baked for the 4-bit (kind::mxf4) flavour
     bool gemm_f8 = false;            // ... or for the e5m2 one (both planes in one GEMM)
     bool plan_ready = false;         // masks / groups / fracs / gcomps / sdefs on the device match the comparisons
+    bool hyp_heavy = false;          // ... and: some comparison is all exact tests (K3b flavour)
     int plan_groups = 0, plan_max_frac = 0, plan_max_comp = 0, plan_max_slot = 0;
     int last_engine = 0;             // engine the last run counted categories with
     DevBuf<int4> counts;
@@ -1246,6 +1247,18 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     CU(c, cudaMemcpyAsync(c->gcomps.p, gcomps.data(), gcomps.size() * sizeof(GroupComp), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaMemcpyAsync(c->sdefs.p, sdefs.data(), sdefs.size() * sizeof(SlotDef), cudaMemcpyHostToDevice, c->st));
     CU(c, cudaStreamSynchronize(c->st));   // the host vectors die here (once per set of comparisons)
+    // K3b flavour: do the hypergeometric batches keep their parameters in shared memory?  Yes when some comparison's
+    // two groups hold fewer than 1000 samples together (every one of its tests is then an exact test, FET.hs:105-111)
+    c->hyp_heavy = false;
+    for (const Comp &cp : c->comps)
+        if (cp.kind == 0 && cp.g1.size() + cp.g2.size() < 1000) c->hyp_heavy = true;
+    for (const Cat &cat : c->cats) {
+        std::vector<int64_t> cnt(static_cast<size_t>(cat.n_values), 0);
+        for (int32_t v : cat.value_of_sample)
+            if (v >= 0) ++cnt[size_t(v)];
+        std::sort(cnt.begin(), cnt.end());
+        if (cnt.size() >= 2 && cnt[0] + cnt[1] < 1000) c->hyp_heavy = true;   // the two smallest values make a pair
+    }
     c->plan_groups = int(groups.size());
     c->plan_max_frac = max_frac; c->plan_max_comp = max_comp; c->plan_max_slot = max_slot;
     c->plan_ready = true;
@@ -1518,20 +1531,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         }
         return FEHT_OK;
     };
-    // K3b flavour: do the hypergeometric batches keep their parameters in shared memory?  Yes when some comparison's
-    // two groups hold fewer than 1000 samples together (every one of its tests is then an exact test, FET.hs:105-111)
-    bool hyp_heavy = false;
-    {
-        for (const Comp &cp : c->comps)
-            if (cp.kind == 0 && cp.g1.size() + cp.g2.size() < 1000) hyp_heavy = true;
-        for (const Cat &cat : c->cats) {
-            std::vector<int64_t> cnt(static_cast<size_t>(cat.n_values), 0);
-            for (int32_t v : cat.value_of_sample)
-                if (v >= 0) ++cnt[size_t(v)];
-            std::sort(cnt.begin(), cnt.end());
-            if (cnt.size() >= 2 && cnt[0] + cnt[1] < 1000) hyp_heavy = true;   // the two smallest values make a pair
-        }
-    }
+    const bool hyp_heavy = c->hyp_heavy;   // decided with the comparison plan
     PvalueIo io{};
     io.rec = c->r_rec.p;
     io.r_comp = c->r_comp.p;
