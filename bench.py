@@ -290,7 +290,10 @@ def main() -> int:
     R = args.rows
     total_rows = R * world
     ctx = capi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a REAL stream: torch's default stream has handle 0, which feht_set_stream reads as "use the context's own
+    # (non-blocking) stream" -- events recorded on the legacy default stream would then not order against the work
+    stream = torch.cuda.Stream(device=dev)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     ctx.set_samples(S)
     # host cores that transcode part of a chars upload (e2e only): this rank's share of the box
@@ -330,6 +333,8 @@ def main() -> int:
     t = ctx.timings()
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    # the window [ev0, ev1] sits on the stream the runs were enqueued on, so it must contain every run's own events
+    assert float(ms.item()) >= 0.999 * stage["total_ms"], (float(ms.item()), stage)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())

@@ -121,6 +121,7 @@ struct feht_ctx {
     Timings tm;
 
     // text upload (text_load.cu): scratch on the device, and the lines of the last call for the host
+    DevBuf<unsigned int> snp_digit_flag;   // feht_add_snp_chars: K0 met a literal '0' / '1'
     DevBuf<uint32_t> txt_counts;
     DevBuf<int32_t> txt_starts, txt_name_len;
     DevBuf<unsigned long long> txt_flags;
@@ -367,7 +368,12 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
         return first;
     };
     std::atomic<int> worker_err{0};
+    std::atomic<int> host_digits{0};   // SNP: a worker met a literal '0' / '1'
     std::atomic<int64_t> host_rows{0};
+    if (snp) {
+        CU(c, ensure(c->snp_digit_flag, 1));
+        CU(c, cudaMemsetAsync(c->snp_digit_flag.p, 0, sizeof(unsigned int), c->st));
+    }
     std::vector<std::thread> pool;
     pool.reserve(size_t(workers));
     for (int t = 0; t < workers; ++t) {
@@ -384,9 +390,9 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
                 const int64_t r0 = piece_first[size_t(i)], r1 = piece_first[size_t(i) + 1];
                 const size_t words = size_t(r1 - r0) * size_t(c->W);
                 const int64_t u0 = first_unit + r0;
-                if (snp)
-                    host_pack_snp(chars, row_offsets, r0, r1, c->S, c->W, buf, buf + words, buf + 2 * words);
-                else
+                if (snp) {
+                    if (host_pack_snp(chars, row_offsets, r0, r1, c->S, c->W, buf, buf + words, buf + 2 * words)) host_digits = 1;
+                } else
                     host_pack_binary(chars, row_offsets, r0, r1, c->S, c->W, buf, buf + words);
                 cudaError_t e = cudaSuccess;
                 for (int pl = 0; pl < n_planes && e == cudaSuccess; ++pl)
@@ -431,7 +437,8 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
         const int64_t u0 = first_unit + r0;
         if (snp)
             derr = launch_pack_snp_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S, c->W,
-                                         c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->plane[2] + u0 * c->W, c->st);
+                                         c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->plane[2] + u0 * c->W,
+                                         c->snp_digit_flag.p, c->st);
         else
             derr = launch_pack_chars(dev + off_pad, reinterpret_cast<const int64_t *>(dev), rows, c->S, c->W,
                                      c->plane[0] + u0 * c->W, c->plane[1] + u0 * c->W, c->st);
@@ -449,6 +456,13 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
     CU(c, cudaStreamSynchronize(c->pack_stream));
     CU(c, cudaStreamSynchronize(c->copy_stream));
     CU(c, cudaStreamSynchronize(c->st));
+    if (snp) {
+        unsigned int dev_digits = 0;
+        CU(c, cudaMemcpy(&dev_digits, c->snp_digit_flag.p, sizeof(dev_digits), cudaMemcpyDeviceToHost));
+        if (dev_digits || host_digits.load())   // nothing is appended (n_units unchanged)
+            return fail(c, FEHT_E_INVALID, "the SNP rows hold literal '0' / '1' calls, which count for all four alleles "
+                        "(Table.hs:194-205): upload the expanded rows with feht_add_rows_chars");
+    }
     c->last_upload_host_rows = host_rows.load();
     c->n_units += n;
     c->has_results = false;
@@ -565,7 +579,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->r_p); release(c->o_p); release(c->o_ratio);
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
-    release(c->live_rows); release(c->live_count);
+    release(c->live_rows); release(c->live_count); release(c->snp_digit_flag);
     release(c->txt_counts); release(c->txt_starts); release(c->txt_name_len); release(c->txt_flags);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
@@ -605,25 +619,31 @@ extern "C" int feht_pack_chars_host(const uint8_t *chars, const int64_t *row_off
     int threads = n_threads > 0 ? n_threads : int(std::thread::hardware_concurrency());
     threads = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 256), n_rows)));
     const bool simd = host_pack_available();
+    std::atomic<int> digits{0};
     auto work = [&](int64_t r0, int64_t r1) {
         const size_t o = size_t(r0) * size_t(row_stride_words);
         if (snp_mode) {   // planes in the order feht_add_snp_packed takes them: hi, lo, valid
-            if (simd) host_pack_snp(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane2 + o, plane1 + o);
-            else host_pack_snp_scalar(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane2 + o, plane1 + o);
+            const bool d = simd ? host_pack_snp(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane2 + o, plane1 + o)
+                                : host_pack_snp_scalar(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane2 + o, plane1 + o);
+            if (d) digits = 1;
         } else {
             if (simd) host_pack_binary(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane1 + o);
             else host_pack_binary_scalar(chars, row_offsets, r0, r1, n_samples, row_stride_words, plane0 + o, plane1 + o);
         }
     };
-    if (threads == 1) { work(0, n_rows); return FEHT_OK; }
-    std::vector<std::thread> pool;
-    const int64_t per = (n_rows + threads - 1) / threads;
-    for (int t = 0; t < threads; ++t) {
-        const int64_t r0 = t * per, r1 = std::min(n_rows, r0 + per);
-        if (r0 < r1) pool.emplace_back(work, r0, r1);
+    if (threads == 1) {
+        work(0, n_rows);
+    } else {
+        std::vector<std::thread> pool;
+        const int64_t per = (n_rows + threads - 1) / threads;
+        for (int t = 0; t < threads; ++t) {
+            const int64_t r0 = t * per, r1 = std::min(n_rows, r0 + per);
+            if (r0 < r1) pool.emplace_back(work, r0, r1);
+        }
+        for (std::thread &th : pool) th.join();
     }
-    for (std::thread &th : pool) th.join();
-    return FEHT_OK;
+    // SNP rows with literal '0' / '1' calls cannot be expressed in the 2-bit planes (Table.hs:194-205)
+    return digits.load() ? FEHT_E_INVALID : FEHT_OK;
 }
 
 extern "C" int feht_set_host_threads(feht_ctx *c, int n_threads) {
@@ -650,6 +670,10 @@ extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
     for (int i = 0; i < 3; ++i) { if (c->plane[i]) cudaFree(c->plane[i]); c->plane[i] = nullptr; }
     c->gemm_ready = false;
     c->plan_ready = false;
+    // comparisons and categories are column lists / per-sample value vectors of the OLD sample count: drop them
+    // (a category's value_of_sample has exactly S entries; keeping it across a larger S would be read out of bounds)
+    c->comps.clear();
+    c->cats.clear();
     c->S = n_samples;
     c->W = ((n_samples + 63) / 64 + 1) & ~int64_t(1);  // even number of 64-bit words: 16-byte rows
     c->snp = -1;

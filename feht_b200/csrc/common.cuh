@@ -54,6 +54,20 @@ struct ScreenGroup {
     int32_t pad;
 };
 
+// SM count of the CURRENT device (cached per device; one process may drive several GPUs).  Launch grids are sized
+// as multiples of it instead of a literal 148.
+inline int sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 struct Timings {
     double count_ms = 0, test_ms = 0, order_ms = 0, total_ms = 0;
     double launches = 0, count_launches = 0, count_bytes = 0;
@@ -65,9 +79,10 @@ struct Timings {
 cudaError_t launch_pack_chars(const uint8_t *d_chars, const int64_t *d_row_offsets, int64_t n_rows,
                               int64_t S, int64_t W, uint64_t *d_value, uint64_t *d_valid,
                               cudaStream_t st);
+// d_digit_flag: set to 1 when a literal '0' / '1' call is met (Table.hs:194-205 leaves those alone)
 cudaError_t launch_pack_snp_chars(const uint8_t *d_chars, const int64_t *d_row_offsets,
                                   int64_t n_sites, int64_t S, int64_t W, uint64_t *d_hi,
-                                  uint64_t *d_valid, uint64_t *d_lo, cudaStream_t st);
+                                  uint64_t *d_valid, uint64_t *d_lo, unsigned int *d_digit_flag, cudaStream_t st);
 cudaError_t launch_synth(const feht_synth_spec *d_spec, int snp_mode, int64_t first_row,
                          int64_t n_rows, int64_t S, int64_t W, uint64_t *d_p0, uint64_t *d_valid,
                          uint64_t *d_lo, cudaStream_t st);
@@ -80,11 +95,12 @@ cudaError_t launch_repack_rows(const uint64_t *d_src, int64_t src_stride, uint64
 bool host_pack_available();
 void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                       uint64_t *value, uint64_t *valid);
-void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+// (the SNP packers return true when they met a literal '0' / '1' call, which the 2-bit planes cannot express)
+bool host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                    uint64_t *hi, uint64_t *valid, uint64_t *lo);
 void host_pack_binary_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                              uint64_t *value, uint64_t *valid);
-void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+bool host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                           uint64_t *hi, uint64_t *valid, uint64_t *lo);
 
 // text_load.cu: lines of a piece of the data file's text, and their rows packed (N2 of SURVEY.md 8f)

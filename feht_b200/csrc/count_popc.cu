@@ -785,7 +785,7 @@ cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
 cudaError_t launch_sum_slots(int4 *d_counts, int64_t n_rows, int slot0, int n, int tot_slot, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     int64_t b = (n_rows + 255) / 256;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > int64_t(sm_count()) * 16) b = int64_t(sm_count()) * 16;
     sum_slots_kernel<<<int(b), 256, 0, st>>>(d_counts, n_rows, slot0, n, tot_slot);
     return cudaGetLastError();
 }

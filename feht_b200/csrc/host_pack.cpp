@@ -9,7 +9,9 @@
 // producers write bit-identical planes (tests/test_gpu_parity.py compares them).
 //
 // Character semantics are K0's: '1' -> value+valid, '0' -> valid, anything else missing (Comparison.hs:53-56,
-// README.md:227-234); SNP: toUpper, A=0 C=1 G=2 T=3 in (hi, lo), anything else missing (Table.hs:194-205).
+// README.md:227-234); SNP: toUpper, A=0 C=1 G=2 T=3 in (hi, lo), anything else missing (Table.hs:194-205) -- except a
+// literal '0' / '1', which the reference's replaceChar leaves alone (it then counts for all four allele rows): the SNP
+// packers report those (return value) and the caller rejects the upload, as feht_add_rows_text does.
 // Characters at index >= row length or >= S contribute nothing.
 #include <immintrin.h>
 #include <stdint.h>
@@ -38,8 +40,9 @@ void host_pack_binary_scalar(const uint8_t *chars, const int64_t *off, int64_t r
         }
     }
 }
-void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+bool host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                           uint64_t *hi, uint64_t *valid, uint64_t *lo) {
+    bool digit = false;   // a literal '0' / '1' call: counts for all four alleles in the reference (Table.hs:194-205)
     for (int64_t r = r0; r < r1; ++r) {
         const uint8_t *src = chars + off[r];
         int64_t n = off[r + 1] - off[r];
@@ -48,6 +51,7 @@ void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, 
         for (int64_t w = 0; w < W; ++w) { ph[w] = 0; pv[w] = 0; pl[w] = 0; }
         for (int64_t j = 0; j < n; ++j) {
             uint8_t c = src[j];
+            digit |= (c == '0' || c == '1');
             if (c >= 'a' && c <= 'z') c = uint8_t(c - 'a' + 'A');   // toUpper (Table.hs:205)
             const uint64_t bit = uint64_t(1) << (j & 63);
             if (c == 'G' || c == 'T') ph[j >> 6] |= bit;
@@ -55,6 +59,7 @@ void host_pack_snp_scalar(const uint8_t *chars, const int64_t *off, int64_t r0, 
             if (c == 'A' || c == 'C' || c == 'G' || c == 'T') pv[j >> 6] |= bit;
         }
     }
+    return digit;
 }
 
 namespace {
@@ -101,10 +106,12 @@ static void host_pack_binary_avx2(const uint8_t *chars, const int64_t *off, int6
 }
 
 __attribute__((target("avx2")))
-static void host_pack_snp_avx2(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+static bool host_pack_snp_avx2(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                    uint64_t *hi, uint64_t *valid, uint64_t *lo) {
     // toUpper on the four letters that matter: (c & 0xDF) == 'A' iff c is 'A' or 'a'
     const __m256i up = _mm256_set1_epi8(char(0xDF));
+    const __m256i c0 = _mm256_set1_epi8('0'), c1 = _mm256_set1_epi8('1');
+    uint64_t digits = 0;   // any literal '0' / '1' (raw characters, before the case fold)
     const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'),
                   cT = _mm256_set1_epi8('T');
     for (int64_t r = r0; r < r1; ++r) {
@@ -114,8 +121,11 @@ static void host_pack_snp_avx2(const uint8_t *chars, const int64_t *off, int64_t
         uint64_t *ph = hi + (r - r0) * W, *pv = valid + (r - r0) * W, *pl = lo + (r - r0) * W;
         const int64_t full = n >> 6;
         for (int64_t w = 0; w < full; ++w) {
-            const __m256i a = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64 * w)), up);
-            const __m256i b = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64 * w + 32)), up);
+            const __m256i ra = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64 * w));
+            const __m256i rb = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + 64 * w + 32));
+            digits |= eq_mask64(ra, rb, c0) | eq_mask64(ra, rb, c1);
+            const __m256i a = _mm256_and_si256(ra, up);
+            const __m256i b = _mm256_and_si256(rb, up);
             const uint64_t mA = eq_mask64(a, b, cA), mC = eq_mask64(a, b, cC), mG = eq_mask64(a, b, cG),
                            mT = eq_mask64(a, b, cT);
             ph[w] = mG | mT;
@@ -127,6 +137,7 @@ static void host_pack_snp_avx2(const uint8_t *chars, const int64_t *off, int64_t
             uint64_t mh = 0, ml = 0, mv = 0;
             for (int64_t j = 64 * full; j < n; ++j) {
                 const uint8_t c = uint8_t(src[j] & 0xDF);
+                digits |= uint64_t(src[j] == '0' || src[j] == '1');
                 const uint64_t bit = uint64_t(1) << (j & 63);
                 if (c == 'G' || c == 'T') mh |= bit;
                 if (c == 'C' || c == 'T') ml |= bit;
@@ -137,6 +148,7 @@ static void host_pack_snp_avx2(const uint8_t *chars, const int64_t *off, int64_t
         }
         for (; w < W; ++w) { ph[w] = 0; pl[w] = 0; pv[w] = 0; }
     }
+    return digits != 0;
 }
 
 
@@ -173,9 +185,11 @@ static void host_pack_binary_avx512(const uint8_t *chars, const int64_t *off, in
 }
 
 __attribute__((target("avx512f,avx512bw")))
-static void host_pack_snp_avx512(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S,
+static bool host_pack_snp_avx512(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S,
                                  int64_t W, uint64_t *hi, uint64_t *valid, uint64_t *lo) {
     const __m512i up = _mm512_set1_epi8(char(0xDF));
+    const __m512i c0 = _mm512_set1_epi8('0'), c1 = _mm512_set1_epi8('1');
+    uint64_t digits = 0;
     const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'),
                   cT = _mm512_set1_epi8('T');
     for (int64_t r = r0; r < r1; ++r) {
@@ -187,7 +201,9 @@ static void host_pack_snp_avx512(const uint8_t *chars, const int64_t *off, int64
         for (int64_t w = 0; w < words; ++w) {
             const int64_t left = n - 64 * w;
             const __mmask64 k = left >= 64 ? ~uint64_t(0) : (uint64_t(1) << left) - 1;
-            const __m512i a = _mm512_and_si512(_mm512_maskz_loadu_epi8(k, src + 64 * w), up);
+            const __m512i raw = _mm512_maskz_loadu_epi8(k, src + 64 * w);
+            digits |= _mm512_mask_cmpeq_epi8_mask(k, raw, c0) | _mm512_mask_cmpeq_epi8_mask(k, raw, c1);
+            const __m512i a = _mm512_and_si512(raw, up);
             const uint64_t mA = _mm512_mask_cmpeq_epi8_mask(k, a, cA), mC = _mm512_mask_cmpeq_epi8_mask(k, a, cC),
                            mG = _mm512_mask_cmpeq_epi8_mask(k, a, cG), mT = _mm512_mask_cmpeq_epi8_mask(k, a, cT);
             ph[w] = mG | mT;
@@ -196,6 +212,7 @@ static void host_pack_snp_avx512(const uint8_t *chars, const int64_t *off, int64
         }
         for (int64_t w = words; w < W; ++w) { ph[w] = 0; pl[w] = 0; pv[w] = 0; }
     }
+    return digits != 0;
 }
 
 static bool use_avx512() {
@@ -209,10 +226,10 @@ void host_pack_binary(const uint8_t *chars, const int64_t *off, int64_t r0, int6
     if (use_avx512()) host_pack_binary_avx512(chars, off, r0, r1, S, W, value, valid);
     else host_pack_binary_avx2(chars, off, r0, r1, S, W, value, valid);
 }
-void host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
+bool host_pack_snp(const uint8_t *chars, const int64_t *off, int64_t r0, int64_t r1, int64_t S, int64_t W,
                    uint64_t *hi, uint64_t *valid, uint64_t *lo) {
-    if (use_avx512()) host_pack_snp_avx512(chars, off, r0, r1, S, W, hi, valid, lo);
-    else host_pack_snp_avx2(chars, off, r0, r1, S, W, hi, valid, lo);
+    if (use_avx512()) return host_pack_snp_avx512(chars, off, r0, r1, S, W, hi, valid, lo);
+    return host_pack_snp_avx2(chars, off, r0, r1, S, W, hi, valid, lo);
 }
 
 }  // namespace feht

@@ -50,7 +50,7 @@ pack_chars_kernel(const uint8_t *__restrict__ chars, const int64_t *__restrict__
 __global__ void __launch_bounds__(256)
 pack_snp_chars_kernel(const uint8_t *__restrict__ chars, const int64_t *__restrict__ row_offsets,
                       int64_t n_sites, int64_t S, int64_t W, uint32_t *__restrict__ hi,
-                      uint32_t *__restrict__ valid, uint32_t *__restrict__ lo) {
+                      uint32_t *__restrict__ valid, uint32_t *__restrict__ lo, unsigned int *__restrict__ digit_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -64,6 +64,9 @@ pack_snp_chars_kernel(const uint8_t *__restrict__ chars, const int64_t *__restri
         const int64_t col = seg * 32 + lane;
         uint8_t c = 0;
         if (col < len && col < S) c = chars[off + col];
+        // replaceChar leaves a literal '0' / '1' as it is, so it counts for all four allele rows (Table.hs:194-205);
+        // the 2-bit planes cannot say that: flag it, the upload is rejected
+        if (__ballot_sync(0xffffffffu, c == '0' || c == '1') && lane == 0) *digit_flag = 1u;
         if (c >= 'a' && c <= 'z') c = uint8_t(c - 'a' + 'A');  // toUpper (Table.hs:205)
         // A=0 C=1 G=2 T=3
         const bool isA = c == 'A', isC = c == 'C', isG = c == 'G', isT = c == 'T';
@@ -145,7 +148,7 @@ repack_rows_kernel(const uint64_t *__restrict__ src, int64_t src_stride, uint64_
 inline int grid_for(int64_t work_items, int per_block) {
     int64_t b = (work_items + per_block - 1) / per_block;
     if (b < 1) b = 1;
-    if (b > 148 * 32) b = 148 * 32;
+    if (b > int64_t(sm_count()) * 32) b = int64_t(sm_count()) * 32;
     return int(b);
 }
 
@@ -163,11 +166,11 @@ cudaError_t launch_pack_chars(const uint8_t *d_chars, const int64_t *d_row_offse
 
 cudaError_t launch_pack_snp_chars(const uint8_t *d_chars, const int64_t *d_row_offsets,
                                   int64_t n_sites, int64_t S, int64_t W, uint64_t *d_hi,
-                                  uint64_t *d_valid, uint64_t *d_lo, cudaStream_t st) {
+                                  uint64_t *d_valid, uint64_t *d_lo, unsigned int *d_digit_flag, cudaStream_t st) {
     if (n_sites == 0) return cudaSuccess;
     pack_snp_chars_kernel<<<grid_for(n_sites * 2 * W, 8), 256, 0, st>>>(
         d_chars, d_row_offsets, n_sites, S, W, reinterpret_cast<uint32_t *>(d_hi),
-        reinterpret_cast<uint32_t *>(d_valid), reinterpret_cast<uint32_t *>(d_lo));
+        reinterpret_cast<uint32_t *>(d_valid), reinterpret_cast<uint32_t *>(d_lo), d_digit_flag);
     return cudaGetLastError();
 }
 

@@ -578,7 +578,7 @@ scatter_rows_kernel(const unsigned char *__restrict__ src, unsigned char *__rest
 inline int blocks_for(int64_t n, int per) {
     int64_t b = (n + per - 1) / per;
     if (b < 1) b = 1;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > int64_t(sm_count()) * 8) b = int64_t(sm_count()) * 8;
     return int(b);
 }
 

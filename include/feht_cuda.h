@@ -63,7 +63,8 @@ int  feht_set_stream(feht_ctx *ctx, void *cuda_stream);
 const char *feht_version(void);
 
 /* ---------------------------------------------------------------- data matrix ---- */
-/* S = number of data-file columns (Table.hs:273,277).  Must be called first; drops any rows. */
+/* S = number of data-file columns (Table.hs:273,277).  Must be called first; drops any rows AND every comparison /
+ * category (their column lists and per-sample value vectors belong to the old sample count). */
 int feht_set_samples(feht_ctx *ctx, int64_t n_samples);
 /* Optional: pre-size device storage for n_rows marker rows (binary) or sites (SNP). */
 int feht_reserve_rows(feht_ctx *ctx, int64_t n_rows);
@@ -142,7 +143,10 @@ int feht_add_rows_packed(feht_ctx *ctx, const uint64_t *value_plane, const uint6
 int feht_add_snp_packed(feht_ctx *ctx, const uint64_t *hi_plane, const uint64_t *lo_plane,
                         const uint64_t *valid_plane, int64_t n_sites, int64_t row_stride_words,
                         const int32_t *name_rank);
-/* SNP sites as characters (one char per sample per site, upper or lower case). */
+/* SNP sites as characters (one char per sample per site, upper or lower case).  A literal '0' / '1' call -- which the
+ * reference's replaceChar leaves alone, so that it counts for all four allele rows (Table.hs:194-205) -- cannot be
+ * held in the 2-bit planes: the call fails with FEHT_E_INVALID and appends nothing (upload the expanded _a/_t/_c/_g
+ * rows with feht_add_rows_chars instead; feht_pack_chars_host reports the same condition the same way). */
 int feht_add_snp_chars(feht_ctx *ctx, const uint8_t *chars, const int64_t *row_offsets,
                        int64_t n_sites, const int32_t *name_rank);
 

@@ -151,7 +151,7 @@ def test_host_transcoder_equals_numpy_packing(cuda_lib):
     for S in (1, 63, 64, 65, 200, 1000):
         R = 97
         for snp in (False, True):
-            alphabet = np.frombuffer(b"ACGTacgt-N01x" if snp else b"01-1 0NX", dtype=np.uint8)
+            alphabet = np.frombuffer(b"ACGTacgt-N?x" if snp else b"01-1 0NX", dtype=np.uint8)
             lens = rng.integers(max(0, S - 70), S + 40, size=R)
             rows = [alphabet[rng.integers(0, len(alphabet), size=int(n))] for n in lens]
             # what the layout means: characters at index >= len(row) or >= S contribute nothing
@@ -165,3 +165,11 @@ def test_host_transcoder_equals_numpy_packing(cuda_lib):
                 assert len(got) == len(want)
                 for g, w in zip(got, want):
                     assert (g == w).all(), (S, snp, threads)
+    # SNP rows with a literal '0' / '1' (Table.hs:194-205: counted for all four alleles) cannot be packed: loud error
+    for S, pos, ch in ((200, 131, b"1"), (64, 63, b"0"), (65, 64, b"1"), (1000, 7, b"0")):
+        row = bytearray(b"ACGT" * (S // 4 + 1))[:S]
+        row[pos:pos + 1] = ch
+        for threads in (1, 3):
+            with pytest.raises(capi.FehtError):
+                capi.pack_chars_host([bytes(row), b"ACGT"], S, snp=True, n_threads=threads)
+        capi.pack_chars_host([bytes(row)], S, snp=False, n_threads=1)   # binary mode: ordinary calls
