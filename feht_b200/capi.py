@@ -32,6 +32,7 @@ EXPORTS = [
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
     "feht_set_host_threads", "feht_last_upload_host_rows", "feht_add_rows_text", "feht_text_lines", "feht_set_name_rank", "feht_set_fet_mode", "feht_pack_chars_host",
+    "feht_create_multi", "feht_num_devices", "feht_merge_shards_device",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -58,6 +59,13 @@ class SynthSpec(C.Structure):
     ]
 
 
+class ShardRows(C.Structure):
+    """feht_shard_rows: device columns of one shard's ordered rows (all comparisons), host segment offsets."""
+    _fields_ = [("row", C.c_void_p), ("goa", C.c_void_p), ("gob", C.c_void_p), ("gta", C.c_void_p),
+                ("gtb", C.c_void_p), ("p", C.c_void_p), ("ratio", C.c_void_p), ("name_rank", C.c_void_p),
+                ("seg_off", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -75,6 +83,10 @@ def lib() -> C.CDLL:
     P = C.POINTER
     L.feht_create.argtypes = [P(vp), C.c_int]
     L.feht_create.restype = C.c_int
+    L.feht_create_multi.argtypes = [P(vp), P(C.c_int), C.c_int]
+    L.feht_create_multi.restype = C.c_int
+    L.feht_num_devices.argtypes = [vp]
+    L.feht_merge_shards_device.argtypes = [vp, C.c_int, i64, P(ShardRows), C.c_int, P(ShardRows)]
     L.feht_destroy.argtypes = [vp]
     L.feht_destroy.restype = None
     L.feht_last_error.argtypes = [vp]
@@ -232,15 +244,23 @@ def merge_sorted(keys, ranks, sort_key=SORT_ABS_RATIO_DESC):
 
 
 class Context:
-    """One feht_ctx = one GPU."""
+    """One feht_ctx: one GPU (device = an int) or a multi-device handle (device = a list of ids, feht_create_multi)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._L = lib()
         h = C.c_void_p()
-        rc = self._L.feht_create(C.byref(h), device)
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self._L.feht_create_multi(C.byref(h), ids, len(device))
+        else:
+            rc = self._L.feht_create(C.byref(h), device)
         if rc != OK:
             raise FehtError(rc, self._L.feht_last_error(None).decode())
         self._h = h
+
+    @property
+    def num_devices(self) -> int:
+        return int(self._L.feht_num_devices(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -429,6 +449,22 @@ class Context:
                                               _ptr(out["ratio"]), _ptr(out["name_rank"])))
         return out
 
+    def fetch_all(self) -> dict:
+        """Rows of every comparison, back to back in comparison order (comparison = -1)."""
+        n = self.result_total()
+        out = {
+            "row": np.empty(n, np.int64), "goa": np.empty(n, np.int32), "gob": np.empty(n, np.int32),
+            "gta": np.empty(n, np.int32), "gtb": np.empty(n, np.int32), "p": np.empty(n, np.float64),
+            "ratio": np.empty(n, np.float64), "name_rank": np.empty(n, np.int32),
+        }
+        self._check(self._L.feht_result_fetch(self._h, -1, _ptr(out["row"]), _ptr(out["goa"]), _ptr(out["gob"]),
+                                              _ptr(out["gta"]), _ptr(out["gtb"]), _ptr(out["p"]),
+                                              _ptr(out["ratio"]), _ptr(out["name_rank"])))
+        return out
+
+    def result_counts(self) -> np.ndarray:
+        return np.array([self.result_count(c) for c in range(self.num_comparisons)], dtype=np.int64)
+
     def fetch_raw(self, c: int, ptrs: dict):
         """ptrs: name -> host address (pinned buffers owned by the caller)."""
         g = ptrs.get
@@ -450,14 +486,33 @@ class Context:
         dp = (C.c_void_p * max(k, 1))(*dest_ptrs)
         self._check(self._L.feht_merge_sorted_device(self._h, k, n, kp, rp, sort_key, dp))
 
+    def merge_shards_device(self, shards, n_comparisons: int, out: dict, out_seg_off: np.ndarray,
+                            sort_key=SORT_ABS_RATIO_DESC):
+        """K5b (feht_merge_shards_device).  shards: list of (dict name -> device address, host int64 seg_off array);
+        out: dict name -> device address of the merged columns; out_seg_off: host int64 [n_comparisons + 1]."""
+        arr = (ShardRows * max(len(shards), 1))()
+        keep = []
+        for i, (ptrs, seg) in enumerate(shards):
+            seg = np.ascontiguousarray(seg, dtype=np.int64)
+            keep.append(seg)
+            for k in ("row", "goa", "gob", "gta", "gtb", "p", "ratio", "name_rank"):
+                setattr(arr[i], k, ptrs.get(k))
+            arr[i].seg_off = seg.ctypes.data
+        o = ShardRows()
+        for k in ("row", "goa", "gob", "gta", "gtb", "p", "ratio", "name_rank"):
+            setattr(o, k, out.get(k))
+        assert out_seg_off.dtype == np.int64 and len(out_seg_off) == n_comparisons + 1
+        o.seg_off = out_seg_off.ctypes.data
+        self._check(self._L.feht_merge_shards_device(self._h, len(shards), n_comparisons, arr, sort_key, C.byref(o)))
+
     def scatter_rows_device(self, src_ptr: int, dst_ptr: int, dest_ptr: int, n: int, elem_bytes: int):
         self._check(self._L.feht_scatter_rows_device(self._h, src_ptr, dst_ptr, dest_ptr, n, elem_bytes))
 
     def timings(self) -> dict:
-        buf = (C.c_double * 8)()
-        self._check(self._L.feht_last_timings(self._h, buf, 8))
+        buf = (C.c_double * 9)()
+        self._check(self._L.feht_last_timings(self._h, buf, 9))
         keys = ["count_ms", "test_ms", "order_ms", "total_ms", "launches", "count_launches", "count_bytes",
-                "engine"]
+                "engine", "merge_ms"]
         return dict(zip(keys, list(buf)))
 
     def timings_accumulated(self, reset: bool = False) -> dict:

@@ -18,6 +18,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "multi.cuh"
 
 using namespace feht;
 
@@ -48,6 +49,9 @@ struct DevBuf {
 }  // namespace
 
 struct feht_ctx {
+    // multi-device handle (feht_create_multi): every entry point forwards to multi.cu; the rest of this struct is
+    // then just a context on the first device (it serves feht_merge_sorted_device / feht_scatter_rows_device)
+    MultiState *multi = nullptr;
     int device = 0;
     int num_sms = 148;
     cudaStream_t own_stream = nullptr, st = nullptr, copy_stream = nullptr;
@@ -147,6 +151,16 @@ int fail(feht_ctx *c, int code, const char *fmt, ...) {
         if (_e != cudaSuccess)                                                                     \
             return fail((c), FEHT_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
                         __LINE__);                                                                 \
+    } while (0)
+
+// multi-device handles: forward the call, keep the message where feht_last_error looks for it
+#define MULTI(c, call)                                                     \
+    do {                                                                   \
+        if ((c) && (c)->multi) {                                           \
+            auto _r = (call);                                              \
+            if (_r < 0) (c)->err = multi::last_error((c)->multi);          \
+            return _r;                                                     \
+        }                                                                  \
     } while (0)
 
 template <class T>
@@ -568,6 +582,7 @@ extern "C" int feht_create(feht_ctx **out, int device) {
 
 extern "C" void feht_destroy(feht_ctx *c) {
     if (!c) return;
+    if (c->multi) { multi::destroy(c->multi); c->multi = nullptr; }
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int i = 0; i < 3; ++i) if (c->plane[i]) cudaFree(c->plane[i]);
@@ -598,8 +613,43 @@ extern "C" void feht_destroy(feht_ctx *c) {
 
 extern "C" const char *feht_last_error(const feht_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
+// One handle for several GPUs of the box (feht_create(ctx, device_ids, n_devices)): rows shard over the
+// listed devices, the merge of the ordered shards happens on device_ids[0] (multi.cu).
+extern "C" int feht_create_multi(feht_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) return fail(nullptr, FEHT_E_INVALID, "out is null");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > 32)
+        return fail(nullptr, FEHT_E_INVALID, "feht_create_multi: between 1 and 32 device ids");
+    feht_ctx *h = nullptr;
+    if (int rc = feht_create(&h, device_ids[0])) return rc;
+    std::string err;
+    MultiState *m = multi::create(device_ids, n_devices, &err);
+    if (!m) {
+        feht_destroy(h);
+        // (a device that is missing or not sm_100-class is the usual reason)
+        return fail(nullptr, FEHT_E_NODEVICE, "%s", err.c_str());
+    }
+    h->multi = m;
+    *out = h;
+    return FEHT_OK;
+}
+
+extern "C" int feht_num_devices(const feht_ctx *c) { return !c ? 0 : (c->multi ? multi::n_devices(c->multi) : 1); }
+
+// (internal, multi.cu) the ordered result columns of a single-device context's last run
+extern "C" int feht_internal_results(feht_ctx *c, ResultSoA *out, const int64_t **seg_off_host, int64_t *n_total, int *device) {
+    if (!c || c->multi) return FEHT_E_INVALID;
+    if (!c->has_results) return fail(c, FEHT_E_INVALID, "no results: call feht_run first");
+    if (out) *out = ResultSoA{c->o_row.p, c->o_rank.p, c->o_goa.p, c->o_gob.p, c->o_gta.p, c->o_gtb.p, c->o_p.p, c->o_ratio.p};
+    if (seg_off_host) *seg_off_host = c->seg_off.data();
+    if (n_total) *n_total = c->n_surv;
+    if (device) *device = c->device;
+    return FEHT_OK;
+}
+
 extern "C" int feht_set_fet_mode(feht_ctx *c, int mode) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::set_fet_mode(c->multi, mode));
     if (mode != FEHT_FET_TWO_TAIL && mode != FEHT_FET_ONE_TAIL) return fail(c, FEHT_E_INVALID, "unknown FET mode %d", mode);
     c->fet_mode = mode;
     c->has_results = false;
@@ -648,14 +698,19 @@ extern "C" int feht_pack_chars_host(const uint8_t *chars, const int64_t *row_off
 
 extern "C" int feht_set_host_threads(feht_ctx *c, int n_threads) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::set_host_threads(c->multi, n_threads));
     c->host_threads = n_threads < 0 ? -1 : n_threads;
     return FEHT_OK;
 }
 
-extern "C" int64_t feht_last_upload_host_rows(const feht_ctx *c) { return c ? c->last_upload_host_rows : FEHT_E_INVALID; }
+extern "C" int64_t feht_last_upload_host_rows(const feht_ctx *c) {
+    if (c && c->multi) return multi::last_upload_host_rows(c->multi);
+    return c ? c->last_upload_host_rows : FEHT_E_INVALID;
+}
 
 extern "C" int feht_set_stream(feht_ctx *c, void *cuda_stream) {
     if (!c) return FEHT_E_INVALID;
+    if (c->multi) return fail(c, FEHT_E_INVALID, "a multi-device context runs every shard on its own stream");
     c->st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return FEHT_OK;
 }
@@ -663,6 +718,7 @@ extern "C" int feht_set_stream(feht_ctx *c, void *cuda_stream) {
 // ============================================================================== data matrix ==
 extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::set_samples(c->multi, n_samples));
     if (n_samples <= 0 || n_samples > (int64_t(1) << 24))
         return fail(c, FEHT_E_INVALID, "n_samples must be in [1, 2^24]");
     if (int rc = use_device(c)) return rc;
@@ -687,6 +743,7 @@ extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
 
 extern "C" int feht_reserve_rows(feht_ctx *c, int64_t n_rows) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::reserve_rows(c->multi, n_rows));
     if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
     if (int rc = use_device(c)) return rc;
     // planes are allocated lazily per mode; remember the wish
@@ -701,6 +758,7 @@ extern "C" int feht_reserve_rows(feht_ctx *c, int64_t n_rows) {
 
 extern "C" int feht_clear_rows(feht_ctx *c) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::clear_rows(c->multi));
     c->n_units = 0;
     c->snp = -1;
     c->rank_is_perm = -1;
@@ -712,11 +770,13 @@ extern "C" int feht_clear_rows(feht_ctx *c) {
 
 extern "C" int feht_add_rows_chars(feht_ctx *c, const uint8_t *chars, const int64_t *row_offsets,
                                    int64_t n_rows, const int32_t *name_rank) {
+    MULTI(c, multi::add_chars(c->multi, chars, row_offsets, n_rows, name_rank, 0));
     return add_chars_common(c, chars, row_offsets, n_rows, name_rank, 0);
 }
 
 extern "C" int feht_add_snp_chars(feht_ctx *c, const uint8_t *chars, const int64_t *row_offsets,
                                   int64_t n_sites, const int32_t *name_rank) {
+    MULTI(c, multi::add_chars(c->multi, chars, row_offsets, n_sites, name_rank, 1));
     return add_chars_common(c, chars, row_offsets, n_sites, name_rank, 1);
 }
 
@@ -726,6 +786,7 @@ extern "C" int feht_add_snp_chars(feht_ctx *c, const uint8_t *chars, const int64
 extern "C" int feht_add_rows_text(feht_ctx *c, const char *text, int64_t len, char delimiter, int snp_mode,
                                   int64_t *n_lines_out) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::add_text(c->multi, text, len, delimiter, snp_mode, n_lines_out));
     if (int rc = use_device(c)) return rc;
     const int snp = snp_mode ? 1 : 0;
     if (int rc = check_mode(c, snp)) return rc;
@@ -837,6 +898,7 @@ extern "C" int feht_add_rows_text(feht_ctx *c, const char *text, int64_t len, ch
 
 extern "C" int feht_text_lines(feht_ctx *c, int64_t *line_begin, int32_t *name_len, int64_t cap) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::text_lines(c->multi, line_begin, name_len, cap));
     const int64_t n = int64_t(c->text_line_begin.size());
     if (cap < n) return fail(c, FEHT_E_INVALID, "feht_text_lines: %lld lines, room for %lld", (long long)n, (long long)cap);
     if (n > 0 && line_begin) std::memcpy(line_begin, c->text_line_begin.data(), size_t(n) * 8);
@@ -846,6 +908,7 @@ extern "C" int feht_text_lines(feht_ctx *c, int64_t *line_begin, int32_t *name_l
 
 extern "C" int feht_set_name_rank(feht_ctx *c, const int32_t *name_rank, int64_t n_marker_rows) {
     if (!c || !name_rank) return FEHT_E_INVALID;
+    MULTI(c, multi::set_name_rank(c->multi, name_rank, n_marker_rows));
     if (int rc = use_device(c)) return rc;
     if (n_marker_rows != marker_rows(c))
         return fail(c, FEHT_E_INVALID, "feht_set_name_rank: %lld ranks for %lld marker rows", (long long)n_marker_rows,
@@ -859,6 +922,7 @@ extern "C" int feht_set_name_rank(feht_ctx *c, const int32_t *name_rank, int64_t
 
 extern "C" int feht_add_rows_packed(feht_ctx *c, const uint64_t *value_plane, const uint64_t *valid_plane,
                                     int64_t n_rows, int64_t row_stride_words, const int32_t *name_rank) {
+    MULTI(c, multi::add_packed(c->multi, value_plane, valid_plane, nullptr, n_rows, row_stride_words, name_rank, 0));
     const uint64_t *src[2] = {valid_plane, value_plane};
     const int dst[2] = {1, 0};
     return add_packed_common(c, src, dst, 2, n_rows, row_stride_words, name_rank, 0);
@@ -867,6 +931,7 @@ extern "C" int feht_add_rows_packed(feht_ctx *c, const uint64_t *value_plane, co
 extern "C" int feht_add_snp_packed(feht_ctx *c, const uint64_t *hi_plane, const uint64_t *lo_plane,
                                    const uint64_t *valid_plane, int64_t n_sites, int64_t row_stride_words,
                                    const int32_t *name_rank) {
+    MULTI(c, multi::add_packed(c->multi, hi_plane, lo_plane, valid_plane, n_sites, row_stride_words, name_rank, 1));
     const uint64_t *src[3] = {valid_plane, hi_plane, lo_plane};
     const int dst[3] = {1, 0, 2};
     return add_packed_common(c, src, dst, 3, n_sites, row_stride_words, name_rank, 1);
@@ -875,6 +940,7 @@ extern "C" int feht_add_snp_packed(feht_ctx *c, const uint64_t *hi_plane, const 
 extern "C" int feht_generate_synthetic(feht_ctx *c, const feht_synth_spec *spec, int snp_mode,
                                        int64_t first_row, int64_t n_rows) {
     if (!c || !spec) return FEHT_E_INVALID;
+    MULTI(c, multi::generate_synthetic(c->multi, spec, snp_mode, first_row, n_rows));
     if (int rc = use_device(c)) return rc;
     if (int rc = check_mode(c, snp_mode ? 1 : 0)) return rc;
     if (spec->n_samples != c->S) return fail(c, FEHT_E_INVALID, "spec.n_samples != feht_set_samples");
@@ -901,6 +967,7 @@ extern "C" int feht_generate_synthetic(feht_ctx *c, const feht_synth_spec *spec,
 
 extern "C" int feht_read_plane(feht_ctx *c, int plane, int64_t row0, int64_t n, uint64_t *out) {
     if (!c || !out) return FEHT_E_INVALID;
+    MULTI(c, multi::read_plane(c->multi, plane, row0, n, out));
     if (int rc = use_device(c)) return rc;
     if (plane < 0 || plane > 2 || !c->plane[plane] || (plane == 2 && c->snp != 1))
         return fail(c, FEHT_E_INVALID, "no such plane");
@@ -910,12 +977,19 @@ extern "C" int feht_read_plane(feht_ctx *c, int plane, int64_t row0, int64_t n, 
     return FEHT_OK;
 }
 
-extern "C" int64_t feht_row_stride_words(const feht_ctx *c) { return c ? c->W : 0; }
-extern "C" int64_t feht_num_rows(const feht_ctx *c) { return c ? marker_rows(c) : 0; }
+extern "C" int64_t feht_row_stride_words(const feht_ctx *c) {
+    if (c && c->multi) return multi::row_stride_words(c->multi);
+    return c ? c->W : 0;
+}
+extern "C" int64_t feht_num_rows(const feht_ctx *c) {
+    if (c && c->multi) return multi::num_rows(c->multi);
+    return c ? marker_rows(c) : 0;
+}
 
 // ============================================================================== comparisons ==
 extern "C" int64_t feht_add_comparison(feht_ctx *c, const int32_t *g1, int64_t n1, const int32_t *g2, int64_t n2) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::add_comparison(c->multi, g1, n1, g2, n2));
     if (n1 < 0 || n2 < 0 || (n1 && !g1) || (n2 && !g2)) return fail(c, FEHT_E_INVALID, "null group");
     Comp cp;
     cp.kind = 0;
@@ -932,6 +1006,7 @@ extern "C" int64_t feht_add_comparison(feht_ctx *c, const int32_t *g1, int64_t n
 
 extern "C" int64_t feht_add_category(feht_ctx *c, const int32_t *value_of_sample, int32_t n_values) {
     if (!c || !value_of_sample) return FEHT_E_INVALID;
+    MULTI(c, multi::add_category(c->multi, value_of_sample, n_values));
     if (c->S <= 0) return fail(c, FEHT_E_INVALID, "feht_set_samples must be called first");
     if (n_values < 2) return fail(c, FEHT_E_INVALID, "a category needs at least 2 values");
     Cat cat;
@@ -963,6 +1038,7 @@ extern "C" int64_t feht_add_category(feht_ctx *c, const int32_t *value_of_sample
 
 extern "C" int feht_clear_comparisons(feht_ctx *c) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::clear_comparisons(c->multi));
     c->comps.clear();
     c->cats.clear();
     c->gemm_ready = false;
@@ -971,9 +1047,13 @@ extern "C" int feht_clear_comparisons(feht_ctx *c) {
     return FEHT_OK;
 }
 
-extern "C" int64_t feht_num_comparisons(const feht_ctx *c) { return c ? int64_t(c->comps.size()) : 0; }
+extern "C" int64_t feht_num_comparisons(const feht_ctx *c) {
+    if (c && c->multi) return multi::num_comparisons(c->multi);
+    return c ? int64_t(c->comps.size()) : 0;
+}
 
 extern "C" int feht_comparison_info(const feht_ctx *c, int64_t i, int32_t *kind, int32_t *category, int32_t *v1, int32_t *v2) {
+    if (c && c->multi) return multi::comparison_info(c->multi, i, kind, category, v1, v2);
     if (!c || i < 0 || i >= int64_t(c->comps.size())) return FEHT_E_INVALID;
     const Comp &cp = c->comps[size_t(i)];
     if (kind) *kind = cp.kind;
@@ -985,6 +1065,7 @@ extern "C" int feht_comparison_info(const feht_ctx *c, int64_t i, int32_t *kind,
 
 extern "C" int feht_set_count_engine(feht_ctx *c, int engine) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::set_count_engine(c->multi, engine));
     if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM_F8) return fail(c, FEHT_E_INVALID, "unknown engine");
     c->engine = engine;
     return FEHT_OK;
@@ -992,6 +1073,7 @@ extern "C" int feht_set_count_engine(feht_ctx *c, int engine) {
 
 extern "C" int feht_set_row_base(feht_ctx *c, int64_t row_base) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::set_row_base(c->multi, row_base));
     c->row_base = row_base;
     return FEHT_OK;
 }
@@ -1607,19 +1689,25 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
 }  // namespace
 
 extern "C" int feht_run(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
+    MULTI(c, multi::run(c->multi, correction, ratio_filter, sort_key, bonferroni_n));
     return run_impl(c, correction, ratio_filter, sort_key, bonferroni_n, false);
 }
 
 extern "C" int feht_run_async(feht_ctx *c, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
+    MULTI(c, multi::run(c->multi, correction, ratio_filter, sort_key, bonferroni_n));   // (the merge needs every shard: blocking)
     return run_impl(c, correction, ratio_filter, sort_key, bonferroni_n, true);
 }
 
 extern "C" int64_t feht_result_count(const feht_ctx *c, int64_t comparison) {
+    if (c && c->multi) return multi::result_count(c->multi, comparison);
     if (!c || !c->has_results || comparison < 0 || comparison + 1 >= int64_t(c->seg_off.size())) return FEHT_E_INVALID;
     return c->seg_off[size_t(comparison) + 1] - c->seg_off[size_t(comparison)];
 }
 
-extern "C" int64_t feht_result_total(const feht_ctx *c) { return (c && c->has_results) ? c->n_surv : FEHT_E_INVALID; }
+extern "C" int64_t feht_result_total(const feht_ctx *c) {
+    if (c && c->multi) return multi::result_total(c->multi);
+    return (c && c->has_results) ? c->n_surv : FEHT_E_INVALID;
+}
 
 namespace {
 // copy comparison c's ordered rows out of the result arrays (host or device destination)
@@ -1627,10 +1715,11 @@ int fetch_common(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, in
                  int32_t *gtb, double *p, double *ratio, int32_t *name_rank, cudaMemcpyKind kind) {
     if (!c) return FEHT_E_INVALID;
     if (!c->has_results) return fail(c, FEHT_E_INVALID, "no results: call feht_run first");
-    if (comparison < 0 || comparison + 1 >= int64_t(c->seg_off.size())) return fail(c, FEHT_E_INVALID, "comparison index");
+    if (comparison < -1 || comparison + 1 >= int64_t(c->seg_off.size())) return fail(c, FEHT_E_INVALID, "comparison index");
     if (int rc = use_device(c)) return rc;
-    const int64_t o = c->seg_off[size_t(comparison)];
-    const size_t nn = size_t(c->seg_off[size_t(comparison) + 1] - o);
+    // comparison == -1: the rows of every comparison, back to back in comparison order
+    const int64_t o = comparison < 0 ? 0 : c->seg_off[size_t(comparison)];
+    const size_t nn = comparison < 0 ? size_t(c->n_surv) : size_t(c->seg_off[size_t(comparison) + 1] - o);
     if (nn == 0) return FEHT_OK;
     if (row) CU(c, cudaMemcpyAsync(row, c->o_row.p + o, nn * 8, kind, c->st));
     if (goa) CU(c, cudaMemcpyAsync(goa, c->o_goa.p + o, nn * 4, kind, c->st));
@@ -1647,12 +1736,14 @@ int fetch_common(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, in
 
 extern "C" int feht_result_fetch(feht_ctx *c, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob,
                                  int32_t *gta, int32_t *gtb, double *p, double *ratio, int32_t *name_rank) {
+    MULTI(c, multi::fetch(c->multi, comparison, row, goa, gob, gta, gtb, p, ratio, name_rank, false));
     return fetch_common(c, comparison, row, goa, gob, gta, gtb, p, ratio, name_rank, cudaMemcpyDeviceToHost);
 }
 
 extern "C" int feht_result_fetch_device(feht_ctx *c, int64_t comparison, int64_t *d_row, int32_t *d_goa,
                                         int32_t *d_gob, int32_t *d_gta, int32_t *d_gtb, double *d_p,
                                         double *d_ratio, int32_t *d_name_rank) {
+    MULTI(c, multi::fetch(c->multi, comparison, d_row, d_goa, d_gob, d_gta, d_gtb, d_p, d_ratio, d_name_rank, true));
     return fetch_common(c, comparison, d_row, d_goa, d_gob, d_gta, d_gtb, d_p, d_ratio, d_name_rank,
                         cudaMemcpyDeviceToDevice);
 }
@@ -1684,9 +1775,62 @@ extern "C" int feht_scatter_rows_device(feht_ctx *c, const void *d_src, void *d_
     return FEHT_OK;
 }
 
+// K5b through the C ABI: the ordered shards of EVERY comparison of a row-sharded job, already on this context's GPU
+// (one process per GPU: moved there by the host's transport), merged and scattered by one kernel launch.
+extern "C" int feht_merge_shards_device(feht_ctx *c, int n_shards, int64_t n_comparisons, const feht_shard_rows *shards,
+                                        int sort_key, const feht_shard_rows *out) {
+    if (!c) return FEHT_E_INVALID;
+    if (n_shards < 0 || n_shards > merge_max_shards())
+        return fail(c, FEHT_E_INVALID, "n_shards must be in [0, %d]", merge_max_shards());
+    if (n_comparisons < 0 || n_comparisons > 65535) return fail(c, FEHT_E_INVALID, "n_comparisons out of range");
+    if (sort_key != FEHT_SORT_ABS_RATIO_DESC && sort_key != FEHT_SORT_PVALUE_ASC)
+        return fail(c, FEHT_E_INVALID, "unknown sort key %d", sort_key);
+    if (!out || !out->seg_off || (n_shards && !shards)) return fail(c, FEHT_E_INVALID, "null shard / output description");
+    const size_t per = size_t(n_comparisons) + 1;
+    std::vector<int64_t> hseg(per * size_t(n_shards + 1), 0);
+    std::vector<MergeShardView> views(static_cast<size_t>(n_shards));
+    int64_t total = 0;
+    for (int i = 0; i < n_shards; ++i) {
+        const feht_shard_rows &s = shards[i];
+        if (!s.seg_off || s.seg_off[0] != 0) return fail(c, FEHT_E_INVALID, "shard %d: seg_off must start at 0", i);
+        for (int64_t k = 0; k < n_comparisons; ++k)
+            if (s.seg_off[k + 1] < s.seg_off[k]) return fail(c, FEHT_E_INVALID, "shard %d: seg_off must be non-decreasing", i);
+        const int64_t n = s.seg_off[n_comparisons];
+        if (n > 0 && (!s.row || !s.goa || !s.gob || !s.gta || !s.gtb || !s.p || !s.ratio || !s.name_rank))
+            return fail(c, FEHT_E_INVALID, "shard %d: null column", i);
+        std::memcpy(hseg.data() + per * size_t(i), s.seg_off, per * 8);
+        for (int64_t k = 0; k < n_comparisons; ++k) hseg[per * size_t(n_shards) + size_t(k) + 1] += s.seg_off[k + 1] - s.seg_off[k];
+        views[size_t(i)].res = ResultSoA{const_cast<int64_t *>(s.row), const_cast<int32_t *>(s.name_rank), const_cast<int32_t *>(s.goa),
+                                         const_cast<int32_t *>(s.gob), const_cast<int32_t *>(s.gta), const_cast<int32_t *>(s.gtb),
+                                         const_cast<double *>(s.p), const_cast<double *>(s.ratio)};
+        views[size_t(i)].n = n;
+        total += n;
+    }
+    for (int64_t k = 0; k < n_comparisons; ++k) hseg[per * size_t(n_shards) + size_t(k) + 1] += hseg[per * size_t(n_shards) + size_t(k)];
+    std::memcpy(const_cast<int64_t *>(out->seg_off), hseg.data() + per * size_t(n_shards), per * 8);
+    if (total == 0) return FEHT_OK;
+    if (!out->row || !out->goa || !out->gob || !out->gta || !out->gtb || !out->p || !out->ratio || !out->name_rank)
+        return fail(c, FEHT_E_INVALID, "null output column");
+    if (int rc = use_device(c)) return rc;
+    DevBuf<int64_t> dseg;
+    CU(c, ensure(dseg, hseg.size()));
+    CU(c, cudaMemcpyAsync(dseg.p, hseg.data(), hseg.size() * 8, cudaMemcpyHostToDevice, c->st));
+    for (int i = 0; i < n_shards; ++i) views[size_t(i)].d_seg_off = dseg.p + per * size_t(i);
+    const ResultSoA o{const_cast<int64_t *>(out->row), const_cast<int32_t *>(out->name_rank), const_cast<int32_t *>(out->goa),
+                      const_cast<int32_t *>(out->gob), const_cast<int32_t *>(out->gta), const_cast<int32_t *>(out->gtb),
+                      const_cast<double *>(out->p), const_cast<double *>(out->ratio)};
+    cudaError_t e = launch_merge_all(n_shards, int(n_comparisons), sort_key, views.data(), dseg.p + per * size_t(n_shards), o, 0, c->st);
+    cudaError_t e2 = cudaStreamSynchronize(c->st);
+    release(dseg);
+    CU(c, e);
+    CU(c, e2);
+    return FEHT_OK;
+}
+
 extern "C" int feht_last_timings(const feht_ctx *cc, double *out, int n) {
     if (!cc || !out) return FEHT_E_INVALID;
     feht_ctx *c = const_cast<feht_ctx *>(cc);
+    MULTI(c, multi::last_timings(c->multi, out, n));
     if (int rc = use_device(c)) return rc;
     if (int rc = settle_all(c)) return rc;
     const double v[8] = {c->tm.count_ms, c->tm.test_ms, c->tm.order_ms, c->tm.total_ms,
@@ -1697,6 +1841,7 @@ extern "C" int feht_last_timings(const feht_ctx *cc, double *out, int n) {
 
 extern "C" int feht_timings_accumulated(feht_ctx *c, double *out, int n, int reset) {
     if (!c || !out) return FEHT_E_INVALID;
+    MULTI(c, multi::timings_accumulated(c->multi, out, n, reset));
     if (int rc = use_device(c)) return rc;
     if (int rc = settle_all(c)) return rc;
     for (int i = 0; i < n && i < 7; ++i) out[i] = c->acc[i];
@@ -1751,6 +1896,7 @@ extern "C" int64_t feht_choose_table(double *out, int64_t cap) {
 extern "C" int feht_eval_tables(feht_ctx *c, const int32_t *goa, const int32_t *gob, const int32_t *gta,
                                 const int32_t *gtb, int64_t n, double *p_out, double *ratio_out) {
     if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::eval_tables(c->multi, goa, gob, gta, gtb, n, p_out, ratio_out));
     if (n < 0 || (n && (!goa || !gob || !gta || !gtb))) return fail(c, FEHT_E_INVALID, "null table arrays");
     if (n == 0) return FEHT_OK;
     if (int rc = use_device(c)) return rc;

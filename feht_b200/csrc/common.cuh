@@ -273,6 +273,19 @@ cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *cons
                               cudaStream_t st);
 cudaError_t launch_scatter_rows(const void *d_src, void *d_dst, const int64_t *d_dest, int64_t n,
                                 int elem_bytes, cudaStream_t st);
+// K5b: every comparison of a row-sharded job merged in ONE launch, all eight columns scattered by the same kernel.
+// A shard's ordered rows of all comparisons lie back to back in `res` (n rows); d_seg_off = its [n_comps + 1] segment
+// offsets on the device.  d_map_* (optional): local unit -> global unit table of a shard that was filled by several
+// uploads (multi-device context); mult = marker rows per unit.
+struct MergeShardView {
+    ResultSoA res;
+    int64_t n = 0;
+    const int64_t *d_seg_off = nullptr;
+    const int64_t *d_map_local = nullptr, *d_map_global = nullptr;
+    int n_map = 0, mult = 1;
+};
+cudaError_t launch_merge_all(int n_shards, int n_comps, int sort_key, const MergeShardView *shards,
+                             const int64_t *d_out_seg_off, const ResultSoA &out, int64_t row_base, cudaStream_t st);
 
 // choose_table.cpp
 const std::vector<double> &host_choose_table();

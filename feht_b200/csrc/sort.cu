@@ -575,6 +575,86 @@ scatter_rows_kernel(const unsigned char *__restrict__ src, unsigned char *__rest
     }
 }
 
+// ---- K5b: the same rank-based k-way merge for EVERY comparison of a sharded job in one launch, fused with the
+// scatter of all result columns.  Shard s holds its ordered rows of all comparisons back to back (segment c =
+// [seg_off_s[c], seg_off_s[c+1])); element j of segment c of shard s goes to
+//     out_seg_off[c] + j + sum over the other shards t of #{e in segment c of t : (key_e, rank_e, t) < (key, rank, s)}
+// -- one binary search per other shard inside that shard's segment, then the eight columns are written at once
+// (no position array, no per-column scatter launches, no loop over comparisons on the host).
+struct MergeAllShard {
+    const long long *row;
+    const int32_t *rank, *goa, *gob, *gta, *gtb;
+    const double *p, *ratio;
+    const long long *seg_off;     // device, [n_comps + 1]
+    // row remap for shards filled by several uploads (multi-device context): local unit -> global unit
+    const long long *map_local;   // device, [n_map + 1] local unit starts (null: rows are global already)
+    const long long *map_global;  // device, [n_map] global unit starts
+    int n_map, mult;              // mult = marker rows per unit (4 in SNP mode)
+};
+struct MergeAllArgs {
+    int n_shards, n_comps, sort_key;
+    long long row_base;           // added to remapped rows
+    MergeAllShard sh[kMaxShards];
+    long long flat_off[kMaxShards + 1];
+    const long long *out_seg_off; // device, [n_comps + 1]
+    ResultSoA out;
+};
+
+__global__ void __launch_bounds__(256) merge_all_kernel(const __grid_constant__ MergeAllArgs A) {
+    const long long total = A.flat_off[A.n_shards];
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        int s = 0;
+        while (g >= A.flat_off[s + 1]) ++s;
+        const MergeAllShard &S = A.sh[s];
+        const long long i = g - A.flat_off[s];
+        // comparison of element i: the last c with seg_off[c] <= i
+        int lo_c = 0, hi_c = A.n_comps;
+        while (hi_c - lo_c > 1) {
+            const int mid = (lo_c + hi_c) >> 1;
+            if (__ldg(S.seg_off + mid) <= i) lo_c = mid; else hi_c = mid;
+        }
+        const int c = lo_c;
+        const double kd = A.sort_key == FEHT_SORT_PVALUE_ASC ? S.p[i] : S.ratio[i];
+        const unsigned long long kb = merge_key_bits(kd, A.sort_key);
+        const uint32_t rk = uint32_t(S.rank[i]);
+        long long pos = __ldg(A.out_seg_off + c) + (i - __ldg(S.seg_off + c));
+        for (int t = 0; t < A.n_shards; ++t) {
+            if (t == s) continue;
+            const MergeAllShard &T = A.sh[t];
+            const long long t0 = __ldg(T.seg_off + c);
+            long long lo = t0, hi = __ldg(T.seg_off + c + 1);
+            const double *tk = A.sort_key == FEHT_SORT_PVALUE_ASC ? T.p : T.ratio;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                const unsigned long long ke = merge_key_bits(__ldg(tk + mid), A.sort_key);
+                bool before = ke < kb;
+                if (ke == kb) {
+                    const uint32_t re = uint32_t(__ldg(T.rank + mid));
+                    before = re < rk || (re == rk && t < s);
+                }
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            pos += lo - t0;
+        }
+        long long row = S.row[i];
+        if (S.map_local) {
+            const long long unit = row / S.mult;
+            int a = 0, b = S.n_map;
+            while (b - a > 1) {
+                const int mid = (a + b) >> 1;
+                if (__ldg(S.map_local + mid) <= unit) a = mid; else b = mid;
+            }
+            row = A.row_base + (__ldg(S.map_global + a) + (unit - __ldg(S.map_local + a))) * S.mult + (row - unit * S.mult);
+        }
+        A.out.row[pos] = row;
+        A.out.rank[pos] = int32_t(rk);
+        A.out.goa[pos] = S.goa[i]; A.out.gob[pos] = S.gob[i]; A.out.gta[pos] = S.gta[i]; A.out.gtb[pos] = S.gtb[i];
+        A.out.p[pos] = S.p[i];
+        A.out.ratio[pos] = S.ratio[i];
+    }
+}
+
 inline int blocks_for(int64_t n, int per) {
     int64_t b = (n + per - 1) / per;
     if (b < 1) b = 1;
@@ -743,6 +823,37 @@ cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *cons
     a.off[n_shards] = off;
     if (off == 0) return cudaSuccess;
     merge_rank_kernel<<<blocks_for(off, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_all(int n_shards, int n_comps, int sort_key, const MergeShardView *shards,
+                             const int64_t *d_out_seg_off, const ResultSoA &out, int64_t row_base, cudaStream_t st) {
+    if (n_shards < 0 || n_shards > kMaxShards) return cudaErrorInvalidValue;
+    MergeAllArgs a{};
+    a.n_shards = n_shards;
+    a.n_comps = n_comps;
+    a.sort_key = sort_key;
+    a.row_base = row_base;
+    long long off = 0;
+    for (int i = 0; i < n_shards; ++i) {
+        const MergeShardView &v = shards[i];
+        MergeAllShard &d = a.sh[i];
+        d.row = reinterpret_cast<const long long *>(v.res.row);
+        d.rank = v.res.rank; d.goa = v.res.goa; d.gob = v.res.gob; d.gta = v.res.gta; d.gtb = v.res.gtb;
+        d.p = v.res.p; d.ratio = v.res.ratio;
+        d.seg_off = reinterpret_cast<const long long *>(v.d_seg_off);
+        d.map_local = reinterpret_cast<const long long *>(v.d_map_local);
+        d.map_global = reinterpret_cast<const long long *>(v.d_map_global);
+        d.n_map = v.n_map;
+        d.mult = v.mult > 0 ? v.mult : 1;
+        a.flat_off[i] = off;
+        off += v.n;
+    }
+    a.flat_off[n_shards] = off;
+    a.out_seg_off = reinterpret_cast<const long long *>(d_out_seg_off);
+    a.out = out;
+    if (off == 0 || n_comps == 0) return cudaSuccess;
+    merge_all_kernel<<<blocks_for(off, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -97,3 +97,53 @@ def gather_and_merge_device(ctx, comparison: int, sort_key: int = capi.SORT_ABS_
             out[k] = merged[:total].cpu()
     torch.cuda.current_stream().synchronize()
     return out
+
+
+def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, dst: int = 0,
+                                host_out: dict | None = None, want_device: bool = False):
+    """The same exchange for EVERY comparison at once (one process per GPU): each rank hands over the ordered rows of
+    all its comparisons (feht_result_fetch_device with comparison = -1: eight device-to-device copies), eight padded
+    `dist.gather`s move them to rank `dst` over NVLink, and ONE call of feht_merge_shards_device (K5b) merges all
+    comparisons and scatters all columns.  Returns (columns, seg_off) on `dst` -- host tensors (into `host_out` when
+    given; device tensors with want_device) and the merged per-comparison offsets -- and (None, None) elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_comps = ctx.num_comparisons
+    seg = np.zeros(n_comps + 1, dtype=np.int64)
+    np.cumsum(ctx.result_counts(), out=seg[1:])
+    seg_t = torch.from_numpy(seg).to(dev)
+    segs = torch.empty((world, n_comps + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(segs, seg_t)
+    segs = segs.cpu().numpy()
+    sizes = [int(x) for x in segs[:, -1]]
+    n_max = max(sizes + [1])
+    local = {k: torch.empty(n_max, dtype=getattr(torch, dt), device=dev) for k, dt in DEV_DTYPES.items()}
+    if sizes[rank]:
+        ctx.fetch_device(-1, {k: v.data_ptr() for k, v in local.items()})
+    gathered = {}
+    for k, v in local.items():
+        lst = [torch.empty_like(v) for _ in range(world)] if rank == dst else None
+        dist.gather(v, lst, dst=dst)
+        gathered[k] = lst
+    if rank != dst:
+        return None, None
+    total = sum(sizes)
+    merged = {k: torch.empty(max(total, 1), dtype=getattr(torch, dt), device=dev) for k, dt in DEV_DTYPES.items()}
+    out_seg = np.zeros(n_comps + 1, dtype=np.int64)
+    torch.cuda.current_stream().synchronize()
+    shards = [({k: gathered[k][s].data_ptr() for k in DEV_DTYPES}, np.ascontiguousarray(segs[s])) for s in range(world)]
+    ctx.merge_shards_device(shards, n_comps, {k: v.data_ptr() for k, v in merged.items()}, out_seg, sort_key)
+    if want_device:
+        return {k: v[:total] for k, v in merged.items()}, out_seg
+    out = {}
+    for k in DEV_DTYPES:
+        if host_out is not None and k in host_out:
+            host_out[k][:total].copy_(merged[k][:total], non_blocking=True)
+            out[k] = host_out[k][:total]
+        else:
+            out[k] = merged[k][:total].cpu()
+    torch.cuda.current_stream().synchronize()
+    return out, out_seg

@@ -17,9 +17,11 @@
  *     returns the message (the host turns it into `error`, the reference's only failure mode);
  *   - plain pointers and sizes only; host pointers need only stay valid for the duration of
  *     the call (the library copies to the device before returning);
- *   - one context drives one GPU; a multi-GPU host makes one context per device (one process
- *     per GPU under torchrun, or several contexts in one process), shards marker rows across
- *     them and merges with feht_merge_sorted().  No context may be used from two threads at once.
+ *   - feht_create() makes a context that drives one GPU; feht_create_multi() makes ONE handle that shards the
+ *     marker rows over several GPUs of the box and merges the ordered shards on the device, behind the same entry
+ *     points (the Haskell host needs nothing else).  A host that runs one process per GPU (torchrun) makes one
+ *     single-device context per process, moves the ordered shards to one GPU itself and merges them there with
+ *     feht_merge_shards_device().  No context may be used from two threads at once.
  *   - there is no CPU fallback: without a usable sm_100-class device feht_create() fails.
  */
 #ifndef FEHT_CUDA_H
@@ -54,6 +56,19 @@ enum { FEHT_FET_TWO_TAIL = 0, FEHT_FET_ONE_TAIL = 1 };
 /* ---------------------------------------------------------------- context ---- */
 /* Replaces: nothing (the reference is a pure function); owns the device state. */
 int  feht_create(feht_ctx **out, int device);
+/*
+ * One handle for n_devices GPUs (north_star: "marker rows shard naturally across the 8 GPUs of one
+ * box; each GPU counts, tests and sorts its shard; the final per-comparison merge is a k-way merge of the sorted
+ * shards, with no other collectives").  Every upload call splits its rows contiguously over the devices (piece d of n
+ * rows = [n*d/D, n*(d+1)/D)) and uploads the pieces in parallel; comparisons and options are replicated; feht_run
+ * starts all shards side by side with Bonferroni's n = the job's row count (Comparison.hs:251), copies the ordered
+ * shards to device_ids[0] (cudaMemcpyPeerAsync, NVLink between peers) and merges ALL comparisons there with one kernel
+ * launch; feht_result_* then return the merged rows -- the same rows in the same order as one context holding
+ * everything.  A device id may be repeated (several shards on one GPU).  Differences from a single-device context:
+ * feht_set_stream is refused, feht_run_async blocks like feht_run.
+ */
+int  feht_create_multi(feht_ctx **out, const int *device_ids, int n_devices);
+int  feht_num_devices(const feht_ctx *ctx);   /* shards behind the handle (1 for feht_create) */
 void feht_destroy(feht_ctx *ctx);
 /* Message of the last failure on ctx (or of the last failed feht_create if ctx == NULL). */
 const char *feht_last_error(const feht_ctx *ctx);
@@ -233,6 +248,8 @@ int64_t feht_result_total(const feht_ctx *ctx);
  * Fetch comparison c's rows in final order into caller buffers of feht_result_count() entries
  * (any pointer may be NULL): the FETResult fields (FET.hs:84-89) + compRatio (Comparison.hs:37-40).
  * row = marker row index in order of insertion (+ row_base, see feht_set_row_base).
+ * comparison = -1 fetches the rows of EVERY comparison, back to back in comparison order (feht_result_total()
+ * entries; comparison c starts at the sum of feht_result_count() of the comparisons before it).
  */
 int feht_result_fetch(feht_ctx *ctx, int64_t comparison, int64_t *row, int32_t *goa, int32_t *gob,
                       int32_t *gta, int32_t *gtb, double *p, double *ratio, int32_t *name_rank);
@@ -247,7 +264,9 @@ int feht_set_row_base(feht_ctx *ctx, int64_t row_base);
 /* Device-side milliseconds of the last feht_run, by stage (CUDA events on the run's stream):
  * out[0] count, out[1] test+correct+filter, out[2] order, out[3] total, out[4] launches (count),
  * out[5] count-kernel launches, out[6] algorithmic bytes read by the count stage,
- * out[7] engine that counted the categories (FEHT_ENGINE_POPC, FEHT_ENGINE_GEMM or FEHT_ENGINE_GEMM_FP4). */
+ * out[7] engine that counted the categories (FEHT_ENGINE_POPC, FEHT_ENGINE_GEMM or FEHT_ENGINE_GEMM_FP4).
+ * Multi-device handle: out[0..2] are the slowest shard's stages, out[3] = slowest shard + merge, out[8] = the merge
+ * (peer copies + K5b) on the first device; launches and bytes are summed over the shards. */
 int feht_last_timings(const feht_ctx *ctx, double *out, int n);
 /* Sums over every run since the last reset (waits for the enqueued runs): out[0] runs, out[1] count ms,
  * out[2] test ms, out[3] order ms, out[4] total ms, out[5] kernel launches, out[6] count-kernel launches. */
@@ -273,6 +292,25 @@ int feht_merge_sorted_device(feht_ctx *ctx, int n_shards, const int64_t *n, cons
                              const int32_t *const *d_name_rank, int sort_key, int64_t *const *d_dest);
 int feht_scatter_rows_device(feht_ctx *ctx, const void *d_src, void *d_dst, const int64_t *d_dest,
                              int64_t n, int32_t elem_bytes);
+
+/*
+ * The merge of a row-sharded job in one call (K5b), for hosts that run one process per GPU: every shard's ordered rows
+ * of ALL comparisons, back to back in the order feht_result_fetch_device returns them comparison by comparison, have
+ * been moved to this context's GPU; seg_off (HOST array, n_comparisons + 1 entries, seg_off[0] = 0) says where each
+ * comparison's rows start inside a shard's columns.  One kernel launch ranks every row against the other shards'
+ * segments of its comparison (binary searches on the total order: key bits, name rank, shard) and writes all eight
+ * columns to their merged places.  `out`: device columns with room for the sum of all shards' rows; out->seg_off
+ * (HOST, n_comparisons + 1) receives the merged offsets.  At most 32 shards.
+ */
+typedef struct {
+    const int64_t *row;
+    const int32_t *goa, *gob, *gta, *gtb;
+    const double  *p, *ratio;
+    const int32_t *name_rank;
+    const int64_t *seg_off;
+} feht_shard_rows;
+int feht_merge_shards_device(feht_ctx *ctx, int n_shards, int64_t n_comparisons, const feht_shard_rows *shards,
+                             int sort_key, const feht_shard_rows *out);
 
 /* Host-built table of the reference's `choose` values C[n][k'], n < 1000, k' <= n/2 (the
  * arithmetic of math-functions 0.2.1.0), as uploaded to the device; for tests.

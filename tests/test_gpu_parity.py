@@ -1104,7 +1104,7 @@ def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
     lens[:100] = rng.integers(0, 64, size=100)                      # very short rows too
     alphabet = np.frombuffer(b"01-1 0NX", dtype=np.uint8)
     rows = [alphabet[rng.integers(0, len(alphabet), size=int(n))] for n in lens]
-    snp_alphabet = np.frombuffer(b"ACGTacgt-N01x", dtype=np.uint8)
+    snp_alphabet = np.frombuffer(b"ACGTacgt-N?.x", dtype=np.uint8)
     snp_rows = [snp_alphabet[rng.integers(0, len(snp_alphabet), size=int(n))] for n in lens]
     for snp, data in ((False, rows), (True, snp_rows)):
         planes = {}
@@ -1127,6 +1127,19 @@ def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
             assert c.num_rows == (4 * R if snp else R)
             for p, a in enumerate(planes[0]):
                 assert (c.read_plane(p, 0, R) == a).all(), (snp, p)
+    # a literal '0' / '1' in SNP rows is rejected by whichever producer meets it: the DMA + K0 path takes the front of
+    # the row range, the host threads the back (Table.hs:194-205)
+    for where, ch in ((200, b"1"), (R - 3, b"0")):
+        bad = list(snp_rows)
+        r = bytearray(bytes(bad[where]))
+        r[len(r) // 2] = ch[0]
+        bad[where] = np.frombuffer(bytes(r), dtype=np.uint8)
+        with capi.Context(0) as c:
+            c.set_samples(S)
+            c.set_host_threads(5)
+            with pytest.raises(capi.FehtError):
+                c.add_snp_chars(bad)
+            assert c.num_rows == 0
 
 
 def test_filtered_output_single_pass_and_capacity_overflow(ctx):

@@ -67,3 +67,213 @@ def test_snp_chars_with_literal_digits_are_rejected(ctx):
         assert (got[k][back] == want[k]).all(), k
     # site 17's four allele rows all count the literal '0' at column 200 as absent
     assert all(want["gtb"][4 * 17 + j] >= 1 for j in range(4))
+
+
+# ------------------------------------------------------------------------- multi-device context
+def _device_count():
+    import ctypes
+    try:
+        cudart = ctypes.CDLL("libcudart.so")
+    except OSError:
+        try:
+            cudart = ctypes.CDLL("libcudart.so.12")
+        except OSError:
+            return 1
+    n = ctypes.c_int(0)
+    cudart.cudaGetDeviceCount(ctypes.byref(n))
+    return max(1, n.value)
+
+
+def _device_lists():
+    """Shards on one GPU always (the driver's test box has one); real device lists when the box has more."""
+    lists = [[0, 0], [0, 0, 0]]
+    n = _device_count()
+    if n >= 2:
+        lists += [[0, 1], list(range(min(n, 8)))]
+    return lists
+
+
+def _random_chars(rng, n_rows, n_samples, p_missing=0.05):
+    freq = rng.beta(0.3, 0.3, size=(n_rows, 1))
+    cells = np.where(rng.random((n_rows, n_samples)) < freq, ord("1"), ord("0")).astype(np.uint8)
+    miss = rng.random((n_rows, n_samples)) < p_missing
+    cells[miss] = ord("-")
+    return cells
+
+
+def _same_results(a, b, n_comps):
+    assert a.result_total() == b.result_total()
+    for ci in range(n_comps):
+        assert a.result_count(ci) == b.result_count(ci), ci
+        x, y = a.fetch(ci), b.fetch(ci)
+        for k in x:
+            if k == "p":
+                assert ((x[k] == y[k]) | (np.isnan(x[k]) & np.isnan(y[k]))).all(), (ci, k)
+            else:
+                assert (x[k] == y[k]).all(), (ci, k)
+
+
+@pytest.mark.parametrize("devices", _device_lists())
+def test_multi_device_context_equals_single_context_and_oracle(cuda_lib, devices):
+    """feht_create_multi: the same calls on one handle that shards the rows over `devices` give the rows of a single
+    context in the same order -- explicit comparisons + a category, dense and filtered, both sort keys, ranks given
+    and default, rows added in one call and in several (the remap path), and a row base."""
+    rng = np.random.default_rng(77)
+    S, R = 700, 5000
+    cells = _random_chars(rng, R, S)
+    cells[:40, :] = ord("0")            # many exact ties: the order is decided by the name rank
+    vos = rng.integers(-1, 5, size=S).astype(np.int32)
+    g1, g2 = np.arange(0, 300), np.arange(250, 700)        # overlapping groups
+    rank = rng.permutation(R).astype(np.int32)
+    for given_rank, splits, base in ((True, [R], 0), (False, [R], 1000), (False, [1700, 400, 2900], 0),
+                                     (True, [10, R - 10], 0)):
+        with capi.Context(0) as one, capi.Context(devices) as many:
+            assert many.num_devices == len(devices) and one.num_devices == 1
+            for c in (one, many):
+                c.set_samples(S)
+                c.set_row_base(base)
+                r0 = 0
+                for n in splits:
+                    c.add_rows_chars(cells[r0:r0 + n], rank[r0:r0 + n] if given_rank else None)
+                    r0 += n
+                c.add_comparison(g1, g2)
+                c.add_category(vos, 5)
+                assert c.num_rows == R and c.num_comparisons == 1 + 10 + 5
+            for corr, rf, key in ((capi.CORRECTION_BONFERRONI, 0.0, capi.SORT_ABS_RATIO_DESC),
+                                  (capi.CORRECTION_NONE, 0.25, capi.SORT_ABS_RATIO_DESC),
+                                  (capi.CORRECTION_BONFERRONI, 0.1, capi.SORT_PVALUE_ASC)):
+                one.run(corr, rf, key)
+                many.run(corr, rf, key)
+                _same_results(one, many, 16)
+            # and against the oracle (the explicit comparison, filtered)
+            many.run(capi.CORRECTION_BONFERRONI, 0.2)
+            want = oracle.run_comparison(cells, g1, g2, correction=1, bonferroni_n=R)
+            order = oracle.filter_and_order(want["ratio"], rank if given_rank else None, 0.2)
+            got = many.fetch(0)
+            assert (got["row"] == order + base).all()
+            for k in ("goa", "gob", "gta", "gtb", "ratio"):
+                assert (got[k] == want[k][order]).all(), k
+            l = (want["goa"] + want["gob"] + want["gta"] + want["gtb"])[order]
+            assert p_close(got["p"], want["p"][order], l >= 1000).all()
+            t = many.timings()
+            assert t["merge_ms"] > 0 and t["total_ms"] >= t["merge_ms"]
+            # planes read back through the handle are the single context's
+            for pl in (0, 1):
+                assert (many.read_plane(pl, 0, R) == one.read_plane(pl, 0, R)).all()
+
+
+def test_multi_device_snp_text_packed_and_synthetic(cuda_lib):
+    """The other upload paths through a multi-device handle: SNP sites (4 marker rows per unit), packed planes, the
+    data file's text (cut at line boundaries, line offsets rebased) and the device generator."""
+    from helpers import make_spec, pack_rows
+    devices = [0, 0, 0] if _device_count() < 3 else [0, 1, 2]
+    rng = np.random.default_rng(78)
+    S, n_sites = 333, 901
+    sites = rng.choice(np.frombuffer(b"ACGTacgt-N", np.uint8), size=(n_sites, S), p=[.3, .2, .2, .2, .02, .02, .02, .02, .01, .01])
+    vos = rng.integers(0, 4, size=S).astype(np.int32)
+    with capi.Context(0) as one, capi.Context(devices) as many:
+        for c in (one, many):
+            c.set_samples(S)
+            c.add_snp_chars(sites[:400])
+            c.add_snp_chars(sites[400:])
+            c.add_category(vos, 4)
+            c.run(capi.CORRECTION_BONFERRONI, 0.05)
+        assert many.num_rows == 4 * n_sites
+        _same_results(one, many, 10)
+        # packed binary planes
+        cells = _random_chars(rng, 1234, S)
+        v, d = pack_rows(cells)
+        for c in (one, many):
+            c.set_samples(S)
+            c.add_rows_packed(v, d)
+            c.add_category(vos, 4)
+            c.run(capi.CORRECTION_NONE, 0.0)
+        _same_results(one, many, 10)
+        # text of the data file
+        lines = [b"gene%05d\t" % i + b"\t".join(bytes([ch]) for ch in cells[i]) for i in range(len(cells))]
+        text = b"\r\n".join(lines) + b"\n"
+        for c in (one, many):
+            c.set_samples(S)
+            begin, name_len = c.add_rows_text(text, "\t", False)
+            assert len(begin) == len(cells)
+            assert all(text[b:b + n] == b"gene%05d" % i for i, (b, n) in enumerate(zip(begin[:50], name_len[:50])))
+            c.set_name_rank(np.arange(len(cells))[::-1].astype(np.int32))
+            c.add_category(vos, 4)
+            c.run(capi.CORRECTION_NONE, 0.1)
+        _same_results(one, many, 10)
+        # device generator: global row indices must not depend on the sharding
+        sp = make_spec(capi.SynthSpec, S)
+        for c in (one, many):
+            c.set_samples(S)
+            c.generate_synthetic(sp, False, 5000, 3000)
+            c.add_comparison(np.arange(0, 150), np.arange(150, 333))
+            c.run(capi.CORRECTION_BONFERRONI, 0.0)
+        assert (many.read_plane(0, 0, 3000) == one.read_plane(0, 0, 3000)).all()
+        _same_results(one, many, 1)
+        # a failing shard fails the call loudly and leaves no partial upload behind
+        bad = sites.copy()
+        bad[800, 5] = ord("1")
+        many.set_samples(S)
+        with pytest.raises(capi.FehtError):
+            many.add_snp_chars(bad)
+        assert many.num_rows == 0
+        with pytest.raises(capi.FehtError):
+            many.set_stream(1234)
+
+
+def test_merge_shards_device_all_comparisons_in_one_call(cuda_lib):
+    """feht_merge_shards_device (K5b) as a one-process-per-GPU host uses it: three single-device contexts hold row
+    shards, their ordered columns of ALL comparisons are handed over as device buffers, one call merges them."""
+    import torch
+    rng = np.random.default_rng(79)
+    S, R = 400, 3000
+    cells = _random_chars(rng, R, S)
+    cells[:30] = ord("1")
+    vos = rng.integers(0, 6, size=S).astype(np.int32)
+    cuts = [0, 900, 1000, R]
+    n_comps = 15 + 6
+    dev = torch.device("cuda", 0)
+    dt = {"row": torch.int64, "goa": torch.int32, "gob": torch.int32, "gta": torch.int32, "gtb": torch.int32,
+          "p": torch.float64, "ratio": torch.float64, "name_rank": torch.int32}
+    with capi.Context(0) as whole:
+        whole.set_samples(S)
+        whole.add_rows_chars(cells)
+        whole.add_category(vos, 6)
+        whole.run(capi.CORRECTION_BONFERRONI, 0.15)
+        shards, keep = [], []
+        ctxs = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            c = capi.Context(0)
+            ctxs.append(c)
+            c.set_samples(S)
+            c.set_row_base(a)
+            c.add_rows_chars(cells[a:b])
+            c.add_category(vos, 6)
+            c.run(capi.CORRECTION_BONFERRONI, 0.15, capi.SORT_ABS_RATIO_DESC, R)
+            seg = np.zeros(n_comps + 1, np.int64)
+            for ci in range(n_comps):
+                seg[ci + 1] = seg[ci] + c.result_count(ci)
+            cols = {k: torch.empty(max(1, int(seg[-1])), dtype=t, device=dev) for k, t in dt.items()}
+            for ci in range(n_comps):
+                if seg[ci + 1] > seg[ci]:
+                    c.fetch_device(ci, {k: v.data_ptr() + int(seg[ci]) * v.element_size() for k, v in cols.items()})
+            keep.append(cols)
+            shards.append(({k: v.data_ptr() for k, v in cols.items()}, seg))
+        total = sum(int(s[1][-1]) for s in shards)
+        assert total == whole.result_total()
+        out = {k: torch.empty(max(1, total), dtype=t, device=dev) for k, t in dt.items()}
+        out_seg = np.zeros(n_comps + 1, np.int64)
+        whole_ptrs = {k: v.data_ptr() for k, v in out.items()}
+        ctxs[0].merge_shards_device(shards, n_comps, whole_ptrs, out_seg)
+        torch.cuda.synchronize()
+        for ci in range(n_comps):
+            want = whole.fetch(ci)
+            assert out_seg[ci + 1] - out_seg[ci] == len(want["row"])
+            for k in dt:
+                got = out[k][int(out_seg[ci]):int(out_seg[ci + 1])].cpu().numpy()
+                if k == "p":
+                    assert ((got == want[k]) | (np.isnan(got) & np.isnan(want[k]))).all(), (ci, k)
+                else:
+                    assert (got == want[k]).all(), (ci, k)
+        for c in ctxs:
+            c.close()
