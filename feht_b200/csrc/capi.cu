@@ -125,6 +125,9 @@ struct feht_ctx {
     Timings tm;
 
     // text upload (text_load.cu): scratch on the device, and the lines of the last call for the host
+    DevBuf<unsigned long long> dd_keys;    // N4 dedup of exact tests (fet.cu): table, owners, waiting list, its length
+    DevBuf<uint32_t> dd_owner, dd_count;
+    DevBuf<uint2> dd_list;
     DevBuf<unsigned int> snp_digit_flag;   // feht_add_snp_chars: K0 met a literal '0' / '1'
     DevBuf<uint32_t> txt_counts;
     DevBuf<int32_t> txt_starts, txt_name_len;
@@ -595,6 +598,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
     release(c->live_rows); release(c->live_count); release(c->snp_digit_flag);
+    release(c->dd_keys); release(c->dd_owner); release(c->dd_count); release(c->dd_list);
     release(c->txt_counts); release(c->txt_starts); release(c->txt_name_len); release(c->txt_flags);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
@@ -1138,6 +1142,11 @@ std::vector<std::vector<GemmF8Column>> f8_columns(const feht_ctx *c, const std::
     }
     return passes;
 }
+// FEHT_DEDUP=0: every exact test evaluates its own hypergeometric sum (A/B measurements)
+bool dedup_enabled() {
+    static const bool on = [] { const char *e = getenv("FEHT_DEDUP"); return !(e && atoi(e) == 0); }();
+    return on;
+}
 // FEHT_SORT=onesweep keeps the tile-per-CTA sort for every size (A/B measurements and tests of that path)
 bool sort_engine_allows_coop() {
     static const bool allow = [] {
@@ -1641,6 +1650,21 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     PvalueIo io{};
     io.rec = c->r_rec.p;
     io.r_comp = c->r_comp.p;
+    if (n > 0 && hyp_heavy && dedup_enabled()) {
+        // N4: one evaluation per distinct 2x2 table (FEHT_DEDUP=0 switches it off).  Table of 2n slots (a power of two,
+        // at most 2^25 = 256 MB of keys); when it runs full a test simply computes its own p.
+        size_t slots = 4096;
+        while (slots < size_t(2) * size_t(n) && slots < (size_t(1) << 25)) slots <<= 1;
+        CU(c, ensure(c->dd_keys, slots));
+        CU(c, ensure(c->dd_owner, slots));
+        CU(c, ensure(c->dd_list, size_t(n)));
+        CU(c, ensure(c->dd_count, 1));
+        CU(c, cudaMemsetAsync(c->dd_keys.p, 0, slots * 8, c->st));
+        CU(c, cudaMemsetAsync(c->dd_count.p, 0, 4, c->st));
+        io.dd_keys = c->dd_keys.p; io.dd_owner = c->dd_owner.p; io.dd_mask = uint32_t(slots - 1);
+        io.dd_list = c->dd_list.p; io.dd_count = c->dd_count.p;
+        ++launches;   // pvalue_fixup_kernel
+    }
     if (n > 0 && fused) {
         if (int rc = order()) return rc;
         CU(c, cudaEventRecord(ev[3], c->st));

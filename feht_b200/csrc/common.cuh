@@ -231,6 +231,14 @@ struct PvalueIo {
     const uint32_t *perm_a, *perm_b, *d_sel;
     ResultSoA out;
     int64_t row_base;
+    // N4, optional: exact tests with the same 2x2 table are evaluated once.  dd_keys: open-addressing
+    // table of dd_mask + 1 packed tables (zeroed by the caller), dd_owner: the test that computes a slot's p,
+    // dd_list / dd_count: the tests that wait for it (zeroed count); pvalue_fixup copies the owners' p afterwards.
+    unsigned long long *dd_keys;
+    uint32_t *dd_owner;
+    uint32_t dd_mask;
+    uint2 *dd_list;
+    uint32_t *dd_count;
 };
 cudaError_t launch_pvalues(const PvalueIo &io, int64_t n, const double *d_choose, int correction,
                            double bonferroni_n, int one_tail, bool hyp_heavy, cudaStream_t st);

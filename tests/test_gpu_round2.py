@@ -277,3 +277,40 @@ def test_merge_shards_device_all_comparisons_in_one_call(cuda_lib):
                     assert (got == want[k]).all(), (ci, k)
         for c in ctxs:
             c.close()
+
+
+# ------------------------------------------------------------------------- N4: one evaluation per distinct table
+def test_exact_tests_with_repeated_tables_are_deduplicated_bit_exact(ctx):
+    """FET.hs:105-112 is a pure function of the 2x2 table: K3b evaluates every distinct table once (hash dedup) and
+    copies p to the other tests.  A matrix built from few distinct row patterns (heavy duplication), plus random
+    rows, through both orders and with a filter -- bit-exact against the oracle on every row."""
+    rng = np.random.default_rng(80)
+    S = 640
+    patterns = _random_chars(rng, 37, S, p_missing=0.03)
+    cells = np.concatenate([patterns[rng.integers(0, 37, size=20000)], _random_chars(rng, 3000, S, p_missing=0.02)])
+    cells = cells[rng.permutation(len(cells))]
+    g1, g2 = np.arange(0, 280), np.arange(280, 640)
+    vos = (np.arange(S) * 3 // S).astype(np.int32)
+    ctx.set_samples(S)
+    ctx.add_rows_chars(cells)
+    ctx.add_comparison(g1, g2)
+    ctx.add_category(vos, 3)
+    comps = [(g1, g2)] + [(np.flatnonzero(vos == i), np.flatnonzero(vos == j)) for i in range(3) for j in range(i + 1, 3)] \
+        + [(np.flatnonzero(vos == v), np.flatnonzero(vos != v)) for v in range(3)]
+    for corr, rf, key in ((1, 0.0, capi.SORT_ABS_RATIO_DESC), (0, 0.05, capi.SORT_ABS_RATIO_DESC),
+                          (1, 0.0, capi.SORT_PVALUE_ASC)):
+        ctx.run(corr, rf, key)
+        for ci, (a, b) in enumerate(comps):
+            want = oracle.run_comparison(cells, a, b, correction=corr, bonferroni_n=len(cells), n_threads=8)
+            got = ctx.fetch(ci)
+            keep = np.flatnonzero(rf <= np.abs(want["ratio"]))
+            assert len(got["row"]) == len(keep), (ci, rf)
+            back = np.argsort(got["row"], kind="stable")
+            assert (got["row"][back] == keep).all()
+            for k in ("goa", "gob", "gta", "gtb", "ratio"):
+                assert (got[k][back] == want[k][keep]).all(), (ci, k)
+            l = (want["goa"] + want["gob"] + want["gta"] + want["gtb"])[keep]
+            assert (l < 1000).all()
+            assert (got["p"][back] == want["p"][keep]).all(), (ci, "p: the exact branch is bit-exact")
+            if key == capi.SORT_PVALUE_ASC:
+                assert (got["p"][:-1] <= got["p"][1:]).all()
