@@ -184,23 +184,9 @@ class ClockSampler:
 
 
 def _synth_rows(spec, snp, row0, n_rows, threads):
-    """oracle.synth_fill on `threads` Python threads (ctypes releases the GIL): rows [row0, row0 + n_rows)."""
-    import oracle
-    from concurrent.futures import ThreadPoolExecutor
-    threads = max(1, min(threads, n_rows // 1000 or 1))
-    if threads == 1:
-        return oracle.synth_fill(spec, snp, row0, n_rows)
-    out = np.empty((n_rows, spec.n_samples), dtype=np.uint8)
-    cuts = [n_rows * t // threads for t in range(threads + 1)]
-
-    def job(t):
-        a, b = cuts[t], cuts[t + 1]
-        if b > a:
-            oracle.lib().fo_synth_fill(__import__("ctypes").byref(spec), int(snp), row0 + a, b - a,
-                                       out[a:b].ctypes.data_as(__import__("ctypes").c_void_p))
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(job, range(threads)))
-    return out
+    """oracle.synth_fill on `threads` Python threads: rows [row0, row0 + n_rows)."""
+    from helpers import synth_rows
+    return synth_rows(spec, snp, row0, n_rows, threads)
 
 
 def cpu_baseline(sample_rows: int, threads: int, reference_style: bool = True, reps: int = 1):
@@ -383,10 +369,13 @@ def run_config(name, cfg, capi, sharding, torch, dist, world, rank, local_rank, 
         total_marker_rows = rows_total * mult
         merged_total = [0]
 
-        def step():
+        merge_times = {}
+
+        def step(times=None):
             ctx.run(capi.CORRECTION_BONFERRONI, rf, capi.SORT_ABS_RATIO_DESC, total_marker_rows)
             if world > 1:
-                cols, seg = sharding.gather_and_merge_all_device(ctx, capi.SORT_ABS_RATIO_DESC, 0, want_device=True)
+                cols, seg = sharding.gather_and_merge_all_device(ctx, capi.SORT_ABS_RATIO_DESC, 0, want_device=True,
+                                                                 times=times)
                 if rank == 0:
                     merged_total[0] = int(seg[-1])
             else:
@@ -405,6 +394,9 @@ def run_config(name, cfg, capi, sharding, torch, dist, world, rank, local_rank, 
             barrier()
         acc = ctx.timings_accumulated(reset=True)
         t = ctx.timings()
+        if world > 1:
+            step(merge_times)     # one more, untimed step with synchronising laps: where the exchange spends its time
+            ctx.timings_accumulated(reset=True)
         ms = torch.tensor([ev0.elapsed_time(ev1) / steps, acc["count_ms"] / steps, acc["test_ms"] / steps,
                            acc["order_ms"] / steps, acc["total_ms"] / steps], device=dev, dtype=torch.float64)
         surv = torch.tensor([ctx.result_total()], device=dev, dtype=torch.int64)
@@ -421,6 +413,7 @@ def run_config(name, cfg, capi, sharding, torch, dist, world, rank, local_rank, 
                "stage_ms_max_over_ranks": {"count": ms[1], "test": ms[2], "order": ms[3], "library_total": ms[4],
                                            "merge_and_host": max(0.0, ms[0] - ms[4])},
                "engine": {1: "popc (K1)", 2: "gemm i8 (K2)", 3: "gemm mxf4 (K2)", 4: "gemm e5m2 (K2)"}.get(int(t["engine"]), "?"),
+               "exchange_breakdown_rank0_ms": merge_times if world > 1 else None,
                "timer": "CUDA events on the launching stream around the steps (run + gather + merge), max over ranks"}
         # ---- rooflines of the stages, per rank (this rank's shard: bytes of its planes / its stage time)
         planes = 3 if snp else 2

@@ -60,7 +60,7 @@ def build_cuda(verbose: bool = False, ptxas_info: bool = False) -> Path:
     objs = []
     rebuilt = False
     for src in _sources():
-        flags = ARCH + COMMON + EXTRA.get(src.name, [])
+        flags = ARCH + COMMON + EXTRA.get(src.name, []) + os.environ.get("FEHT_EXTRA_NVCC_FLAGS", "").split()
         if ptxas_info and src.suffix == ".cu":
             flags = flags + ["-Xptxas", "-v"]
         obj = OBJ / (src.name + ".o")

@@ -32,7 +32,7 @@ EXPORTS = [
     "feht_choose_table", "feht_eval_tables", "feht_result_fetch_device", "feht_merge_sorted_device",
     "feht_scatter_rows_device", "feht_run_async", "feht_timings_accumulated",
     "feht_set_host_threads", "feht_last_upload_host_rows", "feht_add_rows_text", "feht_text_lines", "feht_set_name_rank", "feht_set_fet_mode", "feht_pack_chars_host",
-    "feht_create_multi", "feht_num_devices", "feht_merge_shards_device",
+    "feht_create_multi", "feht_num_devices", "feht_merge_shards_device", "feht_set_comparison_window",
     # include/feht_host.h
     "feht_host_run", "feht_host_plan", "feht_host_show_double", "feht_host_free",
 ]
@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
     L.feht_host_free.argtypes = [vp]
     L.feht_host_free.restype = None
     L.feht_set_row_base.argtypes = [vp, i64]
+    L.feht_set_comparison_window.argtypes = [vp, i64, i64]
     L.feht_last_timings.argtypes = [vp, P(f64), C.c_int]
     L.feht_merge_sorted.argtypes = [C.c_int, P(i64), P(vp), P(vp), C.c_int, vp, vp]
     L.feht_choose_table.argtypes = [vp, i64]
@@ -417,6 +418,10 @@ class Context:
 
     def set_count_engine(self, engine: int):
         self._check(self._L.feht_set_count_engine(self._h, engine))
+
+    def set_comparison_window(self, first: int = 0, count: int = -1):
+        """Emit only comparisons [first, first + count) in the following runs (count < 0: all)."""
+        self._check(self._L.feht_set_comparison_window(self._h, first, count))
 
     def set_row_base(self, base: int):
         self._check(self._L.feht_set_row_base(self._h, base))

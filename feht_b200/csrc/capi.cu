@@ -85,6 +85,11 @@ struct feht_ctx {
     std::vector<Cat> cats;
     int engine = FEHT_ENGINE_AUTO;
     int fet_mode = FEHT_FET_TWO_TAIL;
+    // feht_set_comparison_window: a run emits the comparisons [win_first, win_first + win_count) only (win_count < 0:
+    // all).  While a window is set the counts of the last run are kept (counts_ready) and the next window starts at K3.
+    int64_t win_first = 0, win_count = -1;
+    bool counts_ready = false;
+    int counts_engine = -1;
 
     double *d_choose = nullptr;
     DevBuf<unsigned char> stage[2];
@@ -483,6 +488,7 @@ int add_chars_common(feht_ctx *c, const uint8_t *chars, const int64_t *row_offse
     c->last_upload_host_rows = host_rows.load();
     c->n_units += n;
     c->has_results = false;
+    c->counts_ready = false;
     c->rank_is_perm = -1;
     return FEHT_OK;
 }
@@ -529,6 +535,7 @@ int add_packed_common(feht_ctx *c, const uint64_t *const *src_planes, const int 
     if (int rc = staged_upload(c, next_piece, consume)) return rc;
     c->n_units += n;
     c->has_results = false;
+    c->counts_ready = false;
     c->rank_is_perm = -1;
     return FEHT_OK;
 }
@@ -734,6 +741,7 @@ extern "C" int feht_set_samples(feht_ctx *c, int64_t n_samples) {
     // (a category's value_of_sample has exactly S entries; keeping it across a larger S would be read out of bounds)
     c->comps.clear();
     c->cats.clear();
+    c->counts_ready = false;
     c->S = n_samples;
     c->W = ((n_samples + 63) / 64 + 1) & ~int64_t(1);  // even number of 64-bit words: 16-byte rows
     c->snp = -1;
@@ -769,6 +777,7 @@ extern "C" int feht_clear_rows(feht_ctx *c) {
     c->have_rank = -1;
     c->min_row_len = std::numeric_limits<int64_t>::max();
     c->has_results = false;
+    c->counts_ready = false;
     return FEHT_OK;
 }
 
@@ -896,6 +905,7 @@ extern "C" int feht_add_rows_text(feht_ctx *c, const char *text, int64_t len, ch
     c->n_units = units;
     c->rank_is_perm = -1;
     c->has_results = false;
+    c->counts_ready = false;
     if (n_lines_out) *n_lines_out = units - first_unit;
     return FEHT_OK;
 }
@@ -966,6 +976,7 @@ extern "C" int feht_generate_synthetic(feht_ctx *c, const feht_synth_spec *spec,
     c->min_row_len = std::min(c->min_row_len, c->S);
     c->n_units += n_rows;
     c->has_results = false;
+    c->counts_ready = false;
     return FEHT_OK;
 }
 
@@ -1004,6 +1015,7 @@ extern "C" int64_t feht_add_comparison(feht_ctx *c, const int32_t *g1, int64_t n
     c->comps.push_back(std::move(cp));
     c->gemm_ready = false;
     c->plan_ready = false;  // explicit slots come first: the categories' slot base moves
+    c->counts_ready = false;
     c->has_results = false;
     return int64_t(c->comps.size()) - 1;
 }
@@ -1025,6 +1037,7 @@ extern "C" int64_t feht_add_category(feht_ctx *c, const int32_t *value_of_sample
     c->cats.push_back(std::move(cat));
     c->gemm_ready = false;
     c->plan_ready = false;
+    c->counts_ready = false;
     const int64_t first = int64_t(c->comps.size());
     for (int i = 0; i < n_values; ++i)
         for (int j = i + 1; j < n_values; ++j) {
@@ -1047,6 +1060,7 @@ extern "C" int feht_clear_comparisons(feht_ctx *c) {
     c->cats.clear();
     c->gemm_ready = false;
     c->plan_ready = false;
+    c->counts_ready = false;
     c->has_results = false;
     return FEHT_OK;
 }
@@ -1072,6 +1086,25 @@ extern "C" int feht_set_count_engine(feht_ctx *c, int engine) {
     MULTI(c, multi::set_count_engine(c->multi, engine));
     if (engine < FEHT_ENGINE_AUTO || engine > FEHT_ENGINE_GEMM_F8) return fail(c, FEHT_E_INVALID, "unknown engine");
     c->engine = engine;
+    c->counts_ready = false;
+    return FEHT_OK;
+}
+
+// Emit only the comparisons [first, first + count) in the following runs (count < 0: all again).  For outputs too
+// large for one run -- the reference's default ratioFilter 0 keeps every test (Comparison.hs:148), so a category of
+// V values over R rows is (V(V-1)/2 + V) * R result rows -- the host walks the comparisons window by window:
+// run, fetch, next window.  The contingency counts are computed by the first window's run and kept while a window
+// stays set (they do not depend on the window); rows, comparisons, the engine or feht_set_samples reset them.
+extern "C" int feht_set_comparison_window(feht_ctx *c, int64_t first, int64_t count) {
+    if (!c) return FEHT_E_INVALID;
+    MULTI(c, multi::set_comparison_window(c->multi, first, count));
+    if (first < 0) return fail(c, FEHT_E_INVALID, "window start < 0");
+    if (count < 0) { first = 0; count = -1; }
+    if (c->win_count < 0 || count < 0) c->counts_ready = false;   // entering / leaving windowed mode: count afresh
+    c->win_first = first;
+    c->win_count = count;
+    c->plan_ready = false;     // the screen groups list the emitted comparisons
+    c->has_results = false;
     return FEHT_OK;
 }
 
@@ -1201,14 +1234,21 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     if (sort_key != FEHT_SORT_ABS_RATIO_DESC && sort_key != FEHT_SORT_PVALUE_ASC)
         return fail(c, FEHT_E_INVALID, "unknown sort key %d", sort_key);
     if (ratio_filter != ratio_filter) return fail(c, FEHT_E_INVALID, "ratio_filter is NaN");
-    const int n_comps = int(c->comps.size());
+    const int n_all = int(c->comps.size());
+    // the comparisons this run emits: all of them, or the window of feht_set_comparison_window (local index i <->
+    // comparison w0 + i; the pair-slots are counted for every comparison either way)
+    int w0 = 0, n_comps = n_all;
+    if (c->win_count >= 0) {
+        w0 = int(std::min<int64_t>(c->win_first, n_all));
+        n_comps = int(std::min<int64_t>(c->win_count, n_all - w0));
+    }
     const int64_t R = marker_rows(c);
-    if (n_comps > 65535) return fail(c, FEHT_E_INVALID, "more than 65535 comparisons in one run");
+    if (n_comps > 65535) return fail(c, FEHT_E_INVALID, "more than 65535 comparisons in one run (use feht_set_comparison_window)");
     if (R > int64_t(0x7fffffff)) return fail(c, FEHT_E_INVALID, "more than 2^31-1 marker rows in one context");
     if (c->have_rank != 1 && c->row_base + R > int64_t(0x7fffffff))
         return fail(c, FEHT_E_INVALID, "row_base + rows exceeds 2^31-1: pass name_rank (the default rank is the global row index)");
     if (bonferroni_n <= 0) bonferroni_n = R;
-    c->seg_off.assign(size_t(n_comps) + 1, 0);
+    c->seg_off.assign(size_t(n_all) + 1, 0);
     c->n_surv = 0;
     if (n_comps == 0 || R == 0) {
         if (int rc = settle_all(c)) return rc;
@@ -1216,6 +1256,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         c->has_results = true;
         return FEHT_OK;
     }
+    c->seg_off.assign(size_t(n_comps) + 1, 0);   // offsets of the emitted comparisons; widened to all at the end
 
     // V.! bounds (Comparison.hs:123): every referenced column must exist in every row
     const int64_t row_len = std::min(c->min_row_len, c->S);
@@ -1229,7 +1270,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     const size_t mrow = size_t(plan.w4pad) * 2;  // 64-bit words per padded mask row
     std::vector<int> cat_slot0(c->cats.size(), -1), cat_tot(c->cats.size(), -1);
     int n_slots = 0;
-    for (int i = 0; i < n_comps; ++i) if (c->comps[size_t(i)].kind == 0) ++n_slots;
+    for (int i = 0; i < n_all; ++i) if (c->comps[size_t(i)].kind == 0) ++n_slots;
     const int n_explicit = n_slots;
     for (size_t k = 0; k < c->cats.size(); ++k) {
         cat_slot0[k] = n_slots;
@@ -1257,7 +1298,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         constexpr int kExplicitPerGroup = 64;
         std::vector<int> cat_first(c->cats.size(), -1);  // first comparison index of each category
         int e = 0;
-        for (int i = 0; i < n_comps; ++i) {
+        for (int i = 0; i < n_all; ++i) {
             const Comp &cp = c->comps[size_t(i)];
             if (cp.kind != 0) {
                 if (cat_first[size_t(cp.cat)] < 0) cat_first[size_t(cp.cat)] = i;
@@ -1266,6 +1307,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
             uint64_t *m1 = mask_row(e, 0), *m2 = mask_row(e, 1);
             for (int32_t col : cp.g1) m1[col >> 6] |= 1ULL << (col & 63);
             for (int32_t col : cp.g2) m2[col >> 6] |= 1ULL << (col & 63);
+            if (i < w0 || i >= w0 + n_comps) { ++e; continue; }   // counted, not emitted by this run
             if (groups.empty() || groups.back().n_comp >= kExplicitPerGroup || e % kExplicitPerGroup == 0)
                 groups.push_back(ScreenGroup{int32_t(fracs.size()), 0, int32_t(gcomps.size()), 0,
                                              int32_t(sdefs.size()), 0, -1, 0});
@@ -1273,7 +1315,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
             fracs.push_back(FracDef{e, 0, -1, 0});
             fracs.push_back(FracDef{e, 1, -1, 0});
             sdefs.push_back(SlotDef{e, int16_t(g.n_frac), int16_t(g.n_frac + 1), -1, -1, 0});
-            gcomps.push_back(GroupComp{i, int16_t(g.n_frac), int16_t(g.n_frac + 1)});
+            gcomps.push_back(GroupComp{i - w0, int16_t(g.n_frac), int16_t(g.n_frac + 1)});
             g.n_frac += 2;
             g.n_comp += 1;
             g.n_slot += 1;
@@ -1292,8 +1334,10 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
                 if (cat_tot[k] >= 0) mask_row(cat_tot[k], 0)[s >> 6] |= 1ULL << (s & 63);
             }
             const int first = cat_first[k];
-            auto pair_index = [&](int i, int j) { return first + i * V - i * (i + 1) / 2 + (j - i - 1); };
-            const int ova_first = first + V * (V - 1) / 2;
+            // (local indices: comparison - w0; outside [0, n_comps) = not emitted by this run)
+            auto pair_index = [&](int i, int j) { return first - w0 + i * V - i * (i + 1) / 2 + (j - i - 1); };
+            const int ova_first = first - w0 + V * (V - 1) / 2;
+            auto emitted = [&](int local) { return local >= 0 && local < n_comps; };
             const int nb = (V + kValueBlock - 1) / kValueBlock;
             for (int a = 0; a < nb; ++a)
                 for (int b = a; b < nb; ++b) {
@@ -1311,6 +1355,7 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
                     }
                     for (int i = a0; i < a1; ++i)
                         for (int j = std::max(b0, i + 1); j < b1; ++j) {
+                            if (!emitted(pair_index(i, j))) continue;
                             gcomps.push_back(GroupComp{pair_index(i, j), int16_t(i - a0), int16_t(boff + j - b0)});
                             ++g.n_comp;
                         }
@@ -1318,10 +1363,11 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
                         const int roff = g.n_frac;
                         for (int v = a0; v < a1; ++v) {
                             fracs.push_back(FracDef{cat_slot0[k] + v / 2, v & 1, cat_tot[k], 0});
+                            if (!emitted(ova_first + v)) continue;
                             gcomps.push_back(GroupComp{ova_first + v, int16_t(v - a0), int16_t(roff + v - a0)});
+                            ++g.n_comp;
                         }
                         g.n_frac += a1 - a0;
-                        g.n_comp += a1 - a0;
                     }
                     if (g.n_comp > 0) {
                         // slot view of the same fractions: one record load per pair-slot
@@ -1482,17 +1528,24 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
     c->last_engine = use_gemm ? (f8 ? FEHT_ENGINE_GEMM_F8 : (fp4 ? FEHT_ENGINE_GEMM_FP4 : FEHT_ENGINE_GEMM)) : FEHT_ENGINE_POPC;
 
     CU(c, cudaEventRecord(ev[0], c->st));
+    // windows of one job (feht_set_comparison_window): the pair-slot counts do not depend on which comparisons are
+    // emitted, so only the first window counts.  Never taken without a window: every ordinary run counts.
+    const bool reuse_counts = c->win_count >= 0 && c->counts_ready && c->counts_engine == c->last_engine;
+    c->counts_ready = false;
     const int n_popc_slots = use_gemm ? n_explicit : n_scanned;
     if (n_popc_slots > 0 && size_t(2) * plan.w4pad * 16 > size_t(200) * 1024)
         return fail(c, FEHT_E_INVALID, "%lld samples are too many for the popcount engine (a comparison's two masks must fit "
                     "in shared memory, about 800k samples); use feht_add_category with the GEMM engine", (long long)c->S);
-    if (c->snp == 1)
+    if (reuse_counts) {
+        // nothing to launch
+    } else if (c->snp == 1)
         CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
                                     c->masks.p, n_popc_slots, c->counts.p, c->num_sms, c->st, &count_launches));
     else
         CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_popc_slots,
                                 c->counts.p, c->num_sms, c->st, &count_launches));
-    if (use_gemm && f8) {
+    if (reuse_counts) {
+    } else if (use_gemm && f8) {
         CU(c, launch_count_gemm_f8(c->plane[0], c->plane[1], c->n_units, c->W, c->S, c->gemm_b.p, c->gemm_passes.p,
                                    c->gemm_n_passes, c->counts.p, c->num_sms, c->st, &count_launches));
     } else if (use_gemm) {
@@ -1507,6 +1560,8 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
             }
     }
     launches += count_launches;
+    c->counts_ready = c->win_count >= 0;
+    c->counts_engine = c->last_engine;
     CU(c, cudaEventRecord(ev[1], c->st));
 
     // ---- K3 test + correct + filter
@@ -1628,8 +1683,11 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         }
         c->sw.control = c->sw_control.p;
         if (tp.dense) {
-            if (n_comps == 1 && c->comps[0].kind == 0)
-                CU(c, launch_test_emit_single(tp, 0, c->st));   // the one comparison lives in pair-slot 0
+            if (n_comps == 1 && c->comps[size_t(w0)].kind == 0) {
+                int slot = 0;   // explicit comparisons take the pair-slots 0, 1, ... in the order they were added
+                for (int i = 0; i < w0; ++i) if (c->comps[size_t(i)].kind == 0) ++slot;
+                CU(c, launch_test_emit_single(tp, slot, c->st));
+            }
             else
                 CU(c, launch_test_emit(tp, c->st));
             ++launches;
@@ -1704,6 +1762,15 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         pr.count_launches = count_launches;
         const int n_planes = c->snp == 1 ? 3 : 2;
         pr.count_bytes = double(c->n_units) * double((c->S + 63) / 64) * 8.0 * n_planes;
+    }
+    if (n_comps != n_all) {
+        // result offsets for every comparison of the context: nothing before / after the window
+        std::vector<int64_t> all(size_t(n_all) + 1, 0);
+        for (int i = 0; i < n_all; ++i) {
+            const int64_t rows_i = (i >= w0 && i < w0 + n_comps) ? c->seg_off[size_t(i - w0) + 1] - c->seg_off[size_t(i - w0)] : 0;
+            all[size_t(i) + 1] = all[size_t(i)] + rows_i;
+        }
+        c->seg_off.swap(all);
     }
     if (!async)
         if (int rc = settle_all(c)) return rc;

@@ -58,7 +58,7 @@ constexpr int kThreads = (kExpandWarps + 3) * 32;
 #ifndef FEHT_MMA_WARPS
 #define FEHT_MMA_WARPS 4
 #endif
-constexpr int kMmaWarps = FEHT_MMA_WARPS;                       // i8 / mxf4 kernels: MMA-issuing warps (1, 2 or 4), each owns 4 / kMmaWarps accumulators
+constexpr int kMmaWarps = FEHT_MMA_WARPS;                       // i8 / mxf4 kernels: warps reserved for MMA issue (kABufs of them issue: 3 mxf4, 2 i8)
 constexpr int kThreads2 = (kExpandWarps + 2 + kMmaWarps) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kTmemAccBase = 0;       // + (mt * 2 + plane) * 64
@@ -234,15 +234,17 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
             mbar_init(a_full + i * 8, 1);
             mbar_init(a_empty + i * 8, kExpandWarps);
         }
+        // one issuer handles a whole stage (all four accumulators): it alone hands the A buffer back; a B block serves
+        // kAPerB consecutive stages, i.e. that many issuers
         for (int i = 0; i < 3; ++i) {
             mbar_init(ta_full + i * 8, kExpandWarps);
-            mbar_init(ta_empty + i * 8, kMmaWarps);
+            mbar_init(ta_empty + i * 8, 1);
         }
         for (int i = 0; i < kBStages; ++i) {
             mbar_init(b_full + i * 8, 1);
-            mbar_init(b_empty + i * 8, kMmaWarps);
+            mbar_init(b_empty + i * 8, FP4 ? 2 : 1);
         }
-        mbar_init(acc_full, kMmaWarps);
+        mbar_init(acc_full, FP4 ? 3 : 2);   // = kABufs issuers (below)
         mbar_init(acc_empty, kExpandWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -262,6 +264,20 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
     constexpr int kABuf = 4 * kAColsQ;           // TMEM columns of one A stage buffer
     constexpr int kABufs = FP4 ? 3 : 2;          // A stage buffers in TMEM: 256 + 3 * 64 + 8 / 256 + 2 * 128 columns
     constexpr int kTmemSF = kTmemABase + kABufs * kABuf;   // FP4: eight columns of unit scale factors (0x7F = 2^0)
+
+    if (warp < kExpandWarps) {
+        // every MMA accumulates (the issuers work on different stages of a tile at the same time, so none of them is
+        // "the first"): the accumulators start at zero and the epilogue zeroes what it has read
+        const uint32_t la = uint32_t((warp & 3) * 32) << 16;
+        uint32_t zero[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zero[j] = 0u;
+        for (int c0 = 0; c0 < 128; c0 += 8) tmem_st8(tmem_base + la + kTmemAccBase + (threadIdx.x >> 7) * 128 + c0, zero);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp < kExpandWarps) {
         // =============================================== expanders + epilogue: thread = marker row
@@ -328,6 +344,13 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
                 tmem_ld16(acc_p + c0, P);
                 tmem_ld16(acc_n + c0, N);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                {   // the next tile accumulates onto zeros
+                    uint32_t zero[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zero[j] = 0u;
+                    tmem_st8(acc_p + c0, zero); tmem_st8(acc_p + c0 + 8, zero);
+                    tmem_st8(acc_n + c0, zero); tmem_st8(acc_n + c0 + 8, zero);
+                }
                 if (row < n_rows) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -341,6 +364,7 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
                     }
                 }
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
@@ -378,58 +402,66 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
             }
         }
     } else {
-        // =============================================== MMA issuers: one warp per M tile.  A single issuing thread was the
-        // pace of the kernel (profiles/README.md r1s: ~530 cycles of waits, fence and commits per stage + ~48 per MMA,
-        // whatever the expanders and producers did); two threads issue disjoint accumulators and each commits to the
-        // same barriers (which therefore expect kMmaWarps arrivals).
-        const int mw = warp - (kExpandWarps + 2);   // this issuer's accumulators: q = mw * kQPer .. + kQPer - 1
-        constexpr int kQPer = 4 / kMmaWarps;
-        if (lane == 0) {
+        // =============================================== MMA issuers, one warp per STAGE in flight.  A stage's hand-over
+        // (two mbarrier waits, a fence, the issues, the commits) costs an issuing thread ~530 cycles + ~48 per MMA
+        // whatever the tensor pipe does (profiles/README.md r1s), so issuer w takes every kABufs-th stage
+        // and issues ALL of a stage's MMAs (2 M tiles x 2 planes x K steps): the fixed part is paid once
+        // per 8 (mxf4) / 16 (i8) MMAs and the issuers overlap each other's waits.  Stages of one tile accumulate into
+        // the same four accumulators from different threads: every MMA accumulates (the accumulators are zeroed by the
+        // epilogue), sums of integers below 2^24 do not depend on the order, and the tensor pipe executes one MMA at
+        // a time.  (Round 1 gave each issuer one accumulator and every stage: same MMAs per thread and stage as with
+        // a single issuer per accumulator, the hand-over cost stayed -- halving the MMAs did not change the time.)
+        // As many issuers as A stage buffers, issuer w <-> buffer w: the stages an issuer handles are then consecutive
+        // phases of ITS ta_full barrier (a parity wait cannot tell a phase from the one two before it, so an issuer
+        // must never run a whole ring ahead of the expanders -- with four issuers on three buffers it did, and hung).
+        const int mw = warp - (kExpandWarps + 2);
+        if (lane == 0 && mw < kABufs) {
             // instruction descriptor, N = n_pad, M = 128, both operands K-major.  i8: D s32, A/B unsigned 8-bit.
             // mxf4 (block-scaled layout): A/B e2m1 (format 1), UE8M0 scales, scale ids 0, K = 64.
             const uint32_t idesc = FP4 ? ((1u << 7) | (1u << 10) | (uint32_t(n_pad >> 3) << 17) | (1u << 23) |
                                           (uint32_t(128 >> 4) << 24))
                                        : ((2u << 4) | (uint32_t(n_pad >> 3) << 17) | (uint32_t(128 >> 4) << 24));
-            uint32_t stage_ctr = 0, bblock_ctr = 0, tile_ctr = 0;
+            const uint32_t n_bblocks = uint32_t((n_stages + kAPerB - 1) / kAPerB);
+            uint32_t tile_ctr = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
                 mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
                 tc_fence_after();
-                for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                const uint32_t tile_stage0 = tile_ctr * uint32_t(n_stages);
+                for (int s = int((uint32_t(mw) + uint32_t(kABufs) - tile_stage0 % kABufs) % kABufs); s < n_stages; s += kABufs) {
+                    const uint32_t stage_ctr = tile_stage0 + uint32_t(s);   // stage_ctr % kABufs == mw
+                    const uint32_t bblock_ctr = tile_ctr * n_bblocks + uint32_t(s / kAPerB);
                     const uint32_t tb = stage_ctr % kABufs;
                     const int half = s % kAPerB;                 // which part of the B block this A stage uses
                     const uint32_t bs = bblock_ctr % kBStages;
                     mbar_wait(ta_full + tb * 8, (stage_ctr / kABufs) & 1);
-                    if (half == 0) mbar_wait(b_full + bs * 8, (bblock_ctr / kBStages) & 1);
+                    mbar_wait(b_full + bs * 8, (bblock_ctr / kBStages) & 1);
                     tc_fence_after();
                     const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kBStageBytes);
                     if (FP4) {
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-                            for (int q = kQPer * mw; q < kQPer * mw + kQPer; ++q)   // q = mt * 2 + plane
+                            for (int q = 0; q < 4; ++q)   // q = mt * 2 + plane
                                 mma_fp4_ts(tmem_base + kTmemAccBase + q * 64,
                                            tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
-                                           bdesc + uint64_t((half * 2 + ks) * 2), idesc, tmem_base + kTmemSF,
-                                           (s > 0 || ks > 0) ? 1u : 0u);
+                                           bdesc + uint64_t((half * 2 + ks) * 2), idesc, tmem_base + kTmemSF, 1u);
                         }
                     } else {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                            for (int q = kQPer * mw; q < kQPer * mw + kQPer; ++q) {  // q = mt * 2 + plane
+                            for (int q = 0; q < 4; ++q)   // q = mt * 2 + plane
                                 mma_i8_ts(tmem_base + kTmemAccBase + q * 64,
                                           tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
-                                          bdesc + uint64_t(ks * 2), idesc, (s > 0 || ks > 0) ? 1u : 0u);
-                            }
+                                          bdesc + uint64_t(ks * 2), idesc, 1u);
                         }
                     }
                     tc_commit(ta_empty + tb * 8);
-                    if (half == kAPerB - 1 || s == n_stages - 1) {
-                        tc_commit(b_empty + bs * 8);
-                        ++bblock_ctr;
-                    }
+                    tc_commit(b_empty + bs * 8);
+                    // a trailing B block that serves one stage only still owes its barrier the second arrival
+                    if (FP4 && half == 0 && s == n_stages - 1) tc_commit(b_empty + bs * 8);
                 }
-                tc_commit(acc_full);
+                tc_commit(acc_full);   // arrives once this issuer's MMAs of the tile have retired
             }
         }
     }

@@ -537,6 +537,13 @@ int set_row_base(MultiState *m, int64_t row_base) {
     return FEHT_OK;
 }
 
+int set_comparison_window(MultiState *m, int64_t first, int64_t count) {
+    for (int d = 0; d < D(m); ++d)
+        if (int rc = feht_set_comparison_window(m->kids[size_t(d)], first, count)) return kid_fail(m, d, rc);
+    m->has_results = false;
+    return FEHT_OK;
+}
+
 int run(MultiState *m, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n) {
     m->has_results = false;
     const int nd = D(m), mu = mult(m);

@@ -44,6 +44,7 @@ int comparison_info(const MultiState *m, int64_t c, int32_t *kind, int32_t *cate
 int set_count_engine(MultiState *m, int engine);
 int set_fet_mode(MultiState *m, int mode);
 int set_row_base(MultiState *m, int64_t row_base);
+int set_comparison_window(MultiState *m, int64_t first, int64_t count);
 
 int run(MultiState *m, int correction, double ratio_filter, int sort_key, int64_t bonferroni_n);
 int64_t result_count(const MultiState *m, int64_t comparison);

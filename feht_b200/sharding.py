@@ -100,7 +100,7 @@ def gather_and_merge_device(ctx, comparison: int, sort_key: int = capi.SORT_ABS_
 
 
 def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, dst: int = 0,
-                                host_out: dict | None = None, want_device: bool = False):
+                                host_out: dict | None = None, want_device: bool = False, times: dict | None = None):
     """The same exchange for EVERY comparison at once (one process per GPU): each rank hands over the ordered rows of
     all its comparisons (feht_result_fetch_device with comparison = -1: eight device-to-device copies), eight padded
     `dist.gather`s move them to rank `dst` over NVLink, and ONE call of feht_merge_shards_device (K5b) merges all
@@ -109,8 +109,19 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
     import torch
     import torch.distributed as dist
 
+    import time
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
+    t0 = time.perf_counter()
+
+    def lap(name):
+        # host wall clock between device synchronisations: coarse, for the breakdown in bench.py only
+        nonlocal t0
+        if times is not None:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            times[name] = times.get(name, 0.0) + 1e3 * (t1 - t0)
+            t0 = t1
     n_comps = ctx.num_comparisons
     seg = np.zeros(n_comps + 1, dtype=np.int64)
     np.cumsum(ctx.result_counts(), out=seg[1:])
@@ -123,11 +134,13 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
     local = {k: torch.empty(n_max, dtype=getattr(torch, dt), device=dev) for k, dt in DEV_DTYPES.items()}
     if sizes[rank]:
         ctx.fetch_device(-1, {k: v.data_ptr() for k, v in local.items()})
+    lap("sizes_and_local_copy_ms")
     gathered = {}
     for k, v in local.items():
         lst = [torch.empty_like(v) for _ in range(world)] if rank == dst else None
         dist.gather(v, lst, dst=dst)
         gathered[k] = lst
+    lap("nccl_gather_ms")
     if rank != dst:
         return None, None
     total = sum(sizes)
@@ -136,6 +149,7 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
     torch.cuda.current_stream().synchronize()
     shards = [({k: gathered[k][s].data_ptr() for k in DEV_DTYPES}, np.ascontiguousarray(segs[s])) for s in range(world)]
     ctx.merge_shards_device(shards, n_comps, {k: v.data_ptr() for k, v in merged.items()}, out_seg, sort_key)
+    lap("merge_kernel_ms")
     if want_device:
         return {k: v[:total] for k, v in merged.items()}, out_seg
     out = {}

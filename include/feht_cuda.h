@@ -241,6 +241,17 @@ int feht_run_async(feht_ctx *ctx, int correction, double ratio_filter, int sort_
  * `cumulative (hypergeometric m l k) goa`. */
 int feht_set_fet_mode(feht_ctx *ctx, int mode);
 
+/*
+ * Emit only the comparisons [first, first + count) in the following runs; count < 0 = all comparisons again.
+ * For outputs that do not fit one run (fewer than 2^30 result rows per run): the reference's default ratioFilter 0
+ * keeps every test (Comparison.hs:148), so a category of V values over R marker rows yields (V(V-1)/2 + V) * R
+ * rows.  The host walks the comparisons window by window -- set the window, feht_run, feht_result_fetch the
+ * window's comparisons (the others report 0 rows), next window.  The contingency counts do not depend on the
+ * window: the first window's run computes them, the following windows start at the test stage (until rows,
+ * comparisons, the engine or the sample count change, or the window is dropped with count < 0).
+ */
+int feht_set_comparison_window(feht_ctx *ctx, int64_t first, int64_t count);
+
 /* Surviving rows of comparison c, in final order. */
 int64_t feht_result_count(const feht_ctx *ctx, int64_t comparison);
 int64_t feht_result_total(const feht_ctx *ctx);

@@ -88,3 +88,65 @@ def p_close(got: np.ndarray, want: np.ndarray, chi_branch: np.ndarray):
     absok = np.abs(got - want) <= 2.0**-52
     ok = np.where(chi_branch, exact | rel | absok, exact)
     return ok
+
+
+def synth_rows(spec, snp, row0, n_rows, threads=None):
+    """oracle.synth_fill for rows (SNP: sites) [row0, row0 + n_rows) on several Python threads (ctypes releases the GIL)."""
+    import ctypes
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    import oracle
+    threads = threads or (os.cpu_count() or 1)
+    threads = max(1, min(threads, n_rows // 500 or 1))
+    if threads == 1:
+        return oracle.synth_fill(spec, snp, row0, n_rows)
+    out = np.empty((n_rows, spec.n_samples), dtype=np.uint8)
+    cuts = [n_rows * t // threads for t in range(threads + 1)]
+
+    def job(t):
+        a, b = cuts[t], cuts[t + 1]
+        if b > a:
+            oracle.lib().fo_synth_fill(ctypes.byref(spec), int(snp), row0 + a, b - a, out[a:b].ctypes.data_as(ctypes.c_void_p))
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(job, range(threads)))
+    return out
+
+
+def check_block_against_oracle(ctx, spec, snp, comps, unit0, n_units, n_total, correction, rf, threads=None):
+    """A contiguous block of generated rows (SNP: sites -> 4 allele rows each) through the oracle, compared with the
+    rows the GPU returned for the same block: which rows survive the filter, counts and ratio bit-exact, p (exact on the
+    FET branch, chi-square tolerance otherwise), and the block's rows in the oracle's relative order.
+    comps: {comparison index: (g1, g2)}.  Returns (tests checked, p bit-identical, p compared on the chi-square branch)."""
+    import os
+
+    import oracle
+    threads = threads or (os.cpu_count() or 1)
+    cells = synth_rows(spec, snp, unit0, n_units, threads)
+    mult = 4 if snp else 1
+    if snp:
+        cells = snp_expand(cells)
+    lo, hi = unit0 * mult, (unit0 + n_units) * mult
+    checked = exact = chi_n = 0
+    for ci, (g1, g2) in comps.items():
+        want = oracle.run_comparison(cells, g1, g2, correction=correction, bonferroni_n=n_total, n_threads=threads)
+        got = ctx.fetch(ci)
+        sel = np.flatnonzero((got["row"] >= lo) & (got["row"] < hi))
+        keep = np.flatnonzero(rf <= np.abs(want["ratio"]))
+        rows = got["row"][sel] - lo
+        assert len(rows) == len(keep) and (np.sort(rows) == keep).all(), (ci, len(rows), len(keep))
+        for k in ("goa", "gob", "gta", "gtb"):
+            assert (got[k][sel] == want[k][rows]).all(), (ci, k)
+        assert (got["ratio"][sel] == want["ratio"][rows]).all(), (ci, "ratio")
+        l = (want["goa"] + want["gob"] + want["gta"] + want["gtb"])[rows]
+        ok = p_close(got["p"][sel], want["p"][rows], l >= 1000)
+        assert ok.all(), (ci, got["p"][sel][~ok][:4], want["p"][rows][~ok][:4])
+        # relative order of the block's rows in the output = the oracle's order of the block (ties by global row)
+        order = oracle.filter_and_order(want["ratio"], None, rf)
+        assert (rows == order).all(), (ci, "order inside the block")
+        chi = l >= 1000
+        both = np.isnan(got["p"][sel]) & np.isnan(want["p"][rows])
+        exact += int(((got["p"][sel] == want["p"][rows]) | both)[chi].sum())
+        chi_n += int(chi.sum())
+        checked += len(want["ratio"])
+    return checked, exact, chi_n

@@ -314,3 +314,188 @@ def test_exact_tests_with_repeated_tables_are_deduplicated_bit_exact(ctx):
             assert (got["p"][back] == want["p"][keep]).all(), (ci, "p: the exact branch is bit-exact")
             if key == capi.SORT_PVALUE_ASC:
                 assert (got["p"][:-1] <= got["p"][1:]).all()
+
+
+# ------------------------------------------------------------------------- comparison windows (dense output in blocks)
+@pytest.mark.parametrize("devices", [0, [0, 0]])
+def test_comparison_window_blocks_equal_one_run(cuda_lib, devices):
+    """feht_set_comparison_window: the reference's default ratioFilter 0 keeps every test (Comparison.hs:148), so the
+    output of a large category does not fit one run; the host walks the comparisons window by window.  The rows of
+    every window must be exactly the rows of the one-shot run, the counts are computed by the first window only, and
+    dropping the window restores the ordinary run.  Explicit comparisons + two categories, K1 and the GEMM engines."""
+    rng = np.random.default_rng(81)
+    S, R = 600, 4000
+    cells = _random_chars(rng, R, S)
+    vos_a = rng.integers(0, 9, size=S).astype(np.int32)
+    vos_b = rng.integers(-1, 3, size=S).astype(np.int32)
+    for engine in (capi.ENGINE_POPC, capi.ENGINE_GEMM_FP4, capi.ENGINE_GEMM):
+        with capi.Context(devices) as c:
+            c.set_samples(S)
+            c.add_rows_chars(cells)
+            c.add_comparison(np.arange(0, 100), np.arange(100, 350))
+            c.add_category(vos_a, 9)
+            c.add_comparison(np.arange(50, 300), np.arange(20, 40))
+            c.add_category(vos_b, 3)
+            c.set_count_engine(engine)
+            n_comps = c.num_comparisons
+            assert n_comps == 1 + 36 + 9 + 1 + 3 + 3
+            for rf in (0.0, 0.12):
+                c.set_comparison_window(0, -1)
+                c.run(capi.CORRECTION_BONFERRONI, rf)
+                whole = [c.fetch(ci) for ci in range(n_comps)]
+                first_count_ms = None
+                for w0, wn in ((0, 1), (1, 20), (21, 26), (47, 1), (48, 100)):
+                    c.set_comparison_window(w0, wn)
+                    c.run(capi.CORRECTION_BONFERRONI, rf)
+                    t = c.timings()
+                    if first_count_ms is None:
+                        first_count_ms = t["count_ms"]
+                        assert t["count_launches"] >= 1
+                    else:
+                        assert t["count_launches"] == 0          # the counts of the first window are re-used
+                    for ci in range(n_comps):
+                        got = c.fetch(ci)
+                        if w0 <= ci < w0 + wn:
+                            assert len(got["row"]) == len(whole[ci]["row"]), (engine, rf, ci)
+                            for k in got:
+                                eq = (got[k] == whole[ci][k]) | ((k == "p") & np.isnan(got[k].astype(float)) & np.isnan(whole[ci][k].astype(float)))
+                                assert eq.all(), (engine, rf, ci, k)
+                        else:
+                            assert len(got["row"]) == 0
+                    assert c.result_total() == sum(len(whole[ci]["row"]) for ci in range(w0, min(n_comps, w0 + wn)))
+                # an ordinary run after the windows counts again
+                c.set_comparison_window(0, -1)
+                c.run(capi.CORRECTION_BONFERRONI, rf)
+                assert c.timings()["count_launches"] >= 1
+                assert c.result_total() == sum(len(w["row"]) for w in whole)
+
+
+# ------------------------------------------------------------------------- BASELINE shapes: large contiguous blocks
+def test_config2_block_of_100k_rows_against_oracle(ctx):
+    """BASELINE configs[1] (1M x 5k, one comparison): 100,000 contiguous rows (and the last 20,000) through the oracle
+    -- every 2x2 table, ratio, p and the rows' relative order; chi-square p-values: >= 95% bit-identical."""
+    from helpers import check_block_against_oracle, copy_spec, make_spec
+    S, R = 5000, 1_000_000
+    sp_o = make_spec(oracle.SynthSpec, S)
+    ctx.set_samples(S)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, 0, R)
+    g1, g2 = np.arange(0, 2500), np.arange(2500, 5000)
+    ctx.add_comparison(g1, g2)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.0)
+    n, exact, chi_n = check_block_against_oracle(ctx, sp_o, False, {0: (g1, g2)}, 300_000, 100_000, R, 1, 0.0)
+    n2, e2, c2 = check_block_against_oracle(ctx, sp_o, False, {0: (g1, g2)}, R - 20_000, 20_000, R, 1, 0.0)
+    assert n == 100_000 and n2 == 20_000
+    assert chi_n + c2 > 100_000 and (exact + e2) >= 0.95 * (chi_n + c2), (exact + e2, chi_n + c2)
+    # a filtered run of the same matrix: planted rows survive, the block's survivors are the oracle's
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.3)
+    check_block_against_oracle(ctx, sp_o, False, {0: (g1, g2)}, 300_000, 100_000, R, 1, 0.3)
+
+
+def test_config2b_fet_branch_block_against_oracle(ctx):
+    """C2b (groups of 300 / 400 genomes: every test on the hypergeometric branch, with the dedup of K3b): 50,000
+    contiguous rows bit-exact against the oracle."""
+    from helpers import check_block_against_oracle, copy_spec, make_spec
+    S, R = 5000, 1_000_000
+    sp_o = make_spec(oracle.SynthSpec, S)
+    ctx.set_samples(S)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, 0, R)
+    g1, g2 = np.arange(0, 300), np.arange(300, 700)
+    ctx.add_comparison(g1, g2)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.0)
+    n, exact, chi_n = check_block_against_oracle(ctx, sp_o, False, {0: (g1, g2)}, 640_000, 50_000, R, 1, 0.0)
+    assert n == 50_000 and chi_n == 0
+
+
+def test_config3_block_of_20k_allele_rows_all_comparisons(ctx):
+    """Config 3 (SNP 500k sites x 10k genomes, one 4-value category): 5,000 contiguous sites = 20,000 allele rows x all
+    10 comparisons against the oracle."""
+    from helpers import check_block_against_oracle, copy_spec, make_spec
+    S, SITES = 10_000, 500_000
+    sp_o = make_spec(oracle.SynthSpec, S, law="uniform_half")
+    ctx.set_samples(S)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), True, 0, SITES)
+    vos = (np.arange(S) * 4 // S).astype(np.int32)
+    ctx.add_category(vos, 4)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.0)
+    groups = [np.flatnonzero(vos == v) for v in range(4)]
+    comps = {}
+    ci = 0
+    for i in range(4):
+        for j in range(i + 1, 4):
+            comps[ci] = (groups[i], groups[j])
+            ci += 1
+    for v in range(4):
+        comps[ci] = (groups[v], np.flatnonzero(vos != v))
+        ci += 1
+    n, exact, chi_n = check_block_against_oracle(ctx, sp_o, True, comps, 123_000, 5_000, 4 * SITES, 1, 0.0)
+    assert n == 10 * 20_000 and exact >= 0.95 * chi_n
+
+
+def test_config4_block_of_5k_rows_24_comparisons(ctx):
+    """Config 4 (2M x 20k, one 50-value category, GEMM counts, ratioFilter 0.5 and a low filter that keeps most tests):
+    5,000 contiguous rows x 24 comparisons (pairs inside and across the planted split, one-vs-rest) against the oracle."""
+    from helpers import check_block_against_oracle, copy_spec, make_spec
+    S, R, V = 20_000, 2_000_000, 50
+    sp_o = make_spec(oracle.SynthSpec, S)
+    ctx.set_samples(S)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, 0, R)
+    vos = (np.arange(S) // (S // V)).astype(np.int32)
+    ctx.add_category(vos, V)
+    groups = [np.flatnonzero(vos == v) for v in range(V)]
+    pidx = lambda i, j: i * V - i * (i + 1) // 2 + (j - i - 1)
+    comps = {}
+    for i, j in ((0, 1), (0, 25), (0, 49), (3, 30), (7, 8), (10, 40), (12, 37), (24, 25), (24, 26), (23, 49), (25, 26),
+                 (30, 31), (33, 48), (40, 41), (44, 45), (47, 49), (1, 26), (2, 27), (5, 45), (48, 49)):
+        comps[pidx(i, j)] = (groups[i], groups[j])
+    for v in (0, 7, 24, 49):
+        comps[V * (V - 1) // 2 + v] = (groups[v], np.flatnonzero(vos != v))
+    assert len(comps) == 24
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.5)
+    assert ctx.timings()["engine"] == capi.ENGINE_GEMM_FP4
+    check_block_against_oracle(ctx, sp_o, False, comps, 1_000_000, 5_000, R, 1, 0.5)
+    # a filter most tests pass, on a window of comparisons (the dense output of 1,275 comparisons x 2M rows does not
+    # fit one run): window = the first 30 comparisons, 60M result rows
+    ctx.set_comparison_window(0, 30)
+    ctx.run(capi.CORRECTION_BONFERRONI, 0.02)
+    sub = {ci: g for ci, g in comps.items() if ci < 30}
+    assert len(sub) >= 2
+    n, exact, chi_n = check_block_against_oracle(ctx, sp_o, False, sub, 1_000_000, 5_000, R, 1, 0.02)
+    assert n == 5_000 * len(sub)
+
+
+def test_config5_shard_block_of_5k_rows_24_comparisons(ctx):
+    """Config 5, the fourth of eight shards (1.25M of the 10M x 50k rows, four categories, 281 comparisons): 5,000
+    contiguous rows x 24 comparisons, with a filter low enough to keep rows, Bonferroni n = the global 10M."""
+    from helpers import check_block_against_oracle, copy_spec, make_spec
+    S, R, TOTAL = 50_000, 1_250_000, 10_000_000
+    sp_o = make_spec(oracle.SynthSpec, S)
+    first = 3 * R
+    ctx.set_samples(S)
+    ctx.set_row_base(first)
+    ctx.generate_synthetic(copy_spec(sp_o, capi.SynthSpec), False, first, R)
+    rng = np.random.default_rng(5)
+    nv = (2, 5, 10, 20)
+    cats = [rng.integers(0, v, S).astype(np.int32) for v in nv]
+    cats[0] = (np.arange(S) >= S // 2).astype(np.int32)          # follows the planted split: planted rows survive 0.8
+    for vos, v in zip(cats, nv):
+        ctx.add_category(vos, v)
+    assert ctx.num_comparisons == 281
+    # comparison indices: category k starts after the comparisons of the categories before it
+    start = [0, 1, 1 + 15, 1 + 15 + 55]
+    comps = {0: (np.flatnonzero(cats[0] == 0), np.flatnonzero(cats[0] == 1))}
+    for k in (1, 2, 3):
+        V = nv[k]
+        pidx = lambda i, j: start[k] + i * V - i * (i + 1) // 2 + (j - i - 1)
+        pairs = [(0, 1), (0, V - 1), (1, 2), (V - 2, V - 1), (1, V - 1)]
+        for i, j in pairs:
+            comps[pidx(i, j)] = (np.flatnonzero(cats[k] == i), np.flatnonzero(cats[k] == j))
+        for v in (0, V - 1, V // 2):
+            comps[start[k] + V * (V - 1) // 2 + v] = (np.flatnonzero(cats[k] == v), np.flatnonzero((cats[k] != v)))
+    assert len(comps) >= 24
+    for rf in (0.8, 0.012):
+        ctx.run(capi.CORRECTION_BONFERRONI, rf, capi.SORT_ABS_RATIO_DESC, TOTAL)
+        assert ctx.timings()["engine"] == capi.ENGINE_GEMM_FP4
+        # (check_block works on global row numbers: the shard's rows are first .. first + R)
+        n, exact, chi_n = check_block_against_oracle(ctx, sp_o, False, comps, first + 600_000, 5_000, TOTAL, 1, rf)
+        assert n == 5_000 * len(comps)
+    assert ctx.result_count(0) > 0
