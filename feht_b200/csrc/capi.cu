@@ -1538,9 +1538,16 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
                     "in shared memory, about 800k samples); use feht_add_category with the GEMM engine", (long long)c->S);
     if (reuse_counts) {
         // nothing to launch
-    } else if (c->snp == 1)
+    } else if (c->snp == 1) {
+        // one category of four values that covers every genome (config 3): its four masks partition the samples, and
+        // the scan derives the last mask's counts from the row totals (count_popc.cu, PART)
+        bool part = n_explicit == 0 && c->cats.size() == 1 && c->cats[0].n_values == 4 && n_popc_slots == 2;
+        if (part)
+            for (int32_t v : c->cats[0].value_of_sample)
+                if (v < 0) { part = false; break; }
         CU(c, launch_count_popc_snp(c->plane[0], c->plane[1], c->plane[2], c->n_units, c->W, plan,
-                                    c->masks.p, n_popc_slots, c->counts.p, c->num_sms, c->st, &count_launches));
+                                    c->masks.p, n_popc_slots, c->counts.p, c->num_sms, c->st, &count_launches, part));
+    }
     else
         CU(c, launch_count_popc(c->plane[0], c->plane[1], c->n_units, c->W, plan, c->masks.p, n_popc_slots,
                                 c->counts.p, c->num_sms, c->st, &count_launches));

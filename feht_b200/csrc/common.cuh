@@ -129,7 +129,8 @@ cudaError_t launch_count_popc(const uint64_t *d_value, const uint64_t *d_valid, 
 cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
                                   const uint64_t *d_lo, int64_t n_sites, int64_t W,
                                   const PopcPlan &plan, const uint4 *d_masks, int n_slots,
-                                  int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
+                                  int4 *d_counts, int num_sms, cudaStream_t st, int *launches,
+                                  bool masks_partition = false);   // the 2 * n_slots masks cover every sample exactly once
 
 // counts[tot_slot][row] = (sum of P, sum of N, 0, 0) over both halves of pair-slots [slot0, slot0 + n)
 cudaError_t launch_sum_slots(int4 *d_counts, int64_t n_rows, int slot0, int n, int tot_slot, cudaStream_t st);
@@ -162,6 +163,18 @@ void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_
 cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
                               int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes, bool fp4,
                               int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
+
+// value-plane-only mxf4 flavour (count_gemm.cu "value plane only"): N = column size - missing calls, counted by the
+// expander threads from the valid plane.  gemm_m1_bake returns false when a sample sits in more columns of a pass than
+// the id table holds (the caller then keeps the two-plane kernel).
+size_t gemm_m1_pass_desc_bytes();
+size_t gemm_m1_block_bytes(int n_pad);
+bool gemm_m1_bake(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, uint8_t *out);
+void gemm_m1_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_offset,
+                       const std::vector<std::vector<int32_t>> &columns);
+cudaError_t launch_count_gemm_m1(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
+                                 int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
+                                 int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
 
 // fet.cu  (K3)
 // What the final gather needs about a surviving test: exactly one 32-byte sector.

@@ -75,6 +75,15 @@ struct CountStream {
         asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(twos) : "r"(__popc(c1)), "r"(one));
         asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(twos) : "r"(__popc(c2)), "r"(one));
     }
+    // the same without a mask (the whole row segment counts)
+    __device__ __forceinline__ void add_fma_all(const uint4 &a, int one) {
+        const uint32_t c1 = lop3_maj(ones, a.x, a.y);
+        ones = lop3_xor3(ones, a.x, a.y);
+        const uint32_t c2 = lop3_maj(ones, a.z, a.w);
+        ones = lop3_xor3(ones, a.z, a.w);
+        asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(twos) : "r"(__popc(c1)), "r"(one));
+        asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(twos) : "r"(__popc(c2)), "r"(one));
+    }
     __device__ __forceinline__ int total() const { return 2 * twos + __popc(ones); }
 };
 
@@ -359,7 +368,11 @@ constexpr int kRingMaxStages = 64;
 // The L lane partials of the NP * 2 counts are packed two per register (counts <= S < 65536) and combined by a
 // reduce-scatter over the lanes of a row (NP - 1 + ... shuffles instead of 2 * NP * log2 L); the packed totals go
 // through a few words of shared memory so that a few lanes write one record each.
-template <bool SNP, int CB, int LOGL, int NW>
+// PART: the 2 * CB masks of the pass partition ALL samples (one category whose values cover every genome, the config-3
+// shape): the last mask's counts are the row totals minus the other masks' -- its streams run without the AND and
+// without the mask load (the ring kernel is bound by the ALU pipe: 64 of its 132 ALU instructions per 48 bytes of
+// planes are mask ANDs; this drops 16 of them).
+template <bool SNP, int CB, int LOGL, int NW, bool PART = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 count_popc_ring_kernel(const uint4 *__restrict__ pl0, const uint4 *__restrict__ valid,
                        const uint4 *__restrict__ pl2, int64_t n_units, int w4, int w4pad, int kiter,
@@ -471,6 +484,15 @@ count_popc_ring_kernel(const uint4 *__restrict__ pl0, const uint4 *__restrict__ 
                     for (int c = 0; c < CB; ++c)
 #pragma unroll
                         for (int m = 0; m < 2; ++m) {
+                            if (PART && c == CB - 1 && m == 1) {   // row totals (every sample is in some mask)
+                                st[c][m][0].add_fma_all(h, one);
+                                if (SNP) {
+                                    st[c][m][1].add_fma_all(l, one);
+                                    st[c][m][2].add_fma_all(t, one);
+                                }
+                                st[c][m][NQ - 1].add_fma_all(v, one);
+                                continue;
+                            }
                             const uint4 mk = sm_masks[(c * 2 + m) * w4pad + col];
                             st[c][m][0].add_fma(h, mk, one);
                             if (SNP) {
@@ -486,8 +508,17 @@ count_popc_ring_kernel(const uint4 *__restrict__ pl0, const uint4 *__restrict__ 
 #pragma unroll
             for (int c = 0; c < CB; ++c)
 #pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    pk[c * NQ + q] = uint32_t(st[c][0][q].total()) | (uint32_t(st[c][1][q].total()) << 16);
+                for (int q = 0; q < NQ; ++q) {
+                    int second = st[c][1][q].total();
+                    if (PART && c == CB - 1) {   // last mask = totals - the others (a lane's partial sums are linear too)
+#pragma unroll
+                        for (int cc = 0; cc < CB; ++cc) {
+                            second -= st[cc][0][q].total();
+                            if (cc != CB - 1) second -= st[cc][1][q].total();
+                        }
+                    }
+                    pk[c * NQ + q] = uint32_t(st[c][0][q].total()) | (uint32_t(second) << 16);
+                }
             int n = NP;
 #pragma unroll
             for (int o = L >> 1; o > 0; o >>= 1) {
@@ -629,7 +660,7 @@ cudaError_t dispatch(int ncol, int64_t want_ctas, int n_batches, size_t smem, in
 // ---- ring kernel launch.  Returns cudaErrorNotSupported when the shape does not suit it (every warp needs a tile of
 // its own plus a few in flight, and the packed lane partials need S < 65536); the caller then takes the
 // register-staged kernel.
-template <bool SNP, int CB, int LOGL, int NW>
+template <bool SNP, int CB, int LOGL, int NW, bool PART = false>
 cudaError_t launch_ring_t(const uint4 *p0, const uint4 *valid, const uint4 *p2, int64_t n_units, int w4,
                           const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
                           cudaStream_t st) {
@@ -649,7 +680,7 @@ cudaError_t launch_ring_t(const uint4 *p0, const uint4 *valid, const uint4 *p2, 
     if (n_stages < NW + 4) return cudaErrorNotSupported;
     const int64_t n_tiles = (n_units + int64_t(kiter) * RPW - 1) / (int64_t(kiter) * RPW);
     const size_t smem = mask_bytes + size_t(n_stages) * stage_bytes;
-    auto kernel = count_popc_ring_kernel<SNP, CB, LOGL, NW>;
+    auto kernel = count_popc_ring_kernel<SNP, CB, LOGL, NW, PART>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int64_t gx = num_sms / n_batches;
@@ -671,8 +702,26 @@ inline bool ring_enabled() {   // FEHT_SNP_RING=0 / FEHT_POPC_RING=0: register-s
 template <bool SNP, int CB>
 cudaError_t launch_ring_any(const uint4 *p0, const uint4 *valid, const uint4 *p2, int64_t n_units, int w4,
                             const PopcPlan &pl, const uint4 *masks, int n_batches, int4 *counts, int num_sms,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool part = false) {
     if (!ring_enabled() || int64_t(w4) * 128 >= 65536) return cudaErrorNotSupported;
+    if constexpr (SNP && CB == 2) {
+        static const bool part_on = [] { const char *e = getenv("FEHT_SNP_PART"); return !(e && atoi(e) == 0); }();
+        if (part && part_on && n_batches == 1) {
+            cudaError_t e = cudaErrorNotSupported;
+            switch (pl.logL) {
+#define FEHT_RINGP(LL)                                                                                                            \
+    case LL:                                                                                                                      \
+        e = launch_ring_t<SNP, CB, LL, kRingWarps, true>(p0, valid, p2, n_units, w4, pl, masks, n_batches, counts, num_sms, st);  \
+        if (e == cudaErrorNotSupported)                                                                                           \
+            e = launch_ring_t<SNP, CB, LL, 8, true>(p0, valid, p2, n_units, w4, pl, masks, n_batches, counts, num_sms, st);       \
+        break;
+                FEHT_RINGP(0) FEHT_RINGP(1) FEHT_RINGP(2) FEHT_RINGP(3) FEHT_RINGP(4) FEHT_RINGP(5)
+#undef FEHT_RINGP
+                default: break;
+            }
+            if (e != cudaErrorNotSupported) return e;
+        }
+    }
     cudaError_t e = cudaErrorNotSupported;
     switch (pl.logL) {
         // 16 warps; 8 when the stages of 16 do not fit (wide rows)
@@ -691,7 +740,7 @@ cudaError_t launch_ring_any(const uint4 *p0, const uint4 *valid, const uint4 *p2
 template <bool SNP>
 cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p2, int64_t n,
                        int64_t W, const PopcPlan &plan, const uint4 *d_masks, int n_slots,
-                       int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+                       int4 *d_counts, int num_sms, cudaStream_t st, int *launches, bool masks_partition = false) {
     if (n == 0 || n_slots == 0) return cudaSuccess;
     const int w4 = int(W / 2);
     const int rpw = 32 >> plan.logL;
@@ -715,7 +764,9 @@ cudaError_t launch_any(const uint64_t *p0, const uint64_t *p1, const uint64_t *p
         int4 *out = d_counts + size_t(done) * rows_out;
         cudaError_t e = cudaErrorNotSupported;
         // (one binary pair-slot through the ring: 0.2215 ms on config 2 against 0.2126 ms for the register-staged kernel)
-        if (SNP || CB > 1) e = launch_ring_any<SNP, CB>(a, b, c, n, w4, plan, m, n_batches, out, num_sms, st);
+        if (SNP || CB > 1)
+            e = launch_ring_any<SNP, CB>(a, b, c, n, w4, plan, m, n_batches, out, num_sms, st,
+                                         masks_partition && done == 0 && n_batches * CB == n_slots);
         if (e == cudaErrorNotSupported)
             e = dispatch<CB, SNP>(plan.ncol, want, n_batches, size_t(CB) * 2 * plan.w4pad * 16, num_sms, st, a, b, c, n,
                                   w4, plan, m, out);
@@ -777,9 +828,9 @@ cudaError_t launch_count_popc(const uint64_t *d_value, const uint64_t *d_valid, 
 cudaError_t launch_count_popc_snp(const uint64_t *d_hi, const uint64_t *d_valid,
                                   const uint64_t *d_lo, int64_t n_sites, int64_t W,
                                   const PopcPlan &plan, const uint4 *d_masks, int n_slots,
-                                  int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
+                                  int4 *d_counts, int num_sms, cudaStream_t st, int *launches, bool masks_partition) {
     return launch_any<true>(d_hi, d_valid, d_lo, n_sites, W, plan, d_masks, n_slots, d_counts,
-                            num_sms, st, launches);
+                            num_sms, st, launches, masks_partition);
 }
 
 cudaError_t launch_sum_slots(int4 *d_counts, int64_t n_rows, int slot0, int n, int tot_slot, cudaStream_t st) {

@@ -619,12 +619,45 @@ __global__ void __launch_bounds__(256) merge_all_kernel(const __grid_constant__ 
         const unsigned long long kb = merge_key_bits(kd, A.sort_key);
         const uint32_t rk = uint32_t(S.rank[i]);
         long long pos = __ldg(A.out_seg_off + c) + (i - __ldg(S.seg_off + c));
+        // The 32 rows of a warp are consecutive rows of one sorted segment (when they are: the same shard and
+        // comparison in lanes 0 and 31), so their positions in another shard are monotone: lanes 0 and 31 search the
+        // whole segment, the lanes between them only the window those two found (about as many rows as the warp
+        // has, 5-6 steps instead of ~23: a third of the random reads).
+        const unsigned full = 0xffffffffu;
+        const bool whole_warp = __activemask() == full;
+        bool narrow = false;
+        if (whole_warp) {
+            const int s0 = __shfl_sync(full, s, 0), s1 = __shfl_sync(full, s, 31);
+            const int c0 = __shfl_sync(full, c, 0), c1 = __shfl_sync(full, c, 31);
+            narrow = s0 == s1 && c0 == c1;
+        }
+        const int lane = threadIdx.x & 31;
         for (int t = 0; t < A.n_shards; ++t) {
             if (t == s) continue;
             const MergeAllShard &T = A.sh[t];
             const long long t0 = __ldg(T.seg_off + c);
             long long lo = t0, hi = __ldg(T.seg_off + c + 1);
             const double *tk = A.sort_key == FEHT_SORT_PVALUE_ASC ? T.p : T.ratio;
+            if (narrow) {
+                long long edge = lo;
+                if (lane == 0 || lane == 31) {
+                    long long a = lo, b = hi;
+                    while (a < b) {
+                        const long long mid = (a + b) >> 1;
+                        const unsigned long long ke = merge_key_bits(__ldg(tk + mid), A.sort_key);
+                        bool before = ke < kb;
+                        if (ke == kb) {
+                            const uint32_t re = uint32_t(__ldg(T.rank + mid));
+                            before = re < rk || (re == rk && t < s);
+                        }
+                        if (before) a = mid + 1; else b = mid;
+                    }
+                    edge = a;
+                }
+                lo = __shfl_sync(full, edge, 0);
+                hi = __shfl_sync(full, edge, 31);
+                if (lane == 0 || lane == 31) lo = hi = edge;
+            }
             while (lo < hi) {
                 const long long mid = (lo + hi) >> 1;
                 const unsigned long long ke = merge_key_bits(__ldg(tk + mid), A.sort_key);
