@@ -164,18 +164,6 @@ cudaError_t launch_count_gemm(const uint64_t *d_value, const uint64_t *d_valid, 
                               int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes, bool fp4,
                               int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
 
-// value-plane-only mxf4 flavour (count_gemm.cu "value plane only"): N = column size - missing calls, counted by the
-// expander threads from the valid plane.  gemm_m1_bake returns false when a sample sits in more columns of a pass than
-// the id table holds (the caller then keeps the two-plane kernel).
-size_t gemm_m1_pass_desc_bytes();
-size_t gemm_m1_block_bytes(int n_pad);
-bool gemm_m1_bake(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, uint8_t *out);
-void gemm_m1_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_offset,
-                       const std::vector<std::vector<int32_t>> &columns);
-cudaError_t launch_count_gemm_m1(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
-                                 int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
-                                 int4 *d_counts, int num_sms, cudaStream_t st, int *launches);
-
 // fet.cu  (K3)
 // What the final gather needs about a surviving test: exactly one 32-byte sector.
 struct __align__(16) SurvivorRec {

@@ -22,20 +22,25 @@
 //     byte order the UMMA shared-memory descriptor expects, one contiguous N x 128 B block per
 //     128-sample stage, so a plain 1-D bulk copy (cp.async.bulk, UBLKCP) per stage suffices; the
 //     K order inside a stage is permuted to match the cheap bit expansion (see bake_b()).
-//   * D: four s32 accumulators (2 row tiles x {value, valid} plane) x N <= 64 columns live in TMEM
-//     (256 of the 512 columns; the other 256 are the double-buffered A stages).  One elected thread
-//     issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32); completion is tracked with
-//     tcgen05.commit on mbarriers.  The epilogue reads the accumulators back with tcgen05.ld and
-//     writes the int4 (P_even, N_even, P_odd, N_odd) pair-slot records K3 consumes -- the same
-//     layout K1 produces, so K3/K4 do not care which engine counted.
-//   * warp roles: 0-7 expand + epilogue, 8 TMA producer for the planes, 9 bulk-copy producer for
-//     B, 10 MMA issuer (+ TMEM allocation).  Persistent CTAs, one per SM, static tile round-robin.
+//   * D: four accumulators (2 row tiles x {value, valid} plane) x N <= 64 columns live in TMEM (256 of the 512
+//     columns; the rest are the A stage buffers).  tcgen05.mma.cta_group::1 (kind::i8: M=128, N, K=32; kind::mxf4: K=64)
+//     is issued by single threads; completion is tracked with tcgen05.commit on mbarriers.  Every MMA accumulates: the
+//     accumulators start at zero and the epilogue zeroes what it has read.  The epilogue reads them back with
+//     tcgen05.ld and writes the int4 (P_even, N_even, P_odd, N_odd) pair-slot records K3 consumes -- the same layout
+//     K1 produces, so K3/K4 do not care which engine counted.
+//   * warp roles: 0-7 expand + epilogue, 8 TMA producer for the planes, 9 bulk-copy producer for B, 10-13 MMA
+//     issuers (+ TMEM allocation).  Persistent CTAs, one per SM, static tile round-robin.
 //
-// Bounds (measured, profiles/README.md r1c): one tcgen05.mma of this shape (M=128, K=32, A from
-// TMEM) costs ~85 cycles whatever N <= 64 is -- the tensor pipe itself is busy 32 of them at N=64 --
-// so the kernel runs at the instruction-issue floor of 16 MMAs per 128 samples per 256 rows, about
-// 1.8 int8 POP/s; the expanders (~10 instructions per 32 calls per row) and HBM (planes read once
-// per pass of <= 32 value pairs, 1.8 TB/s) are both under it.
+// What paces it (measured on config 4, 2M x 20k, N = 64; profiles/README.md r1c, r1s, r1t and the round-2 probes):
+//   * the planes alone stream at 6.7 TB/s through the TMA boxes (1.49 ms: the kernel with the stage loop cut out);
+//   * the hand-over skeleton -- every barrier, no expansion, no MMA -- already takes 1.92 ms (~440 cycles per
+//     128-sample stage), and that does not move with the depth of any ring (A buffers 2/3/4, B ring 3..12, plane
+//     buffers 2/3), nor with spinning on test_wait instead of try_wait, nor with half the MMAs (a value-plane-only
+//     variant: 2.08 ms);
+//   * on top of it, a stage's MMAs cost the ISSUING THREAD ~530 cycles + ~48 per MMA, so round 1's four issuers (one
+//     per accumulator, each on every stage) ran at 650 cycles per stage = 2.83 ms.  Round 2, mxf4: one issuer per
+//     stage in flight (three, one per A buffer), each issuing all 8 MMAs of its stage: 2.28 ms = 4.4 TB/s of planes,
+//     0.67 of the measured HBM peak; the i8 flavour keeps an issuer per accumulator (3.3 ms).
 #include <cuda.h>
 
 #include <cstring>
@@ -236,15 +241,17 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
         }
         // one issuer handles a whole stage (all four accumulators): it alone hands the A buffer back; a B block serves
         // kAPerB consecutive stages, i.e. that many issuers
+        // mxf4: one issuer handles a whole stage (it alone hands the A buffer back; a B block serves two stages = two
+        // issuers; three issuers close a tile).  i8: four issuers, one per accumulator, each on every stage.
         for (int i = 0; i < 3; ++i) {
             mbar_init(ta_full + i * 8, kExpandWarps);
-            mbar_init(ta_empty + i * 8, 1);
+            mbar_init(ta_empty + i * 8, FP4 ? 1 : 4);
         }
         for (int i = 0; i < kBStages; ++i) {
             mbar_init(b_full + i * 8, 1);
-            mbar_init(b_empty + i * 8, FP4 ? 2 : 1);
+            mbar_init(b_empty + i * 8, FP4 ? 2 : 4);
         }
-        mbar_init(acc_full, FP4 ? 3 : 2);   // = kABufs issuers (below)
+        mbar_init(acc_full, FP4 ? 3 : 4);
         mbar_init(acc_empty, kExpandWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -402,42 +409,42 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
             }
         }
     } else {
-        // =============================================== MMA issuers, one warp per STAGE in flight.  A stage's hand-over
-        // (two mbarrier waits, a fence, the issues, the commits) costs an issuing thread ~530 cycles + ~48 per MMA
-        // whatever the tensor pipe does (profiles/README.md r1s), so issuer w takes every kABufs-th stage
-        // and issues ALL of a stage's MMAs (2 M tiles x 2 planes x K steps): the fixed part is paid once
-        // per 8 (mxf4) / 16 (i8) MMAs and the issuers overlap each other's waits.  Stages of one tile accumulate into
-        // the same four accumulators from different threads: every MMA accumulates (the accumulators are zeroed by the
-        // epilogue), sums of integers below 2^24 do not depend on the order, and the tensor pipe executes one MMA at
-        // a time.  (Round 1 gave each issuer one accumulator and every stage: same MMAs per thread and stage as with
-        // a single issuer per accumulator, the hand-over cost stayed -- halving the MMAs did not change the time.)
-        // As many issuers as A stage buffers, issuer w <-> buffer w: the stages an issuer handles are then consecutive
-        // phases of ITS ta_full barrier (a parity wait cannot tell a phase from the one two before it, so an issuer
-        // must never run a whole ring ahead of the expanders -- with four issuers on three buffers it did, and hung).
+        // =============================================== MMA issuers.  Every MMA accumulates (the accumulators start at zero
+        // and the epilogue zeroes what it has read), so no issuer is "the first" of a tile.
         const int mw = warp - (kExpandWarps + 2);
-        if (lane == 0 && mw < kABufs) {
-            // instruction descriptor, N = n_pad, M = 128, both operands K-major.  i8: D s32, A/B unsigned 8-bit.
-            // mxf4 (block-scaled layout): A/B e2m1 (format 1), UE8M0 scales, scale ids 0, K = 64.
-            const uint32_t idesc = FP4 ? ((1u << 7) | (1u << 10) | (uint32_t(n_pad >> 3) << 17) | (1u << 23) |
-                                          (uint32_t(128 >> 4) << 24))
-                                       : ((2u << 4) | (uint32_t(n_pad >> 3) << 17) | (uint32_t(128 >> 4) << 24));
-            const uint32_t n_bblocks = uint32_t((n_stages + kAPerB - 1) / kAPerB);
-            uint32_t tile_ctr = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
-                mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tile_stage0 = tile_ctr * uint32_t(n_stages);
-                for (int s = int((uint32_t(mw) + uint32_t(kABufs) - tile_stage0 % kABufs) % kABufs); s < n_stages; s += kABufs) {
-                    const uint32_t stage_ctr = tile_stage0 + uint32_t(s);   // stage_ctr % kABufs == mw
-                    const uint32_t bblock_ctr = tile_ctr * n_bblocks + uint32_t(s / kAPerB);
-                    const uint32_t tb = stage_ctr % kABufs;
-                    const int half = s % kAPerB;                 // which part of the B block this A stage uses
-                    const uint32_t bs = bblock_ctr % kBStages;
-                    mbar_wait(ta_full + tb * 8, (stage_ctr / kABufs) & 1);
-                    mbar_wait(b_full + bs * 8, (bblock_ctr / kBStages) & 1);
+        // instruction descriptor, N = n_pad, M = 128, both operands K-major.  i8: D s32, A/B unsigned 8-bit.
+        // mxf4 (block-scaled layout): A/B e2m1 (format 1), UE8M0 scales, scale ids 0, K = 64.
+        const uint32_t idesc = FP4 ? ((1u << 7) | (1u << 10) | (uint32_t(n_pad >> 3) << 17) | (1u << 23) |
+                                      (uint32_t(128 >> 4) << 24))
+                                   : ((2u << 4) | (uint32_t(n_pad >> 3) << 17) | (uint32_t(128 >> 4) << 24));
+        if (FP4) {
+            // mxf4: one issuer per STAGE in flight.  A stage's hand-over (two mbarrier waits, a fence, the issues, the
+            // commits) costs an issuing thread ~530 cycles + ~48 per MMA whatever the tensor pipe does
+            // (profiles/README.md r1s), so issuer w takes every third stage and issues ALL of its MMAs (2 M tiles x
+            // 2 planes x 2 K steps): the fixed part is paid once per 8 MMAs and the issuers overlap each other's waits
+            // (config 4: 2.83 -> 2.28 ms).  Stages of one tile accumulate into the same four accumulators from
+            // different threads: sums of integers below 2^24 do not depend on the order, and the tensor pipe retires
+            // one MMA at a time (counts bit-identical in every engine test).  As many issuers as A stage buffers,
+            // issuer w <-> buffer w: its stages are consecutive phases of ITS ta_full barrier, and with a B ring of 6
+            // it meets every B slot it uses once per ring cycle -- a parity wait cannot tell a phase from the one two
+            // before it (four issuers on three buffers ran a ring ahead of the expanders, and hung).
+            if (lane == 0 && mw < kABufs) {
+                const uint32_t n_bblocks = uint32_t((n_stages + kAPerB - 1) / kAPerB);
+                uint32_t tile_ctr = 0;
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
+                    mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
                     tc_fence_after();
-                    const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kBStageBytes);
-                    if (FP4) {
+                    const uint32_t tile_stage0 = tile_ctr * uint32_t(n_stages);
+                    for (int s = int((uint32_t(mw) + uint32_t(kABufs) - tile_stage0 % kABufs) % kABufs); s < n_stages; s += kABufs) {
+                        const uint32_t stage_ctr = tile_stage0 + uint32_t(s);   // stage_ctr % kABufs == mw
+                        const uint32_t bblock_ctr = tile_ctr * n_bblocks + uint32_t(s / kAPerB);
+                        const uint32_t tb = stage_ctr % kABufs;
+                        const int half = s % kAPerB;                 // which part of the B block this A stage uses
+                        const uint32_t bs = bblock_ctr % kBStages;
+                        mbar_wait(ta_full + tb * 8, (stage_ctr / kABufs) & 1);
+                        mbar_wait(b_full + bs * 8, (bblock_ctr / kBStages) & 1);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kBStageBytes);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -446,295 +453,40 @@ count_gemm_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_con
                                            tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
                                            bdesc + uint64_t((half * 2 + ks) * 2), idesc, tmem_base + kTmemSF, 1u);
                         }
-                    } else {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)   // q = mt * 2 + plane
-                                mma_i8_ts(tmem_base + kTmemAccBase + q * 64,
-                                          tmem_base + kTmemABase + tb * kABuf + q * kAColsQ + ks * 8,
-                                          bdesc + uint64_t(ks * 2), idesc, 1u);
-                        }
+                        tc_commit(ta_empty + tb * 8);
+                        tc_commit(b_empty + bs * 8);
+                        // a trailing B block that serves one stage only still owes its barrier the second arrival
+                        if (half == 0 && s == n_stages - 1) tc_commit(b_empty + bs * 8);
                     }
-                    tc_commit(ta_empty + tb * 8);
-                    tc_commit(b_empty + bs * 8);
-                    // a trailing B block that serves one stage only still owes its barrier the second arrival
-                    if (FP4 && half == 0 && s == n_stages - 1) tc_commit(b_empty + bs * 8);
+                    tc_commit(acc_full);   // arrives once this issuer's MMAs of the tile have retired
                 }
-                tc_commit(acc_full);   // arrives once this issuer's MMAs of the tile have retired
             }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kExpandWarps + 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
-                     : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------ value plane only
-// kind::mxf4 with ONE contraction (round 2).  With an issuer per stage in flight the two-plane kernel runs at the pace
-// of the tensor pipe: one MMA of M = 128, N = 64 retires every ~65 cycles whatever its K (every MMA reads and writes
-// its whole 128 x N accumulator tile), and a 128-sample stage needs 8 of them (2 M tiles x 2 planes x 2 K steps).
-// N[row][v] = #{valid calls of the samples with value v} does not need a contraction of its own:
-//     N[row][v] = |v| - missing[row][v],      |v| = samples with value v (a constant of the column),
-// and missing calls are rare (~1%), so the expander threads (thread = marker row), which hold the valid plane's words
-// in registers anyway, walk the zero bits: each one looks up the columns of its sample in a small table that travels
-// with the one-hot block (8 column ids per sample, 0xff = none) and bumps a 16-bit counter in shared memory that only
-// this thread touches.  Half the MMAs, half the expansion, half the tensor-memory stores; accumulators and A stages
-// take half the columns, so there are four A stage buffers and four issuers.  The cost grows with the share of
-// missing calls (a loop iteration per missing call and row); FEHT_ENGINE_GEMM_FP4 keeps the two-plane kernel.
-constexpr int kM1BStages = 5;
-constexpr int kM1Ids = 8;                                   // column ids per sample and pass
-constexpr int kM1IdBytes = 256 * kM1Ids;                    // per B block (256 samples)
-constexpr int kM1BStageBytes = kNMax * 128 + kM1IdBytes;
-constexpr int kM1ABufs = 4;
-constexpr int kM1SmemB = kSmemPlanes + 4 * kPlaneTileBytes;
-constexpr int kM1SmemCnt = kM1SmemB + kM1BStages * kM1BStageBytes;    // uint16 missing[kNMax][kTileRows]
-constexpr int kM1SmemBars = kM1SmemCnt + kNMax * kTileRows * 2;
-constexpr int kM1NumBars = 2 + 2 + 2 * kM1BStages + 2 * kM1ABufs + 2;
-constexpr int kM1SmemTmemPtr = kM1SmemBars + kM1NumBars * 8;
-constexpr int kM1SmemTotal = kM1SmemTmemPtr + 16 + 1024;
-constexpr int kM1TmemA = 128;                               // + buf * 32 + mt * 16
-constexpr int kM1TmemSF = kM1TmemA + kM1ABufs * 32;
-
-struct GemmPassM1 {
-    int32_t slot_base, n_pairs, n_pad, pad;
-    int64_t b_offset;            // byte offset of the pass's blocks: [n_bblocks][n_pad * 128 + kM1IdBytes]
-    int32_t col_size[kNMax];     // samples carrying a 1 in GEMM column c
-};
-
-__global__ void __launch_bounds__(kThreads2, 1)
-count_gemm_m1_kernel(const __grid_constant__ CUtensorMap tm_value, const __grid_constant__ CUtensorMap tm_valid,
-                     const uint8_t *__restrict__ bmat, const GemmPassM1 *__restrict__ passes, int n_stages,
-                     int64_t n_rows, int n_tiles, int4 *__restrict__ counts) {
-    extern __shared__ unsigned char smem_dyn[];
-    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    unsigned char *base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-    const uint32_t bars = base + kM1SmemBars;
-    const uint32_t a_full = bars;                           // [2]  planes landed in smem
-    const uint32_t a_empty = a_full + 2 * 8;                // [2]  expanders done with a plane buffer
-    const uint32_t b_full = a_empty + 2 * 8;                // [kM1BStages]
-    const uint32_t b_empty = b_full + kM1BStages * 8;       // [kM1BStages]  issuers' commits + the expanders' scans
-    const uint32_t ta_full = b_empty + kM1BStages * 8;      // [kM1ABufs]
-    const uint32_t ta_empty = ta_full + kM1ABufs * 8;       // [kM1ABufs]
-    const uint32_t acc_full = ta_empty + kM1ABufs * 8;
-    const uint32_t acc_empty = acc_full + 8;
-    volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(base_ptr + kM1SmemTmemPtr);
-    uint16_t *miss = reinterpret_cast<uint16_t *>(base_ptr + kM1SmemCnt);
-    __shared__ int32_t s_col_size[kNMax];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const GemmPassM1 *pass = passes + blockIdx.y;
-    const int n_pad = pass->n_pad, n_pairs = pass->n_pairs, slot_base = pass->slot_base;
-    const uint32_t b_bytes = uint32_t(n_pad) * 128u + uint32_t(kM1IdBytes);
-    const uint32_t n_bblocks = uint32_t((n_stages + 1) / 2);
-    for (int i = threadIdx.x; i < kNMax; i += blockDim.x) s_col_size[i] = pass->col_size[i];
-    for (int i = threadIdx.x; i < kNMax * kTileRows / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(miss)[i] = 0u;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full + i * 8, 1);
-            mbar_init(a_empty + i * 8, kExpandWarps);
-        }
-        for (int i = 0; i < kM1ABufs; ++i) {
-            mbar_init(ta_full + i * 8, kExpandWarps);
-            mbar_init(ta_empty + i * 8, 1);
-        }
-        for (int i = 0; i < kM1BStages; ++i) {
-            mbar_init(b_full + i * 8, 1);
-            mbar_init(b_empty + i * 8, 2 + 2 * kExpandWarps);   // two stages: an issuer's commit + eight scanning warps each
-        }
-        mbar_init(acc_full, kM1ABufs);
-        mbar_init(acc_empty, kExpandWarps);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kExpandWarps + 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(const_cast<uint32_t *>(tmem_ptr_smem))), "n"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const int n_chunks = (n_stages + kStagesPerChunk - 1) / kStagesPerChunk;
-
-    if (warp < kExpandWarps) {
-        // accumulators start at zero (every MMA accumulates), scale columns hold UE8M0 1.0
-        const uint32_t la = uint32_t((warp & 3) * 32) << 16;
-        uint32_t zero[8], one[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { zero[j] = 0u; one[j] = 0x7F7F7F7Fu; }
-        for (int c0 = 0; c0 < 64; c0 += 8) tmem_st8(tmem_base + la + (threadIdx.x >> 7) * 64 + c0, zero);
-        if (warp < 4) tmem_st8(tmem_base + la + kM1TmemSF, one);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    if (warp < kExpandWarps) {
-        // =============================================== expanders + missing scan + epilogue: thread = marker row
-        const int r = threadIdx.x;
-        const int mt = r >> 7;
-        const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
-        const uint32_t row_off = uint32_t(r) * kChunkBytes;
-        const uint32_t sw = uint32_t(r & 7);
-        uint32_t chunk_ctr = 0, stage_ctr = 0, tile_ctr = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
-            for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-                const uint32_t cb = chunk_ctr & 1;
-                mbar_wait(a_full + cb * 8, (chunk_ctr >> 1) & 1);
-                const unsigned char *pv = base_ptr + kSmemPlanes + (cb * 2 + 0) * kPlaneTileBytes + row_off;
-                const unsigned char *pd = base_ptr + kSmemPlanes + (cb * 2 + 1) * kPlaneTileBytes + row_off;
-                const int st_n = min(kStagesPerChunk, n_stages - ch * kStagesPerChunk);
-                for (int st = 0; st < st_n; ++st, ++stage_ctr) {
-                    const uint32_t phys = (uint32_t(st) ^ sw) << 4;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(pv + phys);
-                    const uint4 d = *reinterpret_cast<const uint4 *>(pd + phys);
-                    const uint32_t tb = stage_ctr % kM1ABufs;
-                    mbar_wait(ta_empty + tb * 8, ((stage_ctr / kM1ABufs) & 1) ^ 1);
+        } else {
+            // i8: one issuer per ACCUMULATOR (2 M tiles x 2 planes), each on every stage -- with only two A stage
+            // buffers (tensor memory is full: 256 accumulator + 2 x 128 operand columns) a stage-parallel scheme has
+            // two issuers, which is slower (4.1 ms against 3.3 ms on config 4).
+            if (lane == 0) {
+                uint32_t stage_ctr = 0, tile_ctr = 0;
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
+                    mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t ta = tmem_base + lane_addr + kM1TmemA + tb * 32 + mt * 16;
-                    expand_store_fp4(ta + 0, v.x, v.y);
-                    expand_store_fp4(ta + 8, v.z, v.w);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(ta_full + tb * 8);
-                    // ---- the missing calls of this row in this stage: zero bits of the valid plane.  Padding bits
-                    // (samples >= S, rows past the end) are zero too: their ids say "no column".
-                    const int s_in_tile = ch * kStagesPerChunk + st;
-                    const uint32_t bblock_ctr = tile_ctr * n_bblocks + uint32_t(s_in_tile >> 1);
-                    const uint32_t bs = bblock_ctr % kM1BStages;
-                    const uint32_t inv[4] = {~d.x, ~d.y, ~d.z, ~d.w};
-                    if (__any_sync(0xffffffffu, (inv[0] | inv[1] | inv[2] | inv[3]) != 0u)) {
-                        mbar_wait(b_full + bs * 8, (bblock_ctr / kM1BStages) & 1);
-                        const uint2 *ids = reinterpret_cast<const uint2 *>(base_ptr + kM1SmemB + bs * kM1BStageBytes +
-                                                                            uint32_t(n_pad) * 128u) + (s_in_tile & 1) * 128;
+                    for (int s = 0; s < n_stages; ++s, ++stage_ctr) {
+                        const uint32_t tb = stage_ctr % kABufs;
+                        const uint32_t bs = stage_ctr % kBStages;
+                        mbar_wait(ta_full + tb * 8, (stage_ctr / kABufs) & 1);
+                        mbar_wait(b_full + bs * 8, (stage_ctr / kBStages) & 1);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_b_desc(base + kSmemB + bs * kBStageBytes);
 #pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            uint32_t x = inv[w];
-                            while (x) {
-                                const int b = __ffs(int(x)) - 1;
-                                x &= x - 1u;
-                                uint2 id = ids[w * 32 + b];
-#pragma unroll 1
-                                for (int k = 0; k < kM1Ids; ++k) {
-                                    const uint32_t c = (k < 4 ? id.x >> (8 * k) : id.y >> (8 * (k - 4))) & 0xffu;
-                                    if (c == 0xffu) break;
-                                    miss[c * kTileRows + r] = uint16_t(miss[c * kTileRows + r] + 1u);
-                                }
-                            }
-                        }
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_i8_ts(tmem_base + kTmemAccBase + mw * 64,
+                                      tmem_base + kTmemABase + tb * kABuf + mw * kAColsQ + ks * 8,
+                                      bdesc + uint64_t(ks * 2), idesc, 1u);
+                        tc_commit(ta_empty + tb * 8);
+                        tc_commit(b_empty + bs * 8);
                     }
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(b_empty + bs * 8);
-                        // a trailing B block serves one stage only: it still owes its barrier the other stage's arrivals
-                        if ((s_in_tile & 1) == 0 && s_in_tile == n_stages - 1) mbar_arrive(b_empty + bs * 8);
-                    }
+                    tc_commit(acc_full);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_empty + cb * 8);
-            }
-            // ---- epilogue: P from the accumulator, N = column size - missing; both are reset for the next tile
-            mbar_wait(acc_full, tile_ctr & 1);
-            tc_fence_after();
-            const int64_t row = int64_t(tile) * kTileRows + r;
-            const uint32_t acc_p = tmem_base + lane_addr + mt * 64;
-            for (int c0 = 0; c0 < n_pad; c0 += 16) {
-                uint32_t P[16];
-                tmem_ld16(acc_p + c0, P);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                {
-                    uint32_t zero[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) zero[j] = 0u;
-                    tmem_st8(acc_p + c0, zero); tmem_st8(acc_p + c0 + 8, zero);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int pair = (c0 >> 1) + j;
-                    const int ce = c0 + 2 * j, co = ce + 1;
-                    const int me = miss[ce * kTileRows + r], mo = miss[co * kTileRows + r];
-                    miss[ce * kTileRows + r] = 0; miss[co * kTileRows + r] = 0;
-                    if (row < n_rows && pair < n_pairs)
-                        counts[size_t(slot_base + pair) * size_t(n_rows) + size_t(row)] =
-                            make_int4(__float2int_rn(__uint_as_float(P[2 * j])), s_col_size[ce] - me,
-                                      __float2int_rn(__uint_as_float(P[2 * j + 1])), s_col_size[co] - mo);
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
-        }
-    } else if (warp == kExpandWarps) {
-        // =============================================== TMA producer: bit-plane boxes (both planes: the scan reads valid)
-        if (lane == 0) {
-            uint32_t chunk_ctr = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-                    const uint32_t cb = chunk_ctr & 1;
-                    mbar_wait(a_empty + cb * 8, ((chunk_ctr >> 1) & 1) ^ 1);
-                    mbar_expect_tx(a_full + cb * 8, 2u * kPlaneTileBytes);
-                    tma_load_2d(base + kSmemPlanes + (cb * 2 + 0) * kPlaneTileBytes, &tm_value,
-                                ch * kChunkBytes, tile * kTileRows, a_full + cb * 8);
-                    tma_load_2d(base + kSmemPlanes + (cb * 2 + 1) * kPlaneTileBytes, &tm_valid,
-                                ch * kChunkBytes, tile * kTileRows, a_full + cb * 8);
-                }
-            }
-        }
-    } else if (warp == kExpandWarps + 1) {
-        // =============================================== bulk-copy producer: one-hot block + the samples' column ids
-        if (lane == 0) {
-            uint32_t ctr = 0;
-            const uint8_t *bsrc = bmat + pass->b_offset;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (uint32_t s = 0; s < n_bblocks; ++s, ++ctr) {
-                    const uint32_t bs = ctr % kM1BStages;
-                    mbar_wait(b_empty + bs * 8, ((ctr / kM1BStages) & 1) ^ 1);
-                    mbar_expect_tx(b_full + bs * 8, b_bytes);
-                    bulk_load_1d(base + kM1SmemB + bs * kM1BStageBytes, bsrc + size_t(s) * b_bytes, b_bytes, b_full + bs * 8);
-                }
-            }
-        }
-    } else {
-        // =============================================== MMA issuers: issuer w <-> A buffer w (see count_gemm_kernel)
-        const int mw = warp - (kExpandWarps + 2);
-        if (lane == 0 && mw < kM1ABufs) {
-            const uint32_t idesc = (1u << 7) | (1u << 10) | (uint32_t(n_pad >> 3) << 17) | (1u << 23) | (uint32_t(128 >> 4) << 24);
-            uint32_t tile_ctr = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_ctr) {
-                mbar_wait(acc_empty, (tile_ctr & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tile_stage0 = tile_ctr * uint32_t(n_stages);
-                for (int s = int((uint32_t(mw) + uint32_t(kM1ABufs) - tile_stage0 % kM1ABufs) % kM1ABufs); s < n_stages; s += kM1ABufs) {
-                    const uint32_t stage_ctr = tile_stage0 + uint32_t(s);
-                    const uint32_t bblock_ctr = tile_ctr * n_bblocks + uint32_t(s >> 1);
-                    const uint32_t tb = stage_ctr % kM1ABufs;
-                    const int half = s & 1;
-                    const uint32_t bs = bblock_ctr % kM1BStages;
-                    mbar_wait(ta_full + tb * 8, (stage_ctr / kM1ABufs) & 1);
-                    mbar_wait(b_full + bs * 8, (bblock_ctr / kM1BStages) & 1);
-                    tc_fence_after();
-                    const uint64_t bdesc = make_b_desc(base + kM1SmemB + bs * kM1BStageBytes);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                        for (int m = 0; m < 2; ++m)
-                            mma_fp4_ts(tmem_base + m * 64, tmem_base + kM1TmemA + tb * 32 + m * 16 + ks * 8,
-                                       bdesc + uint64_t((half * 2 + ks) * 2), idesc, tmem_base + kM1TmemSF, 1u);
-                    tc_commit(ta_empty + tb * 8);
-                    tc_commit(b_empty + bs * 8);
-                    if (half == 0 && s == n_stages - 1) tc_commit(b_empty + bs * 8);
-                }
-                tc_commit(acc_full);
             }
         }
     }
@@ -1095,41 +847,6 @@ void gemm_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_
     std::memcpy(dst, &p, sizeof(p));
 }
 
-// ---- value-plane-only flavour: blocks of [n_pad][128] one-hot e2m1 (the fp4 layout) followed by the column ids of
-// the block's 256 samples.  False when some sample sits in more than kM1Ids columns of the pass.
-size_t gemm_m1_pass_desc_bytes() { return sizeof(GemmPassM1); }
-size_t gemm_m1_block_bytes(int n_pad) { return size_t(n_pad) * 128 + kM1IdBytes; }
-bool gemm_m1_bake(const std::vector<std::vector<int32_t>> &columns, int n_pad, int64_t S, uint8_t *out) {
-    const int n_blocks = gemm_bblock_count(S, true);
-    const size_t hot = size_t(n_pad) * 128, blk = gemm_m1_block_bytes(n_pad);
-    std::vector<uint8_t> tmp(size_t(n_blocks) * hot);
-    gemm_bake_b(columns, n_pad, S, true, tmp.data());
-    std::vector<uint8_t> fill(size_t(n_blocks) * 256, 0);   // ids used per sample slot
-    for (int g = 0; g < n_blocks; ++g) {
-        std::memcpy(out + size_t(g) * blk, tmp.data() + size_t(g) * hot, hot);
-        std::memset(out + size_t(g) * blk + hot, 0xff, kM1IdBytes);
-    }
-    for (size_t n = 0; n < columns.size(); ++n)
-        for (int32_t s : columns[n]) {
-            const size_t g = size_t(s) / 256, p = size_t(s) % 256;
-            uint8_t &used = fill[g * 256 + p];
-            if (used >= kM1Ids) return false;
-            out[g * blk + hot + p * kM1Ids + used] = uint8_t(n);
-            ++used;
-        }
-    return true;
-}
-void gemm_m1_fill_pass(void *dst, int slot_base, int n_pairs, int n_pad, int64_t b_offset,
-                       const std::vector<std::vector<int32_t>> &columns) {
-    GemmPassM1 p{};
-    p.slot_base = slot_base;
-    p.n_pairs = n_pairs;
-    p.n_pad = n_pad;
-    p.b_offset = b_offset;
-    for (int i = 0; i < kNMax; ++i) p.col_size[i] = i < int(columns.size()) ? int32_t(columns[size_t(i)].size()) : 0;
-    std::memcpy(dst, &p, sizeof(p));
-}
-
 // ---- e5m2 flavour: one GEMM column per (value, chunk of <= 4095 member samples)
 size_t gemm_f8_pass_desc_bytes() { return sizeof(GemmPassF8); }
 int gemm_f8_max_cols() { return kF8NMax; }
@@ -1180,26 +897,6 @@ cudaError_t launch_count_gemm_f8(const uint64_t *d_value, const uint64_t *d_vali
     if (gx > n_tiles) gx = n_tiles;
     count_gemm_f8_kernel<<<dim3(unsigned(gx), unsigned(n_passes)), kF8Threads, kF8SmemTotal, st>>>(
         tm_value, tm_valid, d_bmat, static_cast<const GemmPassF8 *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
-        d_counts);
-    if (launches) ++*launches;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_count_gemm_m1(const uint64_t *d_value, const uint64_t *d_valid, int64_t n_rows, int64_t W,
-                                 int64_t S, const uint8_t *d_bmat, const void *d_passes, int n_passes,
-                                 int4 *d_counts, int num_sms, cudaStream_t st, int *launches) {
-    if (n_rows == 0 || n_passes == 0) return cudaSuccess;
-    CUtensorMap tm_value, tm_valid;
-    if (!make_plane_map(&tm_value, d_value, n_rows, W) || !make_plane_map(&tm_valid, d_valid, n_rows, W))
-        return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(count_gemm_m1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kM1SmemTotal);
-    if (e != cudaSuccess) return e;
-    const int n_tiles = int((n_rows + kTileRows - 1) / kTileRows);
-    int gx = num_sms / n_passes;
-    if (gx < 1) gx = 1;
-    if (gx > n_tiles) gx = n_tiles;
-    count_gemm_m1_kernel<<<dim3(unsigned(gx), unsigned(n_passes)), kThreads2, kM1SmemTotal, st>>>(
-        tm_value, tm_valid, d_bmat, static_cast<const GemmPassM1 *>(d_passes), gemm_stage_count(S), n_rows, n_tiles,
         d_counts);
     if (launches) ++*launches;
     return cudaGetLastError();

@@ -15,7 +15,7 @@ from feht_b200 import capi  # noqa: E402
 from helpers import make_spec  # noqa: E402
 
 
-def run(cfg, rows, engine, steps, ratio_filter=None, samples=None):
+def run(cfg, rows, engine, steps, ratio_filter=None, samples=None, missing=None):
     eng = {"popc": capi.ENGINE_POPC, "gemm": capi.ENGINE_GEMM, "fp4": capi.ENGINE_GEMM_FP4, "f8": capi.ENGINE_GEMM_F8, "auto": capi.ENGINE_AUTO}[engine]
     with capi.Context(0) as ctx:
         if cfg == "c3":      # SNP 500k sites x 10k, one 4-value category -> 10 comparisons x 2M allele rows
@@ -48,7 +48,7 @@ def run(cfg, rows, engine, steps, ratio_filter=None, samples=None):
             cats = [[(np.arange(S) * 4 // S).astype(np.int32), 4]]
         ctx.set_samples(S)
         ctx.reserve_rows(rows)
-        sp = make_spec(capi.SynthSpec, S, law="uniform_half" if snp else "beta")
+        sp = make_spec(capi.SynthSpec, S, law="uniform_half" if snp else "beta", **({} if missing is None else {"missing": missing}))
         ctx.generate_synthetic(sp, snp, 0, rows)
         if cfg == "c2b":
             ctx.add_comparison(np.arange(0, 300), np.arange(300, 700))
@@ -97,5 +97,6 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--ratio-filter", type=float, default=None)
     ap.add_argument("--samples", type=int, default=None)
+    ap.add_argument("--missing", type=float, default=None, help="share of missing calls of the synthetic matrix (default 0.01)")
     a = ap.parse_args()
-    run(a.cfg, a.rows, a.engine, a.steps, a.ratio_filter, a.samples)
+    run(a.cfg, a.rows, a.engine, a.steps, a.ratio_filter, a.samples, a.missing)
