@@ -34,9 +34,10 @@
 // What paces it (measured on config 4, 2M x 20k, N = 64; profiles/README.md r1c, r1s, r1t and the round-2 probes):
 //   * the planes alone stream at 6.7 TB/s through the TMA boxes (1.49 ms: the kernel with the stage loop cut out);
 //   * the hand-over skeleton -- every barrier, no expansion, no MMA -- already takes 1.92 ms (~440 cycles per
-//     128-sample stage), and that does not move with the depth of any ring (A buffers 2/3/4, B ring 3..12, plane
-//     buffers 2/3), nor with spinning on test_wait instead of try_wait, nor with half the MMAs (a value-plane-only
-//     variant: 2.08 ms);
+//     128-sample stage), and that does not move with the depth of any ring (A buffers 2/3/4, B ring 6/12 -- 3 or 4
+//     slots are too few --, plane chunks as two 64 KB tiles or five 32 KB half tiles), nor with spinning on test_wait
+//     instead of try_wait, nor with half the MMAs (a value-plane-only variant that counts the valid calls from the
+//     missing ones: 2.08 ms without its scan);
 //   * on top of it, a stage's MMAs cost the ISSUING THREAD ~530 cycles + ~48 per MMA, so round 1's four issuers (one
 //     per accumulator, each on every stage) ran at 650 cycles per stage = 2.83 ms.  Round 2, mxf4: one issuer per
 //     stage in flight (three, one per A buffer), each issuing all 8 MMAs of its stage: 2.28 ms = 4.4 TB/s of planes,
