@@ -204,6 +204,16 @@ def cpu_baseline(sample_rows: int, threads: int, reference_style: bool = True, r
     return sample_rows * reps / dt, dt
 
 
+def _config(world: int, rows_per_gpu: int) -> dict:
+    """The `config` object of the JSON line: the same in both arms (ours and --impl reference)."""
+    return {"workload": "C2: synthetic pangenome binary matrix 1M markers x 5k genomes per GPU, single "
+                        "--one/--two comparison (2500 vs 2500 genomes)",
+            "markers_per_gpu": rows_per_gpu, "genomes": S, "comparisons": 1, "correction": "bonferroni",
+            "ratio_filter": 0.0, "sort_key": "abs(ratio) desc, name rank",
+            "l2": "inputs larger than L2 (1.28 GB of bit-planes per pass vs 126 MB L2)",
+            "parallelism": f"rows sharded over {world} GPU(s), no data-path collective"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the Haskell binary cannot be built in this
     image: no ghc/stack) on all host cores, same workload/metric.  Each step is one pass over ALL 1,000,000 marker
@@ -235,9 +245,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcount + f64",
         "data": "synthetic",
-        "config": {"workload": "C2: synthetic pangenome binary matrix 1M markers x 5k genomes, single "
-                               "--one/--two comparison (2500 vs 2500 genomes)", "markers_per_step": sample, "genomes": S,
-                   "comparisons": 1, "correction": "bonferroni", "ratio_filter": 0.0},
+        "config": _config(args.gpus, ROWS_PER_GPU),
+        "reference_run": {"markers_per_step": sample, "host_threads": cores, "sampled": sample != ROWS_PER_GPU,
+                          "note": "the CPU arm processes one GPU's share of the job (1M marker rows) per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -788,15 +798,10 @@ def main() -> int:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 popcount + f64", "data": "synthetic",
-            "config": {"workload": "C2: synthetic pangenome binary matrix 1M markers x 5k genomes per GPU, single "
-                                   "--one/--two comparison (2500 vs 2500 genomes)",
-                       "markers_per_gpu": R, "genomes": S, "comparisons": 1, "correction": "bonferroni",
-                       "ratio_filter": 0.0, "sort_key": "abs(ratio) desc, name rank",
-                       "l2": "inputs larger than L2 (1.28 GB of bit-planes per pass vs 126 MB L2)",
-                       "parallelism": f"rows sharded over {world} GPU(s), no data-path collective",
-                       "stage_ms_per_step": {k: stage[k] / args.steps for k in ("count_ms", "test_ms", "order_ms", "total_ms")},
-                       "timed_window": "CUDA events on the stream the runs are enqueued on; ms_per_step >= sum of the "
-                                       "library's own stage events (asserted)"},
+            "config": _config(world, R),
+            "stage_ms_per_step": {k: stage[k] / args.steps for k in ("count_ms", "test_ms", "order_ms", "total_ms")},
+            "timed_window": "CUDA events on the stream the runs are enqueued on; ms_per_step >= sum of the library's own "
+                            "stage events (asserted)",
             "roofline": {"bound": "hbm", "kernel": "count_popc_kernel (K1)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
