@@ -43,6 +43,9 @@ struct MultiState {
     int64_t last_upload_host_rows = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // one copy stream (+ event) per shard on the root device: the peer copies from different GPUs run side by side
+    std::vector<cudaStream_t> copy_st;
+    std::vector<cudaEvent_t> copy_ev;
     // staged copies of the other devices' ordered results, and the merged rows, on the root device
     struct Cols { void *p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; size_t cap = 0; };
     std::vector<Cols> staged;
@@ -213,6 +216,12 @@ MultiState *create(const int *device_ids, int n, std::string *err) {
     cudaError_t e = cudaSetDevice(m->root);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->ev[i]);
+    m->copy_st.assign(size_t(n), nullptr);
+    m->copy_ev.assign(size_t(n), nullptr);
+    for (int i = 1; i < n && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&m->copy_st[size_t(i)], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->copy_ev[size_t(i)], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) return bail(m, std::string("feht_create_multi: ") + cudaGetErrorString(e));
     // direct peer access root <- others makes cudaMemcpyPeerAsync a single NVLink transfer (without it the runtime
     // stages through the host, still correct)
@@ -241,6 +250,8 @@ void destroy(MultiState *m) {
     if (m->d_seg) cudaFree(m->d_seg);
     if (m->d_map) cudaFree(m->d_map);
     for (cudaEvent_t e : m->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->copy_ev) if (e) cudaEventDestroy(e);
+    for (cudaStream_t q : m->copy_st) if (q) cudaStreamDestroy(q);
     if (m->st) cudaStreamDestroy(m->st);
     delete m;
 }
@@ -651,9 +662,13 @@ int run(MultiState *m, int correction, double ratio_filter, int sort_key, int64_
             if (m->dev[size_t(d)] != m->root && v.n > 0) {
                 // the shard's ordered columns travel GPU to GPU (the kid's run has finished: feht_run is blocking)
                 if (int r = ensure_cols(m, m->staged[size_t(d)], size_t(v.n))) return r;
+                cudaStream_t cs = m->copy_st[size_t(d)];
+                MCU(m, cudaStreamWaitEvent(cs, m->ev[0], 0));      // after the merge's start mark (and earlier merges)
                 for (int i = 0; i < 8; ++i)
                     MCU(m, cudaMemcpyPeerAsync(m->staged[size_t(d)].p[i], m->root, soa_col(v.res, i), m->dev[size_t(d)],
-                                               size_t(v.n) * kColBytes[i], m->st));
+                                               size_t(v.n) * kColBytes[i], cs));
+                MCU(m, cudaEventRecord(m->copy_ev[size_t(d)], cs));
+                MCU(m, cudaStreamWaitEvent(m->st, m->copy_ev[size_t(d)], 0));
                 v.res = as_soa(m->staged[size_t(d)]);
             }
         }

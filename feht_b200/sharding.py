@@ -102,8 +102,8 @@ def gather_and_merge_device(ctx, comparison: int, sort_key: int = capi.SORT_ABS_
 def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, dst: int = 0,
                                 host_out: dict | None = None, want_device: bool = False, times: dict | None = None):
     """The same exchange for EVERY comparison at once (one process per GPU): each rank hands over the ordered rows of
-    all its comparisons (feht_result_fetch_device with comparison = -1: eight device-to-device copies), eight padded
-    `dist.gather`s move them to rank `dst` over NVLink, and ONE call of feht_merge_shards_device (K5b) merges all
+    all its comparisons (feht_result_fetch_device with comparison = -1: eight device-to-device copies into one packed
+    buffer), ONE `all_gather_into_tensor` moves them over NVLink, and ONE call of feht_merge_shards_device (K5b) merges all
     comparisons and scatters all columns.  Returns (columns, seg_off) on `dst` -- host tensors (into `host_out` when
     given; device tensors with want_device) and the merged per-comparison offsets -- and (None, None) elsewhere."""
     import torch
@@ -130,16 +130,21 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
     dist.all_gather_into_tensor(segs, seg_t)
     segs = segs.cpu().numpy()
     sizes = [int(x) for x in segs[:, -1]]
-    n_max = max(sizes + [1])
-    local = {k: torch.empty(n_max, dtype=getattr(torch, dt), device=dev) for k, dt in DEV_DTYPES.items()}
+    # one packed buffer per rank (the eight columns back to back, n_max rows each) and ONE collective: eight padded
+    # dist.gather calls -- send / recv pairs to rank 0, one tensor after the other -- took 15 ms for 20M rows on 8 GPUs
+    n_max = (max(sizes + [1]) + 15) // 16 * 16
+    widths = {k: torch.empty(0, dtype=getattr(torch, dt)).element_size() for k, dt in DEV_DTYPES.items()}
+    order = sorted(DEV_DTYPES, key=lambda k: -widths[k])          # 8-byte columns first: every column stays aligned
+    offs, o = {}, 0
+    for k in order:
+        offs[k] = o
+        o += widths[k] * n_max
+    pack = torch.empty(o, dtype=torch.uint8, device=dev)
     if sizes[rank]:
-        ctx.fetch_device(-1, {k: v.data_ptr() for k, v in local.items()})
+        ctx.fetch_device(-1, {k: pack.data_ptr() + offs[k] for k in DEV_DTYPES})
     lap("sizes_and_local_copy_ms")
-    gathered = {}
-    for k, v in local.items():
-        lst = [torch.empty_like(v) for _ in range(world)] if rank == dst else None
-        dist.gather(v, lst, dst=dst)
-        gathered[k] = lst
+    everything = torch.empty(world * o, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(everything, pack)
     lap("nccl_gather_ms")
     if rank != dst:
         return None, None
@@ -147,7 +152,8 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
     merged = {k: torch.empty(max(total, 1), dtype=getattr(torch, dt), device=dev) for k, dt in DEV_DTYPES.items()}
     out_seg = np.zeros(n_comps + 1, dtype=np.int64)
     torch.cuda.current_stream().synchronize()
-    shards = [({k: gathered[k][s].data_ptr() for k in DEV_DTYPES}, np.ascontiguousarray(segs[s])) for s in range(world)]
+    shards = [({k: everything.data_ptr() + s * o + offs[k] for k in DEV_DTYPES}, np.ascontiguousarray(segs[s]))
+              for s in range(world)]
     ctx.merge_shards_device(shards, n_comps, {k: v.data_ptr() for k, v in merged.items()}, out_seg, sort_key)
     lap("merge_kernel_ms")
     if want_device:
