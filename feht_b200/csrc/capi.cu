@@ -133,6 +133,7 @@ struct feht_ctx {
     DevBuf<unsigned long long> dd_keys;    // N4 dedup of exact tests (fet.cu): table, owners, waiting list, its length
     DevBuf<uint32_t> dd_owner, dd_count;
     DevBuf<uint2> dd_list;
+    DevBuf<int64_t> merge_dest;            // feht_merge_shards_device: final positions (two-phase K5b)
     DevBuf<unsigned int> snp_digit_flag;   // feht_add_snp_chars: K0 met a literal '0' / '1'
     DevBuf<uint32_t> txt_counts;
     DevBuf<int32_t> txt_starts, txt_name_len;
@@ -605,7 +606,7 @@ extern "C" void feht_destroy(feht_ctx *c) {
     release(c->sw_key_a); release(c->sw_key_b); release(c->sw_val_a); release(c->sw_val_b);
     release(c->sw_control); release(c->sw_oa); release(c->sw_coop);
     release(c->live_rows); release(c->live_count); release(c->snp_digit_flag);
-    release(c->dd_keys); release(c->dd_owner); release(c->dd_count); release(c->dd_list);
+    release(c->dd_keys); release(c->dd_owner); release(c->dd_count); release(c->dd_list); release(c->merge_dest);
     release(c->txt_counts); release(c->txt_starts); release(c->txt_name_len); release(c->txt_flags);
     if (c->d_choose) cudaFree(c->d_choose);
     for (int k = 0; k < 2; ++k)
@@ -1912,12 +1913,14 @@ extern "C" int feht_merge_shards_device(feht_ctx *c, int n_shards, int64_t n_com
     if (int rc = use_device(c)) return rc;
     DevBuf<int64_t> dseg;
     CU(c, ensure(dseg, hseg.size()));
+    CU(c, ensure(c->merge_dest, size_t(total) + merge_bounds_words(total, n_shards)));   // positions, then block bounds
     CU(c, cudaMemcpyAsync(dseg.p, hseg.data(), hseg.size() * 8, cudaMemcpyHostToDevice, c->st));
     for (int i = 0; i < n_shards; ++i) views[size_t(i)].d_seg_off = dseg.p + per * size_t(i);
     const ResultSoA o{const_cast<int64_t *>(out->row), const_cast<int32_t *>(out->name_rank), const_cast<int32_t *>(out->goa),
                       const_cast<int32_t *>(out->gob), const_cast<int32_t *>(out->gta), const_cast<int32_t *>(out->gtb),
                       const_cast<double *>(out->p), const_cast<double *>(out->ratio)};
-    cudaError_t e = launch_merge_all(n_shards, int(n_comparisons), sort_key, views.data(), dseg.p + per * size_t(n_shards), o, 0, c->st);
+    cudaError_t e = launch_merge_all(n_shards, int(n_comparisons), sort_key, views.data(), dseg.p + per * size_t(n_shards), o, 0,
+                                     c->merge_dest.p, c->merge_dest.p + total, c->st);
     cudaError_t e2 = cudaStreamSynchronize(c->st);
     release(dseg);
     CU(c, e);

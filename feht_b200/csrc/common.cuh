@@ -293,8 +293,13 @@ struct MergeShardView {
     const int64_t *d_map_local = nullptr, *d_map_global = nullptr;
     int n_map = 0, mult = 1;
 };
+// d_dest_scratch: optional int64 [sum of the shards' rows]; with it, jobs of more than two shards rank first and then
+// place the rows tile by tile with coalesced writes.
+// d_bounds_scratch: int64 [merge_bounds_words(rows, shards)]: where every 256-row block starts in the other shards.
+size_t merge_bounds_words(int64_t total_rows, int n_shards);
 cudaError_t launch_merge_all(int n_shards, int n_comps, int sort_key, const MergeShardView *shards,
-                             const int64_t *d_out_seg_off, const ResultSoA &out, int64_t row_base, cudaStream_t st);
+                             const int64_t *d_out_seg_off, const ResultSoA &out, int64_t row_base, int64_t *d_dest_scratch,
+                             int64_t *d_bounds_scratch, cudaStream_t st);
 
 // choose_table.cpp
 const std::vector<double> &host_choose_table();

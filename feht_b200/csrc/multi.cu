@@ -54,6 +54,8 @@ struct MultiState {
     size_t d_seg_cap = 0;
     int64_t *d_map = nullptr;
     size_t d_map_cap = 0;
+    int64_t *d_dest = nullptr;   // final positions of all rows (two-phase K5b)
+    size_t d_dest_cap = 0;
     std::vector<int64_t> seg_off;
     int64_t n_total = 0;
     bool has_results = false;
@@ -249,6 +251,7 @@ void destroy(MultiState *m) {
     for (void *p : m->merged.p) if (p) cudaFree(p);
     if (m->d_seg) cudaFree(m->d_seg);
     if (m->d_map) cudaFree(m->d_map);
+    if (m->d_dest) cudaFree(m->d_dest);
     for (cudaEvent_t e : m->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : m->copy_ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t q : m->copy_st) if (q) cudaStreamDestroy(q);
@@ -673,8 +676,15 @@ int run(MultiState *m, int correction, double ratio_filter, int sort_key, int64_
             }
         }
         if (int r = ensure_cols(m, m->merged, size_t(total))) return r;
+        const size_t need = size_t(total) + merge_bounds_words(total, nd);   // positions, then block bounds
+        if (need > m->d_dest_cap) {
+            if (m->d_dest) cudaFree(m->d_dest);
+            m->d_dest = nullptr;
+            MCU(m, cudaMalloc(&m->d_dest, (need + need / 8) * 8));
+            m->d_dest_cap = need + need / 8;
+        }
         MCU(m, launch_merge_all(nd, int(n_comps), sort_key, views.data(), m->d_seg + per * size_t(nd), as_soa(m->merged),
-                                m->row_base, m->st));
+                                m->row_base, m->d_dest, m->d_dest + total, m->st));
         m->tm[4] += 1;
     }
     MCU(m, cudaEventRecord(m->ev[1], m->st));

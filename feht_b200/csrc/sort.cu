@@ -598,109 +598,209 @@ struct MergeAllArgs {
     long long flat_off[kMaxShards + 1];
     const long long *out_seg_off; // device, [n_comps + 1]
     ResultSoA out;
+    long long *dest;              // scratch [total rows]: final position of every row, in shard-flat order (two-phase
+                                  // variant: rank, then a tile-wise gather with coalesced writes); null = scatter at once
 };
 
-__global__ void __launch_bounds__(256) merge_all_kernel(const __grid_constant__ MergeAllArgs A) {
+// a shard's local marker row -> the job's global row (shards filled by several uploads: segment table)
+__device__ __forceinline__ long long merge_global_row(const MergeAllArgs &A, const MergeAllShard &S, long long row) {
+    if (!S.map_local) return row;
+    const long long unit = row / S.mult;
+    int a = 0, b = S.n_map;
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (__ldg(S.map_local + mid) <= unit) a = mid; else b = mid;
+    }
+    return A.row_base + (__ldg(S.map_global + a) + (unit - __ldg(S.map_local + a))) * S.mult + (row - unit * S.mult);
+}
+
+// number of rows e of segment c of shard t with (key_e, rank_e, t) < (kb, rk, s), searched in [lo, hi)
+__device__ __forceinline__ long long merge_lower_bound(const MergeAllArgs &A, int t, int s, unsigned long long kb, uint32_t rk,
+                                                       long long lo, long long hi) {
+    const MergeAllShard &T = A.sh[t];
+    const double *tk = A.sort_key == FEHT_SORT_PVALUE_ASC ? T.p : T.ratio;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        const unsigned long long ke = merge_key_bits(__ldg(tk + mid), A.sort_key);
+        bool before = ke < kb;
+        if (ke == kb) {
+            const uint32_t re = uint32_t(__ldg(T.rank + mid));
+            before = re < rk || (re == rk && t < s);
+        }
+        if (before) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// shard, index in the shard and comparison of flat row g
+__device__ __forceinline__ void merge_locate(const MergeAllArgs &A, long long g, int &s, long long &i, int &c) {
+    s = 0;
+    while (g >= A.flat_off[s + 1]) ++s;
+    i = g - A.flat_off[s];
+    const long long *so = A.sh[s].seg_off;
+    int lo_c = 0, hi_c = A.n_comps;      // the last c with seg_off[c] <= i
+    while (hi_c - lo_c > 1) {
+        const int mid = (lo_c + hi_c) >> 1;
+        if (__ldg(so + mid) <= i) lo_c = mid; else hi_c = mid;
+    }
+    c = lo_c;
+}
+
+// Level 1: where does the FIRST row of every 256-row block stand in every other shard?  One thread per (block, shard):
+// a full binary search each, for 1/256 of the rows.  The rows of a block are consecutive rows of a sorted segment, so
+// the answers for the block's rows lie between its own entry and the next block's (merge_all_kernel).
+constexpr int kMergeBlock = 256;
+__global__ void __launch_bounds__(256) merge_bounds_kernel(const __grid_constant__ MergeAllArgs A, long long *__restrict__ bounds) {
     const long long total = A.flat_off[A.n_shards];
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        int s = 0;
-        while (g >= A.flat_off[s + 1]) ++s;
-        const MergeAllShard &S = A.sh[s];
-        const long long i = g - A.flat_off[s];
-        // comparison of element i: the last c with seg_off[c] <= i
-        int lo_c = 0, hi_c = A.n_comps;
-        while (hi_c - lo_c > 1) {
-            const int mid = (lo_c + hi_c) >> 1;
-            if (__ldg(S.seg_off + mid) <= i) lo_c = mid; else hi_c = mid;
+    const long long n_blocks = (total + kMergeBlock - 1) / kMergeBlock;
+    const long long n_items = n_blocks * A.n_shards;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_items;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long blk = idx / A.n_shards;
+        const int t = int(idx - blk * A.n_shards);
+        int s, c;
+        long long i;
+        merge_locate(A, blk * kMergeBlock, s, i, c);
+        long long b = 0;
+        if (t != s) {
+            const unsigned long long kb = merge_key_bits(A.sort_key == FEHT_SORT_PVALUE_ASC ? A.sh[s].p[i] : A.sh[s].ratio[i], A.sort_key);
+            b = merge_lower_bound(A, t, s, kb, uint32_t(A.sh[s].rank[i]), __ldg(A.sh[t].seg_off + c), __ldg(A.sh[t].seg_off + c + 1));
         }
-        const int c = lo_c;
-        const double kd = A.sort_key == FEHT_SORT_PVALUE_ASC ? S.p[i] : S.ratio[i];
-        const unsigned long long kb = merge_key_bits(kd, A.sort_key);
-        const uint32_t rk = uint32_t(S.rank[i]);
-        long long pos = __ldg(A.out_seg_off + c) + (i - __ldg(S.seg_off + c));
-        // The 32 rows of a warp are consecutive rows of one sorted segment (when they are: the same shard and
-        // comparison in lanes 0 and 31), so their positions in another shard are monotone: lanes 0 and 31 search the
-        // whole segment, the lanes between them only the window those two found (about as many rows as the warp
-        // has, 5-6 steps instead of ~23: a third of the random reads).
-        const unsigned full = 0xffffffffu;
-        const bool whole_warp = __activemask() == full;
-        bool narrow = false;
-        if (whole_warp) {
-            const int s0 = __shfl_sync(full, s, 0), s1 = __shfl_sync(full, s, 31);
-            const int c0 = __shfl_sync(full, c, 0), c1 = __shfl_sync(full, c, 31);
-            narrow = s0 == s1 && c0 == c1;
-        }
-        const int lane = threadIdx.x & 31;
-        for (int t = 0; t < A.n_shards; ++t) {
-            if (t == s) continue;
-            const MergeAllShard &T = A.sh[t];
-            const long long t0 = __ldg(T.seg_off + c);
-            long long lo = t0, hi = __ldg(T.seg_off + c + 1);
-            const double *tk = A.sort_key == FEHT_SORT_PVALUE_ASC ? T.p : T.ratio;
-            if (narrow) {
-                // the two whole-segment searches are done by the WARP: 32 probes per step (a 32-ary search, 4-5 steps
-                // for a million rows instead of ~23 dependent loads on two lanes while thirty wait)
-                long long edge[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const unsigned long long ekb = __shfl_sync(full, kb, e * 31);
-                    const uint32_t erk = __shfl_sync(full, rk, e * 31);
-                    long long a = lo, b = hi;                       // answer in [a, b]
-                    while (b - a > 0) {
-                        // probes at a + (j + 1) * step - 1, j = 0..31, clipped to the range; "before" is monotone
-                        const long long step = (b - a + 31) >> 5;
-                        long long pos = a + (long long)(lane + 1) * step - 1;
-                        const bool in = pos < b;
-                        if (!in) pos = b - 1;
-                        const unsigned long long ke = merge_key_bits(__ldg(tk + pos), A.sort_key);
-                        bool before = ke < ekb;
-                        if (ke == ekb) {
-                            const uint32_t re = uint32_t(__ldg(T.rank + pos));
-                            before = re < erk || (re == erk && t < s);
-                        }
-                        const unsigned bal = __ballot_sync(full, before && in);
-                        const int nb = __popc(bal);                 // probes 0 .. nb - 1 lie before the key
-                        const long long na = a + (long long)nb * step;          // first candidate after probe nb - 1
-                        const long long nbound = min(b, a + (long long)(nb + 1) * step - 1);   // probe nb is not before
-                        a = min(na, b);
-                        b = nb == 32 ? b : max(a, nbound);
-                        if (step == 1) break;
-                    }
-                    edge[e] = a;
-                }
-                lo = edge[0];
-                hi = edge[1];
-                if (lane == 0) hi = lo;
-                if (lane == 31) lo = hi;
+        bounds[idx] = b;
+    }
+}
+
+// Level 2: every row's final position.  A block whose 256 rows (and the next block's first row) belong to one sorted
+// segment searches only the windows level 1 found -- a few hundred rows per other shard, 8-9 steps that stay in L1 --
+// instead of whole segments (~23 dependent L2 round trips per other shard and row: 6.6 ms for 20M rows in 8 shards).
+__global__ void __launch_bounds__(kMergeBlock) merge_all_kernel(const __grid_constant__ MergeAllArgs A, const long long *__restrict__ bounds) {
+    __shared__ long long w_lo[kMaxShards], w_hi[kMaxShards];
+    __shared__ int first_s, first_c, windowed;
+    const long long total = A.flat_off[A.n_shards];
+    const long long n_blocks = (total + kMergeBlock - 1) / kMergeBlock;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const long long g = blk * kMergeBlock + threadIdx.x;
+        const bool valid = g < total;
+        int s = 0, c = 0;
+        long long i = 0;
+        if (valid) merge_locate(A, g, s, i, c);
+        if (threadIdx.x == 0) { first_s = s; first_c = c; }
+        __syncthreads();
+        const bool same = !valid || (s == first_s && c == first_c);
+        const int uniform = __syncthreads_and(same);
+        if (threadIdx.x == 0) windowed = uniform;
+        if (uniform && threadIdx.x < A.n_shards) {
+            const int t = threadIdx.x;
+            // window of shard t: [this block's entry, the next block's entry] when the next block starts in the same
+            // segment, else up to the end of shard t's segment
+            const long long g_next = (blk + 1) * kMergeBlock;
+            bool next_same = false;
+            if (g_next < total && g_next < A.flat_off[first_s + 1]) {
+                const long long i_next = g_next - A.flat_off[first_s];
+                next_same = i_next < __ldg(A.sh[first_s].seg_off + first_c + 1);
             }
+            w_lo[t] = bounds[blk * A.n_shards + t];
+            w_hi[t] = next_same ? bounds[(blk + 1) * A.n_shards + t] : __ldg(A.sh[t].seg_off + first_c + 1);
+        }
+        __syncthreads();
+        if (valid) {
+            const MergeAllShard &S = A.sh[s];
+            const double kd = A.sort_key == FEHT_SORT_PVALUE_ASC ? S.p[i] : S.ratio[i];
+            const unsigned long long kb = merge_key_bits(kd, A.sort_key);
+            const uint32_t rk = uint32_t(S.rank[i]);
+            long long pos = __ldg(A.out_seg_off + c) + (i - __ldg(S.seg_off + c));
+            for (int t = 0; t < A.n_shards; ++t) {
+                if (t == s) continue;
+                const long long t0 = __ldg(A.sh[t].seg_off + c);
+                const long long lo = windowed ? w_lo[t] : t0;
+                const long long hi = windowed ? w_hi[t] : __ldg(A.sh[t].seg_off + c + 1);
+                pos += merge_lower_bound(A, t, s, kb, rk, lo, hi) - t0;
+            }
+            if (A.dest) {   // two-phase: the columns move in merge_place_kernel
+                A.dest[g] = pos;
+            } else {
+                A.out.row[pos] = merge_global_row(A, S, S.row[i]);
+                A.out.rank[pos] = int32_t(rk);
+                A.out.goa[pos] = S.goa[i]; A.out.gob[pos] = S.gob[i]; A.out.gta[pos] = S.gta[i]; A.out.gtb[pos] = S.gtb[i];
+                A.out.p[pos] = S.p[i];
+                A.out.ratio[pos] = S.ratio[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Phase 2 of the two-phase variant.  Scattering row by row writes every output sector 1/n_shards full (a warp's 32
+// consecutive rows of one shard land n_shards apart): at 8 shards the one-kernel variant spent 6.6 ms on 20M rows.
+// Here a CTA owns a tile of kPlaceTile consecutive OUTPUT positions.  A shard's positions increase along the shard, so
+// the rows that fall into the tile are one contiguous run per shard (two binary searches on `dest` per shard and
+// tile); the runs are read with consecutive threads on consecutive rows, parked in shared memory at (position - tile
+// start), and written out with consecutive threads on consecutive positions.
+constexpr int kPlaceTile = 1024;
+__global__ void __launch_bounds__(256) merge_place_kernel(const __grid_constant__ MergeAllArgs A) {
+    __shared__ long long s_row[kPlaceTile];
+    __shared__ double s_p[kPlaceTile], s_ratio[kPlaceTile];
+    __shared__ int32_t s_rank[kPlaceTile], s_goa[kPlaceTile], s_gob[kPlaceTile], s_gta[kPlaceTile], s_gtb[kPlaceTile];
+    __shared__ long long run_lo[kMaxShards];
+    __shared__ int run_cum[kMaxShards + 1];
+    const long long total = A.flat_off[A.n_shards];
+    const long long n_tiles = (total + kPlaceTile - 1) / kPlaceTile;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long q0 = tile * kPlaceTile, q1 = min(total, q0 + kPlaceTile);
+        // the run of every shard inside [q0, q1): first row with dest >= q0 .. first row with dest >= q1
+        if (threadIdx.x < 2 * A.n_shards) {
+            const int sh = threadIdx.x >> 1;
+            const long long want = (threadIdx.x & 1) ? q1 : q0;
+            const long long *d = A.dest + A.flat_off[sh];
+            long long lo = 0, hi = A.flat_off[sh + 1] - A.flat_off[sh];
             while (lo < hi) {
                 const long long mid = (lo + hi) >> 1;
-                const unsigned long long ke = merge_key_bits(__ldg(tk + mid), A.sort_key);
-                bool before = ke < kb;
-                if (ke == kb) {
-                    const uint32_t re = uint32_t(__ldg(T.rank + mid));
-                    before = re < rk || (re == rk && t < s);
-                }
-                if (before) lo = mid + 1; else hi = mid;
+                if (__ldg(d + mid) < want) lo = mid + 1; else hi = mid;
             }
-            pos += lo - t0;
+            if (threadIdx.x & 1) s_row[sh] = lo; else run_lo[sh] = lo;     // (s_row doubles as scratch for the run ends)
         }
-        long long row = S.row[i];
-        if (S.map_local) {
-            const long long unit = row / S.mult;
-            int a = 0, b = S.n_map;
-            while (b - a > 1) {
-                const int mid = (a + b) >> 1;
-                if (__ldg(S.map_local + mid) <= unit) a = mid; else b = mid;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0;
+            for (int sh = 0; sh < A.n_shards; ++sh) { run_cum[sh] = cum; cum += int(s_row[sh] - run_lo[sh]); }
+            run_cum[A.n_shards] = cum;
+        }
+        __syncthreads();
+        const int n_in = run_cum[A.n_shards];      // == q1 - q0
+        long long my_row[kPlaceTile / 256];
+        int my_slot[kPlaceTile / 256];
+#pragma unroll
+        for (int it = 0; it < kPlaceTile / 256; ++it) {
+            const int j = it * 256 + threadIdx.x;
+            my_slot[it] = -1;
+            if (j < n_in) {
+                int sh = 0;
+                while (j >= run_cum[sh + 1]) ++sh;
+                const MergeAllShard &S = A.sh[sh];
+                const long long i = run_lo[sh] + (j - run_cum[sh]);
+                my_slot[it] = int(A.dest[A.flat_off[sh] + i] - q0);
+                my_row[it] = merge_global_row(A, S, S.row[i]);
+                const int k = my_slot[it];
+                s_rank[k] = S.rank[i];
+                s_goa[k] = S.goa[i]; s_gob[k] = S.gob[i]; s_gta[k] = S.gta[i]; s_gtb[k] = S.gtb[i];
+                s_p[k] = S.p[i];
+                s_ratio[k] = S.ratio[i];
             }
-            row = A.row_base + (__ldg(S.map_global + a) + (unit - __ldg(S.map_local + a))) * S.mult + (row - unit * S.mult);
         }
-        A.out.row[pos] = row;
-        A.out.rank[pos] = int32_t(rk);
-        A.out.goa[pos] = S.goa[i]; A.out.gob[pos] = S.gob[i]; A.out.gta[pos] = S.gta[i]; A.out.gtb[pos] = S.gtb[i];
-        A.out.p[pos] = S.p[i];
-        A.out.ratio[pos] = S.ratio[i];
+        __syncthreads();    // run ends (kept in s_row) are consumed: the rows may go in
+#pragma unroll
+        for (int it = 0; it < kPlaceTile / 256; ++it)
+            if (my_slot[it] >= 0) s_row[my_slot[it]] = my_row[it];
+        __syncthreads();
+        for (int k = threadIdx.x; k < int(q1 - q0); k += 256) {
+            const long long q = q0 + k;
+            A.out.row[q] = s_row[k];
+            A.out.rank[q] = s_rank[k];
+            A.out.goa[q] = s_goa[k]; A.out.gob[q] = s_gob[k]; A.out.gta[q] = s_gta[k]; A.out.gtb[q] = s_gtb[k];
+            A.out.p[q] = s_p[k];
+            A.out.ratio[q] = s_ratio[k];
+        }
+        __syncthreads();
     }
 }
 
@@ -712,6 +812,10 @@ inline int blocks_for(int64_t n, int per) {
 }
 
 }  // namespace
+
+size_t merge_bounds_words(int64_t total_rows, int n_shards) {
+    return size_t((total_rows + kMergeBlock - 1) / kMergeBlock + 1) * size_t(n_shards > 0 ? n_shards : 1);
+}
 
 size_t sort_status_words(int64_t n) { return size_t((n + kTile - 1) / kTile) * 256; }
 
@@ -876,7 +980,9 @@ cudaError_t launch_merge_rank(int n_shards, const int64_t *n, const double *cons
 }
 
 cudaError_t launch_merge_all(int n_shards, int n_comps, int sort_key, const MergeShardView *shards,
-                             const int64_t *d_out_seg_off, const ResultSoA &out, int64_t row_base, cudaStream_t st) {
+                             const int64_t *d_out_seg_off, const ResultSoA &out, int64_t row_base, int64_t *d_dest_scratch,
+                             int64_t *d_bounds_scratch, cudaStream_t st) {
+    if (!d_bounds_scratch) return cudaErrorInvalidValue;
     if (n_shards < 0 || n_shards > kMaxShards) return cudaErrorInvalidValue;
     MergeAllArgs a{};
     a.n_shards = n_shards;
@@ -902,7 +1008,19 @@ cudaError_t launch_merge_all(int n_shards, int n_comps, int sort_key, const Merg
     a.out_seg_off = reinterpret_cast<const long long *>(d_out_seg_off);
     a.out = out;
     if (off == 0 || n_comps == 0) return cudaSuccess;
-    merge_all_kernel<<<blocks_for(off, 256), 256, 0, st>>>(a);
+    // small outputs and two shards (one kernel is faster there: 0.70 against 1.00 ms for 20M rows): scatter at once; otherwise rank, then place
+    a.dest = (d_dest_scratch && n_shards > 2 && off >= (1 << 16)) ? reinterpret_cast<long long *>(d_dest_scratch) : nullptr;
+    const int64_t n_blocks = (off + kMergeBlock - 1) / kMergeBlock;
+    long long *d_bounds = reinterpret_cast<long long *>(d_bounds_scratch);
+    merge_bounds_kernel<<<blocks_for(n_blocks * n_shards, 256), 256, 0, st>>>(a, d_bounds);
+    int64_t gb = n_blocks;
+    if (gb > int64_t(sm_count()) * 16) gb = int64_t(sm_count()) * 16;
+    merge_all_kernel<<<int(gb), kMergeBlock, 0, st>>>(a, d_bounds);
+    if (a.dest) {
+        int64_t tiles = (off + kPlaceTile - 1) / kPlaceTile;
+        if (tiles > int64_t(sm_count()) * 8) tiles = int64_t(sm_count()) * 8;
+        merge_place_kernel<<<int(tiles), 256, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
