@@ -544,7 +544,7 @@ int add_packed_common(feht_ctx *c, const uint64_t *const *src_planes, const int 
 }  // namespace
 
 // =================================================================================== context ==
-extern "C" const char *feht_version(void) { return "feht_b200 0.2 (sm_100a; K0 pack, K1 popc, K2 i8 tcgen05 gemm, K3 fet, K4 sort)"; }
+extern "C" const char *feht_version(void) { return "feht_b200 0.3 (sm_100a; K0 pack, K1 popc, K2 tcgen05 gemm i8/mxf4, K3 fet, K4 sort, K5b merge; multi-device)"; }
 
 extern "C" int feht_create(feht_ctx **out, int device) {
     if (!out) return fail(nullptr, FEHT_E_INVALID, "out is null");
