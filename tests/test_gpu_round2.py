@@ -499,3 +499,40 @@ def test_config5_shard_block_of_5k_rows_24_comparisons(ctx):
         n, exact, chi_n = check_block_against_oracle(ctx, sp_o, False, comps, first + 600_000, 5_000, TOTAL, 1, rf)
         assert n == 5_000 * len(comps)
     assert ctx.result_count(0) > 0
+
+
+def test_multi_device_edge_cases(cuda_lib):
+    """Fewer rows than shards (empty shards), no rows, no comparisons, a window on a multi-device handle, one device
+    listed once (a 1-shard "multi" handle), and an invalid device id."""
+    rng = np.random.default_rng(83)
+    S = 90
+    cells = _random_chars(rng, 2, S)
+    g1, g2 = np.arange(0, 40), np.arange(40, 90)
+    with capi.Context(0) as one, capi.Context([0, 0, 0]) as many, capi.Context([0]) as single:
+        for c in (one, many, single):
+            c.set_samples(S)
+            c.run()                                  # nothing to do
+            assert c.result_total() == 0
+            c.add_comparison(g1, g2)
+            c.run()                                  # no rows
+            assert c.result_total() == 0 and c.result_count(0) == 0
+            c.add_rows_chars(cells)                  # 2 rows over 3 shards: one shard stays empty
+            c.add_category((np.arange(S) % 3).astype(np.int32), 3)
+            c.run(capi.CORRECTION_BONFERRONI, 0.0)
+        assert many.num_devices == 3 and single.num_devices == 1
+        _same_results(one, many, 7)
+        _same_results(one, single, 7)
+        for c in (one, many):
+            c.set_comparison_window(2, 3)
+            c.run(capi.CORRECTION_BONFERRONI, 0.0)
+            assert c.result_total() == 3 * 2
+        _same_results(one, many, 7)
+        for c in (one, many):
+            c.clear_comparisons()
+            c.set_comparison_window(0, -1)
+            c.run()
+            assert c.result_total() == 0 and c.num_comparisons == 0
+    with pytest.raises(capi.FehtError):
+        capi.Context([0, 99])
+    with pytest.raises(capi.FehtError):
+        capi.Context([])
