@@ -267,6 +267,11 @@ constexpr size_t kHostPackBufWords = size_t(4) << 17;   // 4 MB of 64-bit words
 constexpr size_t kHostPackMinBytes = size_t(64) << 20;  // smaller uploads are not worth waking the cores for
 // AUTO engine: categories go to the GEMM from this many pair-slots on (measured crossover)
 constexpr int kGemmAutoMinSlots = 8;
+// ... and from 4 pair-slots on for matrices of at least this many rows: K2 streams the planes at ~4.1 TB/s whatever the
+// number of value columns (<= 64), K1 at 4.4 TB/s for two pair-slots but 2.6 TB/s for three or four (16 count streams)
+// and 1.7 TB/s for six (profiles/README.md round 2, c2cat3 .. c2cat12)
+constexpr int kGemmAutoMinSlotsLarge = 4;
+constexpr int64_t kGemmAutoLargeRows = 16384;
 constexpr bool kGemmAutoFp4 = true;   // 1.37x the int8 flavour on C4 / C5, bit-identical counts (profiles/README.md r1j)
 
 // Upload `total` bytes from host in pieces chosen by `next_piece` and hand each staged piece to
@@ -1444,7 +1449,8 @@ int run_impl(feht_ctx *c, int correction, double ratio_filter, int sort_key, int
         if (n_cat_slots == 0) return fail(c, FEHT_E_INVALID, "the GEMM counting engine needs a category (feht_add_category)");
         use_gemm = true;
     } else if (c->engine == FEHT_ENGINE_AUTO) {
-        use_gemm = c->snp != 1 && n_cat_slots >= kGemmAutoMinSlots;
+        use_gemm = c->snp != 1 && (n_cat_slots >= kGemmAutoMinSlots ||
+                                   (n_cat_slots >= kGemmAutoMinSlotsLarge && R >= kGemmAutoLargeRows));
     }
     if (use_gemm && f8 && !(c->gemm_ready && c->gemm_f8)) {
         // ---- e5m2 flavour: columns, pass descriptors and baked B blocks
