@@ -442,11 +442,15 @@ def run_config(name, cfg, capi, sharding, torch, dist, world, rank, local_rank, 
             npad_tot = sum(-(-min(64, npad - 64 * q) // 16) * 16 for q in range(passes))
             ops = 2.0 * local_units * (-(-S // 128) * 128) * npad_tot * 2
             pops = ops / (local_count_ms * 1e-3) / 1e15
-            roofs.append({"kernel": "K2 tcgen05 GEMM counts", "bound": "tensor", "achieved": pops, "peak": 4.5,
-                          "unit": "POP/s (int8-equivalent MACs x 2, both planes, N padded to 16)", "frac": pops / 4.5,
-                          "peak_source": "nominal dense int8 4.5 POP/s (no measured int8 figure)",
+            fp4 = int(t["engine"]) == 3
+            tpeak = 9.0 if fp4 else 4.5
+            roofs.append({"kernel": "K2 tcgen05 GEMM counts (" + ("kind::mxf4" if fp4 else "kind::i8 / f8f6f4") + ")",
+                          "bound": "tensor", "achieved": pops, "peak": tpeak,
+                          "unit": "POP/s (MACs x 2 of both planes, N padded to 16)", "frac": pops / tpeak,
+                          "peak_source": "nominal dense " + ("fp4 9" if fp4 else "int8 / fp8 4.5") + " POP/s (no measured figure for this type)",
+                          "frac_of_int8_nominal_4.5": pops / 4.5,
                           "frac_of_2x_measured_bf16": pops / (2 * bf16_burst / 1e3),
-                          "tensor_pipe_pct_ncu": (ncu.get("k2") or {}).get("tensor_pipe_pct")})
+                          "tensor_pipe_pct_ncu": (ncu.get("k2" if fp4 else "k2_i8") or {}).get("tensor_pipe_pct")})
         n_out = ctx.result_total()
         if n_out > 0 and acc["order_ms"] > 0:
             local_order_ms = acc["order_ms"] / steps
