@@ -759,12 +759,13 @@ def main() -> int:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v_all, dt_all = cpu_baseline(args.cpu_sample_rows, cores, reps=1)
-        one_rows = max(2000, args.cpu_sample_rows // 20)
+        reps = 4     # ~16-20 core-seconds of CPU work in all
+        v_all, dt_all = cpu_baseline(args.cpu_sample_rows, cores, reps=reps)
+        one_rows = max(2000, args.cpu_sample_rows // 4)
         v_one, dt_one = cpu_baseline(one_rows, 1, reps=1)
         cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
                "single_thread_value": v_one,
-               "sample": f"{args.cpu_sample_rows} of the 1,000,000 marker rows (same generator, same comparison), one pass, "
+               "sample": f"{args.cpu_sample_rows} of the 1,000,000 marker rows (same generator, same comparison), {reps} passes, "
                          f"oracle C port of the reference algorithm row-sharded over {cores} threads "
                          f"({dt_all:.2f} s wall = {dt_all * cores:.0f} core-seconds); single-thread figure on "
                          f"{one_rows} rows ({dt_one:.2f} s) -- the real feht binary is single-threaded and could not "
