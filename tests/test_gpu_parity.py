@@ -30,7 +30,10 @@ def _random_chars(rng, n_rows, n_samples, p_missing=0.05, ragged=False):
 def _check_against_oracle(ctx, rows, comps, correction, ratio_filter, name_rank=None, bonf_n=None):
     """rows: 2-D uint8 or list of bytes as held by the reference host; comps: list of (g1, g2)."""
     n_rows = len(rows)
-    for ci, (g1, g2) in enumerate(comps):
+    for ci, pair in enumerate(comps):
+        if pair is None:      # not part of this run (comparison window)
+            continue
+        g1, g2 = pair
         want = oracle.run_comparison(rows, g1, g2, correction=correction,
                                      bonferroni_n=n_rows if bonf_n is None else bonf_n)
         order = oracle.filter_and_order(want["ratio"], name_rank, ratio_filter)
@@ -1230,6 +1233,8 @@ def test_randomised_shapes_against_oracle(cuda_lib):
     for case in range(int(os.environ.get("FEHT_FUZZ_CASES", "40"))):
         S = int(rng.choice([1, 2, 7, 63, 64, 65, 127, 128, 129, int(rng.integers(1, 301))]))
         R = int(rng.choice([1, 2, 31, 32, 33, int(rng.integers(1, 501))]))
+        if rng.random() < 0.15:      # table totals past 1000 (chi-square branch), several tiles of every kernel
+            S, R = int(rng.integers(1000, 2300)), int(rng.integers(1000, 5000))
         snp = bool(rng.random() < 0.3)
         if snp:
             alphabet = np.frombuffer(b"ACGTacgt-N", dtype=np.uint8)
@@ -1264,7 +1269,10 @@ def test_randomised_shapes_against_oracle(cuda_lib):
         rank = rng.permutation(n_marker).astype(np.int32) if rng.random() < 0.5 else None
         correction = int(rng.integers(0, 2))
         rf = float(rng.choice([0.0, 0.0, 0.1, 0.34, 1.0]))
-        with capi.Context(0) as c:
+        # one device, or the multi-device handle with two / three shards (on the same GPU when the box has one)
+        devices = [0, [0, 0], [0, 0, 0]][int(rng.choice([0, 0, 1, 2]))]
+        windowed = len(comps) >= 2 and rng.random() < 0.25
+        with capi.Context(devices) as c:
             c.set_samples(S)
             if snp:
                 c.add_snp_chars(sites, rank)
@@ -1278,9 +1286,22 @@ def test_randomised_shapes_against_oracle(cuda_lib):
                 for g1, g2 in comps:
                     c.add_comparison(g1, g2)
             assert c.num_comparisons == len(comps), case
-            c.run(correction, rf)
+            what = (f"case {case}: S={S} R={R} snp={snp} cat={use_cat} rf={rf} corr={correction} devices={devices} "
+                    f"windowed={windowed} rank={'yes' if rank is not None else 'no'}")
             try:
-                _check_against_oracle(c, cells, comps, correction, rf, rank)
+                if windowed:
+                    # the comparisons in two windows (feht_set_comparison_window): each holds its own comparisons only
+                    h = int(rng.integers(1, len(comps)))
+                    for w0, wn in ((0, h), (h, len(comps) - h)):
+                        c.set_comparison_window(w0, wn)
+                        c.run(correction, rf)
+                        inside = [comps[ci] if w0 <= ci < w0 + wn else None for ci in range(len(comps))]
+                        for ci, pair in enumerate(inside):
+                            if pair is None:
+                                assert len(c.fetch(ci)["row"]) == 0, (ci, "outside the window")
+                        _check_against_oracle(c, cells, inside, correction, rf, rank)
+                else:
+                    c.run(correction, rf)
+                    _check_against_oracle(c, cells, comps, correction, rf, rank)
             except AssertionError as e:
-                raise AssertionError(f"case {case}: S={S} R={R} snp={snp} cat={use_cat} rf={rf} corr={correction} "
-                                     f"rank={'yes' if rank is not None else 'no'}: {e}") from e
+                raise AssertionError(f"{what}: {e}") from e
