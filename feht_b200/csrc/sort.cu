@@ -509,6 +509,232 @@ __global__ void __launch_bounds__(kCoopThreads, 1) coop_sort_kernel(const __grid
     if (cta == 0 && tid == 0) *A.sel = uint32_t(cur);
 }
 
+// Multi-chunk variant with TWO 512-thread CTAs per SM (chunks of up to 4096 survivors): the phases of a chunk -- load,
+// rank, stage, write -- are separated by CTA barriers, and with one 1024-thread CTA per SM nothing else ran while a
+// phase waited on memory (ncu r3g: issue active 40%, stalls spread over global loads and the barrier).  Two CTAs
+// interleave their phases.  Same algorithm and exchange as coop_sort_kernel<true>; FEHT_SORT_MULTI=1024 selects that one.
+constexpr int kM2Threads = 512;
+constexpr int kM2Warps = kM2Threads / 32;
+constexpr int kM2Cap = kM2Threads * kCoopItems;   // 4096 items per chunk
+constexpr size_t kM2DynSmem = size_t(kM2Cap) * (8 + 4 + 1);
+
+__global__ void __launch_bounds__(kM2Threads, 2) coop_sort_multi2_kernel(const __grid_constant__ CoopArgs A) {
+    __shared__ __align__(16) unsigned int cnt[kM2Warps][256];   // per-warp digit counters; then 8 x {before, total} x 256
+    __shared__ unsigned int lstart[256], goff[256], run_off[256];
+    __shared__ unsigned int wsum[8];
+    extern __shared__ __align__(16) unsigned char dyn[];
+    unsigned long long *stage_k = reinterpret_cast<unsigned long long *>(dyn);
+    uint32_t *stage_v = reinterpret_cast<uint32_t *>(dyn + size_t(kM2Cap) * 8);
+    unsigned char *stage_d = dyn + size_t(kM2Cap) * 12;
+    unsigned int(*part)[256] = cnt;        // [0..7] before, [8..15] total
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int n_chunks = A.chunks;
+    const int64_t cta_base = int64_t(cta) * A.chunk * n_chunks;
+    const int rounds = A.rounds;
+    const int wbase = wid * 32 * rounds;
+    uint32_t oa[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) oa[j] = A.or_and[j];
+    unsigned todo = 0;
+#pragma unroll
+    for (int cand = 0; cand < 16; ++cand) {
+        const int w = cand < 4 ? 0 : (cand < 8 ? 1 : (cand < 12 ? 2 : 3));
+        if (((((oa[w] ^ oa[4 + w]) >> (8 * (cand & 3))) & 255u) != 0u) && !(cand < 4 && A.rank_presorted))
+            todo |= 1u << cand;
+    }
+    int cur = 0;
+    unsigned target = 0;
+
+    while (todo) {
+        const int cand = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int src = (cand >= 4 && cand < 12) ? 0 : 1;
+        const int shift = src == 0 ? 8 * (cand - 4) : 8 * (cand & 3);
+        const uint32_t *word = cand < 4 ? A.r_rank : A.r_comp;
+        const int wstride = cand < 4 ? kRankStride : 1;
+
+        const unsigned long long *kin = A.key[cur];
+        const uint32_t *vin = A.val[cur];
+        unsigned long long *kout = A.key[cur ^ 1];
+        uint32_t *vout = A.val[cur ^ 1];
+
+        // sweep 1: digit counts of the CTA's whole range
+        for (int j = tid; j < kM2Warps * 256; j += kM2Threads) (&cnt[0][0])[j] = 0;
+        __syncthreads();
+        {
+            const int64_t lo = cta_base, hi = min(A.n, cta_base + int64_t(A.chunk) * n_chunks);
+            if (src == 0) {
+                for (int64_t i0 = lo + tid; i0 < hi; i0 += 8 * kM2Threads) {
+                    unsigned long long kk[8];   // eight keys in flight per thread
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t i = i0 + int64_t(u) * kM2Threads;
+                        kk[u] = i < hi ? __ldcg(kin + i) : 0ull;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (i0 + int64_t(u) * kM2Threads < hi) atomicAdd(&cnt[wid][uint32_t(kk[u] >> shift) & 255u], 1u);
+                }
+            } else {
+                for (int64_t i = lo + tid; i < hi; i += kM2Threads) {
+                    const uint32_t d = (__ldg(word + size_t(__ldcg(vin + i)) * wstride) >> shift) & 255u;
+                    atomicAdd(&cnt[wid][d], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned run = 0;
+#pragma unroll 8
+            for (int ww = 0; ww < kM2Warps; ++ww) run += cnt[ww][tid];
+            A.hist[size_t(cta) * 256 + tid] = run;
+        }
+        grid_barrier(A.bar, target);
+
+        // a chunk's keys and indices are loaded while the previous chunk is written out (k / v are free once the chunk
+        // is staged): ncu r3o had 7% of the samples on the first use of these loads
+        unsigned long long k[kCoopItems];
+        uint32_t v[kCoopItems];
+        auto load_chunk = [&](int ch) {
+            const int64_t base = cta_base + int64_t(ch) * A.chunk;
+            const int count = int(min(int64_t(A.chunk), max(int64_t(0), A.n - base)));
+#pragma unroll
+            for (int it = 0; it < kCoopItems; ++it) {
+                const int li = wbase + it * 32 + lane;
+                const bool in = it < rounds && li < count;
+                // .cg: the ping-pong buffers are rewritten by other SMs every pass
+                k[it] = in ? __ldcg(kin + base + li) : 0ull;
+                v[it] = in ? __ldcg(vin + base + li) : 0u;
+            }
+        };
+        load_chunk(0);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int64_t base = cta_base + int64_t(ch) * A.chunk;
+            const int count = int(min(int64_t(A.chunk), max(int64_t(0), A.n - base)));
+            __syncthreads();   // the previous chunk's stage and cnt are consumed
+            for (int j = tid; j < kM2Warps * 256; j += kM2Threads) (&cnt[0][0])[j] = 0;
+            uint32_t dr[kCoopItems];   // digit | rank inside the warp's items << 9
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < kCoopItems; ++it) {
+                if (it < rounds) {
+                    const bool in = wbase + it * 32 + lane < count;
+                    const uint32_t d = in ? digit_of(src, shift, k[it], v[it], word, wstride) : 256u;
+                    // MATCH.ANY here: this kernel is bound by issue slots, not by the latency of one warp's chain (the nine
+                    // ballots of peers_of cost 54 of the ~97 instructions of a round: C3 order 1.73 -> 1.58 ms; the
+                    // single-chunk kernel, one latency chain per pass, is 8% faster with the ballots)
+                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    const unsigned lower = peers & ((1u << lane) - 1u);
+                    uint32_t b = 0;
+                    if (d < 256u) b = cnt[wid][d];
+                    __syncwarp();
+                    if (d < 256u && lower == 0) cnt[wid][d] = b + __popc(peers);
+                    __syncwarp();
+                    dr[it] = d | ((b + __popc(lower)) << 9);
+                }
+            }
+            __syncthreads();
+            unsigned my_run = 0;   // threads 0..255: items of digit tid in this chunk
+            if (tid < 256) {
+                unsigned run = 0;
+#pragma unroll 8
+                for (int ww = 0; ww < kM2Warps; ++ww) {
+                    const unsigned c = cnt[ww][tid];
+                    cnt[ww][tid] = run;
+                    run += c;
+                }
+                my_run = run;
+                unsigned inc = run;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) wsum[wid] = inc;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                unsigned wb = 0;
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww)
+                    if (ww < wid) wb += wsum[ww];
+                lstart[tid] = wb + inc - run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < kCoopItems; ++it) {
+                if (it < rounds) {
+                    const uint32_t d = dr[it] & 511u;
+                    if (d < 256u) {
+                        const uint32_t li = lstart[d] + cnt[wid][d] + (dr[it] >> 9);
+                        stage_k[li] = k[it];
+                        stage_v[li] = v[it];
+                        stage_d[li] = (unsigned char)d;
+                    }
+                }
+            }
+            __syncthreads();
+            if (ch + 1 < n_chunks) load_chunk(ch + 1);
+            if (ch == 0) {
+                // counts of every digit in the CTAs before me and in all CTAs (plain counts, published before the grid
+                // barrier): thread = 4 digits x one of 8 slices of the CTA list, eight 128-bit loads in flight
+                const int q = tid & 63, grp = tid >> 6;
+                uint4 before = make_uint4(0, 0, 0, 0), total = make_uint4(0, 0, 0, 0);
+                const uint4 *h4 = reinterpret_cast<const uint4 *>(A.hist);
+                for (int c0 = grp; c0 < G; c0 += 64) {
+                    uint4 h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = c0 + 8 * j;
+                        h[j] = c < G ? __ldcg(h4 + size_t(c) * 64 + q) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = c0 + 8 * j;
+                        total.x += h[j].x; total.y += h[j].y; total.z += h[j].z; total.w += h[j].w;
+                        if (c < cta) { before.x += h[j].x; before.y += h[j].y; before.z += h[j].z; before.w += h[j].w; }
+                    }
+                }
+                *reinterpret_cast<uint4 *>(&part[grp][4 * q]) = before;
+                *reinterpret_cast<uint4 *>(&part[8 + grp][4 * q]) = total;
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned before1 = 0, total1 = 0;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        before1 += part[g][tid];
+                        total1 += part[8 + g][tid];
+                    }
+                    unsigned inc = total1;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    if (lane == 31) wsum[wid] = inc;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    unsigned wb = 0;
+#pragma unroll
+                    for (int ww = 0; ww < 8; ++ww)
+                        if (ww < wid) wb += wsum[ww];
+                    run_off[tid] = wb + inc - total1 + before1;
+                }
+            }
+            if (tid < 256) {
+                goff[tid] = run_off[tid] - lstart[tid];
+                run_off[tid] += my_run;
+            }
+            __syncthreads();
+            for (int li = tid; li < count; li += kM2Threads) {
+                const uint32_t pos = goff[stage_d[li]] + uint32_t(li);
+                kout[pos] = stage_k[li];
+                vout[pos] = stage_v[li];
+            }
+        }
+        cur ^= 1;
+        if (todo) grid_barrier(A.bar, target);
+    }
+    if (cta == 0 && tid == 0) *A.sel = uint32_t(cur);
+}
+
 __global__ void __launch_bounds__(256)
 gather_kernel(const uint32_t *__restrict__ perm_a, const uint32_t *__restrict__ perm_b,
               const uint32_t *__restrict__ sel, int64_t n, int64_t row_base, const SurvivorRec *__restrict__ rec,
@@ -896,12 +1122,19 @@ cudaError_t radix_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec
 
 int64_t coop_sort_capacity(int num_sms) { return int64_t(num_sms) * kCoopCap; }
 int coop_sort_max_grid() { return 160; }   // kSlice * 16 in the kernel
-size_t coop_sort_control_words(int num_sms) { return size_t(num_sms) * 256 + 8; }
+// rows of the [grid][256] count table: the two-CTAs-per-SM multi-chunk kernel runs 2 * num_sms CTAs
+static size_t coop_rows(int num_sms) { return size_t(2) * size_t(num_sms); }
+size_t coop_sort_control_words(int num_sms) { return coop_rows(num_sms) * 256 + 8; }
+
+static bool sort_multi_two_ctas() {
+    static const bool on = [] { const char *e = getenv("FEHT_SORT_MULTI"); return !(e && strcmp(e, "1024") == 0); }();
+    return on;
+}
 
 cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec, const int32_t *r_comp,
                            bool rank_presorted, int num_sms, cudaStream_t st, int *launches) {
     // control block: [grid][256] digit counts, the buffer selector, the barrier counter
-    uint32_t *sel = ws.coop + size_t(num_sms) * 256;
+    uint32_t *sel = ws.coop + coop_rows(num_sms) * 256;
     cudaError_t e = cudaMemsetAsync(sel, 0, 2 * sizeof(uint32_t), st);
     if (e != cudaSuccess || n <= 1) return e;
     CoopArgs a{};
@@ -909,6 +1142,16 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec,
     a.val[0] = ws.val_a; a.val[1] = ws.val_b;
     a.n = n;
     const bool multi = n > coop_sort_capacity(num_sms);
+    bool two = false;
+    if (multi && sort_multi_two_ctas()) {
+        // (the attribute first: the occupancy query counts the dynamic shared memory it is given)
+        e = cudaFuncSetAttribute(coop_sort_multi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kM2DynSmem));
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_sort_multi2_kernel, kM2Threads, kM2DynSmem);
+        if (e != cudaSuccess) return e;
+        two = per_sm >= 2;    // a cooperative launch needs every CTA resident
+    }
     int grid;
     if (!multi) {
         // whole warps per CTA, as few CTAs idle as possible
@@ -918,6 +1161,15 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec,
         a.rounds = int(chunk / kCoopThreads);
         a.chunks = 1;
         grid = int((n + chunk - 1) / chunk);
+    } else if (two) {
+        // two 512-thread CTAs per SM, chunks of up to 4096: same rule, twice the CTAs
+        const int64_t ctas = int64_t(2) * num_sms, cap = ctas * kM2Cap;
+        a.chunks = int((n + cap - 1) / cap);
+        int64_t chunk = (n + ctas * a.chunks - 1) / (ctas * a.chunks);
+        chunk = (chunk + kM2Threads - 1) / kM2Threads * kM2Threads;
+        a.chunk = int(chunk);
+        a.rounds = int(chunk / kM2Threads);
+        grid = int((n + chunk * a.chunks - 1) / (chunk * a.chunks));
     } else {
         // as many chunks per CTA as full-size chunks would need, then the chunk shrunk so that every SM gets work
         // (1.24M keys: 2 chunks of 5120 on 121 CTAs, not 2 x 8192 on 76)
@@ -950,10 +1202,16 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec,
     }
     // (set on every launch: the attribute belongs to the current device's copy of the function, and one process
     // may drive several GPUs)
+    void *args[] = {&a};
+    if (two) {
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(coop_sort_multi2_kernel), dim3(grid), dim3(kM2Threads),
+                                        args, kM2DynSmem, st);
+        if (launches) ++*launches;
+        return e;
+    }
     e = cudaFuncSetAttribute(multi ? coop_sort_kernel<true> : coop_sort_kernel<false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCoopDynSmem));
     if (e != cudaSuccess) return e;
-    void *args[] = {&a};
     const void *fn = multi ? reinterpret_cast<const void *>(coop_sort_kernel<true>)
                            : reinterpret_cast<const void *>(coop_sort_kernel<false>);
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopThreads), args, kCoopDynSmem, st);
@@ -961,7 +1219,7 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec,
     return e;
 }
 
-const uint32_t *coop_sort_selector(const SortWorkspace &ws, int num_sms) { return ws.coop + size_t(num_sms) * 256; }
+const uint32_t *coop_sort_selector(const SortWorkspace &ws, int num_sms) { return ws.coop + coop_rows(num_sms) * 256; }
 
 cudaError_t launch_gather_results(const uint32_t *perm_a, const uint32_t *perm_b, const uint32_t *d_sel, int64_t n,
                                   int64_t row_base, const SurvivorRec *rec, const double *r_p, const ResultSoA &o,
