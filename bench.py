@@ -519,6 +519,11 @@ def main() -> int:
     dev = torch.device("cuda", local_rank)
 
     def barrier():
+        # synchronise FIRST: dist.barrier() launches its NCCL kernel behind torch's current stream only, not behind the
+        # stream the library runs on; a rank that had finished enqueuing would start the barrier kernel while its last
+        # steps were still queued, and that kernel (spinning until every rank joins) keeps the cooperative sort from
+        # getting all its CTAs resident -- the ranks then wait for one another (seen once at N = 8: +0.6 ms per window)
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
