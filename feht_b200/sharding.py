@@ -103,7 +103,7 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
                                 host_out: dict | None = None, want_device: bool = False, times: dict | None = None):
     """The same exchange for EVERY comparison at once (one process per GPU): each rank hands over the ordered rows of
     all its comparisons (feht_result_fetch_device with comparison = -1: eight device-to-device copies into one packed
-    buffer), ONE `all_gather_into_tensor` moves them over NVLink, and ONE call of feht_merge_shards_device (K5b) merges all
+    buffer), ONE `dist.gather` moves them over NVLink to `dst`, and ONE call of feht_merge_shards_device (K5b) merges all
     comparisons and scatters all columns.  Returns (columns, seg_off) on `dst` -- host tensors (into `host_out` when
     given; device tensors with want_device) and the merged per-comparison offsets -- and (None, None) elsewhere."""
     import torch
@@ -143,8 +143,18 @@ def gather_and_merge_all_device(ctx, sort_key: int = capi.SORT_ABS_RATIO_DESC, d
     if sizes[rank]:
         ctx.fetch_device(-1, {k: pack.data_ptr() + offs[k] for k in DEV_DTYPES})
     lap("sizes_and_local_copy_ms")
-    everything = torch.empty(world * o, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(everything, pack)
+    # ONE gather of the packed buffers to `dst` (grouped send / recv: the root's NVLink ingress is the bound, 7 x 110 MB
+    # for 20M rows on 8 GPUs).  An all-gather of the same buffers delivers every shard to every rank and took 2.9 ms
+    # there; FEHT_EXCHANGE=allgather keeps it for comparison.
+    import os
+    if os.environ.get("FEHT_EXCHANGE") == "allgather":
+        everything = torch.empty(world * o, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everything, pack)
+    elif rank == dst:
+        everything = torch.empty(world * o, dtype=torch.uint8, device=dev)
+        dist.gather(pack, [everything[s * o:(s + 1) * o] for s in range(world)], dst=dst)
+    else:
+        dist.gather(pack, None, dst=dst)
     lap("nccl_gather_ms")
     if rank != dst:
         return None, None
