@@ -222,6 +222,7 @@ struct CoopArgs {
     uint32_t *sel;              // out: which val buffer holds the permutation
     uint32_t tag_base;          // 32 * launch number: tags of different launches never coincide
     uint32_t *bar;              // grid barrier counter between passes, zeroed before the launch
+    uint32_t *flags;            // [grid] (two-CTAs-per-SM variant): pass number whose counts the CTA has published, zeroed
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
@@ -546,8 +547,10 @@ __global__ void __launch_bounds__(kM2Threads, 2) coop_sort_multi2_kernel(const _
     }
     int cur = 0;
     unsigned target = 0;
+    uint32_t pass_no = 0;
 
     while (todo) {
+        ++pass_no;
         const int cand = __ffs(todo) - 1;
         todo &= todo - 1;
         const int src = (cand >= 4 && cand < 12) ? 0 : 1;
@@ -591,7 +594,14 @@ __global__ void __launch_bounds__(kM2Threads, 2) coop_sort_multi2_kernel(const _
             for (int ww = 0; ww < kM2Warps; ++ww) run += cnt[ww][tid];
             A.hist[size_t(cta) * 256 + tid] = run;
         }
-        grid_barrier(A.bar, target);
+        // No grid barrier here: the counts are published with a flag (release), and nothing needs the other CTAs'
+        // counts before the first chunk has been ranked and staged -- the wait for the slowest sweep hides behind that
+        // work (ncu r3p: 19% of the samples sat in the two grid barriers of a pass).
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.flags + cta), "r"(pass_no) : "memory");
+        }
 
         // a chunk's keys and indices are loaded while the previous chunk is written out (k / v are free once the chunk
         // is staged): ncu r3o had 7% of the samples on the first use of these loads
@@ -675,8 +685,11 @@ __global__ void __launch_bounds__(kM2Threads, 2) coop_sort_multi2_kernel(const _
             __syncthreads();
             if (ch + 1 < n_chunks) load_chunk(ch + 1);
             if (ch == 0) {
-                // counts of every digit in the CTAs before me and in all CTAs (plain counts, published before the grid
-                // barrier): thread = 4 digits x one of 8 slices of the CTA list, eight 128-bit loads in flight
+                for (int c = tid; c < G; c += kM2Threads)
+                    while (ld_acquire_u32(A.flags + c) != pass_no) {}
+                __syncthreads();
+                // counts of every digit in the CTAs before me and in all CTAs (plain counts, published with the flag
+                // above): thread = 4 digits x one of 8 slices of the CTA list, eight 128-bit loads in flight
                 const int q = tid & 63, grp = tid >> 6;
                 uint4 before = make_uint4(0, 0, 0, 0), total = make_uint4(0, 0, 0, 0);
                 const uint4 *h4 = reinterpret_cast<const uint4 *>(A.hist);
@@ -1124,7 +1137,7 @@ int64_t coop_sort_capacity(int num_sms) { return int64_t(num_sms) * kCoopCap; }
 int coop_sort_max_grid() { return 160; }   // kSlice * 16 in the kernel
 // rows of the [grid][256] count table: the two-CTAs-per-SM multi-chunk kernel runs 2 * num_sms CTAs
 static size_t coop_rows(int num_sms) { return size_t(2) * size_t(num_sms); }
-size_t coop_sort_control_words(int num_sms) { return coop_rows(num_sms) * 256 + 8; }
+size_t coop_sort_control_words(int num_sms) { return coop_rows(num_sms) * 256 + 8 + coop_rows(num_sms); }
 
 static bool sort_multi_two_ctas() {
     static const bool on = [] { const char *e = getenv("FEHT_SORT_MULTI"); return !(e && strcmp(e, "1024") == 0); }();
@@ -1204,6 +1217,9 @@ cudaError_t coop_sort_perm(SortWorkspace &ws, int64_t n, const SurvivorRec *rec,
     // may drive several GPUs)
     void *args[] = {&a};
     if (two) {
+        a.flags = sel + 8;
+        e = cudaMemsetAsync(a.flags, 0, coop_rows(num_sms) * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
         e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(coop_sort_multi2_kernel), dim3(grid), dim3(kM2Threads),
                                         args, kM2DynSmem, st);
         if (launches) ++*launches;
