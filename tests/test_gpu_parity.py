@@ -1062,7 +1062,7 @@ def test_run_async_back_to_back_equals_blocking_run(ctx):
 
 
 def test_sort_engines_agree(cuda_lib):
-    """K4 has two engines: one cooperative launch (up to 8192 survivors per SM) and one kernel per pass
+    """K4 has two engines: one cooperative launch (one chunk per SM, or several chunks per CTA) and one kernel per pass
     (tile per CTA, look-back).  FEHT_SORT=onesweep forces the second at any size (read once per process,
     hence the subprocesses); both must give the oracle's order on many comparisons, filtered output (name-rank
     passes) and the p-value key."""
@@ -1073,7 +1073,7 @@ def test_sort_engines_agree(cuda_lib):
         import oracle, hashlib
         from feht_b200 import capi
         rng = np.random.default_rng(31)
-        S, R = 240, 30000
+        S, R = 240, 70000        # 21 comparisons x 70k rows = 1.47M dense results: past one chunk per SM
         f = rng.beta(0.4, 0.4, size=(R, 1))
         cells = np.where(rng.random((R, S)) < f, ord('1'), ord('0')).astype(np.uint8)
         cells[rng.random((R, S)) < 0.03] = ord('-')
@@ -1096,12 +1096,15 @@ def test_sort_engines_agree(cuda_lib):
         print(h.hexdigest())
     """) % (str(ROOT_DIR), str(ROOT_DIR / "tests"))
     digests = {}
-    for eng in ("coop", "onesweep"):
-        env = dict(os.environ, FEHT_SORT=eng)
+    # the cooperative engine's multi-chunk kernel comes in two shapes (two 512-thread CTAs per SM; FEHT_SORT_MULTI=1024:
+    # one 1024-thread CTA per SM)
+    for name, eng, multi in (("coop", "coop", ""), ("coop1024", "coop", "1024"), ("onesweep", "onesweep", "")):
+        env = dict(os.environ, FEHT_SORT=eng, FEHT_SORT_MULTI=multi)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        digests[eng] = r.stdout.strip().split()[-1]
+        digests[name] = r.stdout.strip().split()[-1]
     assert digests["coop"] == digests["onesweep"]
+    assert digests["coop1024"] == digests["onesweep"]
 
 
 def test_host_transcoder_planes_equal_gpu_pack(cuda_lib):
